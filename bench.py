@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the message-passing hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (N = 1): BASELINE.json configs[3] ("C4") - 3-layer SAGEConv mean-aggregation on an
+ogbn-products-shaped synthetic graph (2,449,029 nodes, 61,859,140 directed edges, 100 input
+features, 256/256/47 outputs), generated on the device with a seeded RMAT sampler.
+A "step" is one full forward + backward + SGD update of that model through the package's public
+layers (every aggregation is a kgb_gather_reduce launch).  metric = aggregated edges per second
+per layer, forward + backward:  value = n_layers * E / t_step  (GTEPS).
+
+For N > 1 the same model runs on a graph N times larger (weak scaling), 1-D node-partitioned
+across the ranks with a halo exchange before every aggregation (keras_geometric_b200.dist).
+
+`--impl reference` times the CPU restatement of the reference's path (oracle/, "port") on the
+box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C4 = dict(nodes=2_449_029, edges=61_859_140, feats=100, hidden=256, classes=47, rmat_scale=22)
+RMAT = (0.57, 0.19, 0.19, 0.05)
+
+
+# ------------------------------------------------------------------------------------------ data
+def rmat_edge_index(n_nodes: int, n_edges: int, scale: int, seed: int, device) -> torch.Tensor:
+    """Symmetrised RMAT graph, duplicates kept: n_edges/2 sampled pairs, both directions.
+    int32 [2, n_edges] with row 0 = source, row 1 = target."""
+    half = n_edges // 2
+    gen = torch.Generator(device=device).manual_seed(seed)
+    a, b, c, _ = RMAT
+    src = torch.zeros(half, dtype=torch.int32, device=device)
+    dst = torch.zeros(half, dtype=torch.int32, device=device)
+    for _level in range(scale):
+        r = torch.rand(half, device=device, generator=gen)
+        sbit = (r >= a + b).to(torch.int32)
+        dbit = (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int32)
+        src = src * 2 + sbit
+        dst = dst * 2 + dbit
+    src = torch.remainder(src, n_nodes)
+    dst = torch.remainder(dst, n_nodes)
+    ei = torch.empty((2, 2 * half), dtype=torch.int32, device=device)
+    ei[0, :half], ei[0, half:] = src, dst
+    ei[1, :half], ei[1, half:] = dst, src
+    return ei
+
+
+def gather_bytes(nnz: int, n_rows: int, F: int, extra_edge: int = 0, extra_row: int = 0) -> int:
+    """Algorithmic bytes of one gather-reduce launch (SURVEY 8(d) / DESIGN.md):
+    nnz*(4F + 4 col [+4 per-edge weight or scale]) + n_rows*4F written + (n_rows+1)*8 rowptr."""
+    return nnz * (4 * F + 4 + extra_edge) + n_rows * (4 * F + extra_row) + (n_rows + 1) * 8
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------- our arm
+def build_model(feats, hidden, classes, seed=0):
+    from keras_geometric_b200 import SAGEConv
+    torch.manual_seed(seed)
+    layers = [SAGEConv(hidden, aggregator="mean"), SAGEConv(hidden, aggregator="mean"),
+              SAGEConv(classes, aggregator="mean")]
+    dims = [feats, hidden, hidden]
+    for lyr, d in zip(layers, dims):
+        lyr.build([(None, d), (2, None)])
+        lyr.built = True
+    return layers
+
+
+def run_ours(args):
+    import keras_geometric_b200  # noqa: F401
+    from keras_geometric_b200 import _lib, ops
+    from keras_geometric_b200.graph import clear_cache, get_graph
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import bench_dist  # multi-GPU path lives beside this file
+        return bench_dist.run(args, world, rank, local_rank)
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    cfg = dict(C4)
+    if args.scale_div > 1:  # debugging aid only; the reported workload is scale_div == 1
+        cfg["nodes"] //= args.scale_div
+        cfg["edges"] = cfg["edges"] // args.scale_div // 2 * 2
+        cfg["rmat_scale"] = max(8, cfg["rmat_scale"] - (args.scale_div.bit_length() - 1))
+    n, e = cfg["nodes"], cfg["edges"]
+    ei = rmat_edge_index(n, e, cfg["rmat_scale"], 0, dev)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn((n, cfg["feats"]), device=dev, generator=gen)
+    y = torch.randint(0, cfg["classes"], (n,), device=dev, generator=gen)
+    layers = build_model(cfg["feats"], cfg["hidden"], cfg["classes"])
+    params = [p for lyr in layers for p in lyr.trainable_weights]
+    opt = torch.optim.SGD(params, lr=1e-3)
+
+    def step(x_in, ei_in):
+        opt.zero_grad(set_to_none=True)
+        h = x_in
+        for lyr in layers:
+            h = lyr([h, ei_in])
+        loss = torch.nn.functional.cross_entropy(h, y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    # ---- device-resident timing (value) -------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(x, ei)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ops.PROFILE = []
+    l0 = lib.kgb_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(args.steps):
+        loss = step(x, ei)
+    t1.record()
+    torch.cuda.synchronize()
+    launches = lib.kgb_launch_count() - l0
+    prof, ops.PROFILE = ops.PROFILE, None
+    clocks = sampler.stop()
+    ms_step = t0.elapsed_time(t1) / args.steps
+    n_layers = len(layers)
+    value = n_layers * e / (ms_step * 1e-3) / 1e9
+
+    # ---- per-kernel roofline from the in-step CUDA events ---------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    groups = {}
+    for rec in prof:
+        ms = rec["start"].elapsed_time(rec["end"])
+        g = groups.setdefault(rec["label"], {"ms": 0.0, "bytes": 0, "n": 0})
+        g["ms"] += ms
+        g["bytes"] += rec["bytes"]
+        g["n"] += 1
+    kernels = {k: {"launches": v["n"], "ms_per_launch": v["ms"] / v["n"], "GBps": v["bytes"] / v["ms"] / 1e6,
+                   "frac": v["bytes"] / v["ms"] / 1e6 / peak, "share_of_step": v["ms"] / (ms_step * args.steps)}
+               for k, v in groups.items()}
+    dom = max(groups, key=lambda k: groups[k]["ms"]) if groups else None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "ms_per_launch": kernels[dom]["ms_per_launch"], "share_of_step": kernels[dom]["share_of_step"]}
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            roofline["traffic"] = json.load(open(tr)).get(dom)
+
+    # ---- end-to-end through the public API with host buffers ----------------------------------------
+    x_host = x.cpu().pin_memory()
+    ei_host = ei.cpu().pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        clear_cache()  # a fresh edge list arrives every step: the CSR/CSC build is inside the timed region
+        xd = x_host.to(dev, non_blocking=True)
+        eid = ei_host.to(dev, non_blocking=True)
+        return float(step(xd, eid).item())  # device -> host read of the loss
+
+    e2e_step()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - w0) * 1e3 / e2e_steps
+    e2e = {"value": n_layers * e / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": x_host.numel() * 4 + ei_host.numel() * 4, "d2h_bytes_per_step": 4,
+           "includes": "H2D of x and edge_index from pinned memory, CSR+CSC build, fwd+bwd+SGD, loss readback"}
+
+    out = {
+        "metric": "aggregated edges/sec per layer fwd+bwd", "value": value, "unit": "GTEPS", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4: 3-layer SAGEConv(mean) 100->256->256->47 on products-shaped RMAT graph",
+                   "nodes": n, "edges": e, "layers": n_layers, "rmat": list(RMAT), "seed": 0,
+                   "l2": "inputs (x 0.98 GB, activations 2.5 GB) exceed the 126 MB L2; no flush needed",
+                   "step": "forward + backward + SGD update, cross-entropy over all nodes"},
+        "roofline": roofline, "kernels": kernels, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
+        "loss": float(loss.item()),
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(sample_div=args.cpu_sample_div, steps=1, warmup=0)
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------- reference arm
+def cpu_reference_step_factory(sample_div: int):
+    """3-layer SAGE-mean fwd+bwd+SGD with the oracle's restatement of the reference path (host)."""
+    from oracle import reference_path as ref
+    cfg = dict(C4)
+    n = cfg["nodes"] // sample_div
+    e = cfg["edges"] // sample_div // 2 * 2
+    scale = max(8, cfg["rmat_scale"] - (sample_div.bit_length() - 1))
+    ei = rmat_edge_index(n, e, scale, 0, torch.device("cpu"))
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn((n, cfg["feats"]), generator=gen)
+    y = torch.randint(0, cfg["classes"], (n,), generator=gen)
+    dims = [cfg["feats"], cfg["hidden"], cfg["hidden"], cfg["classes"]]
+    torch.manual_seed(0)
+    ws = []
+    for i in range(3):
+        lim = (6.0 / (dims[i] + dims[i + 1])) ** 0.5
+        ws.append([((torch.rand(dims[i], dims[i + 1]) * 2 - 1) * lim).requires_grad_(True),
+                   ((torch.rand(dims[i], dims[i + 1]) * 2 - 1) * lim).requires_grad_(True),
+                   torch.zeros(dims[i + 1], requires_grad=True)])
+    opt = torch.optim.SGD([p for w in ws for p in w], lr=1e-3)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        h = x
+        for wn, wsf, b in ws:
+            h = ref.sage_conv(h, ei, wn, wsf, b, "mean", torch.relu, False)
+        loss = torch.nn.functional.cross_entropy(h, y)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return step, n, e
+
+
+def cpu_baseline(sample_div: int, steps: int, warmup: int):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, n, e = cpu_reference_step_factory(sample_div)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": 3 * e / dt / 1e9, "unit": "GTEPS", "cores": cores, "kind": "port",
+            "sample": f"same 3-layer SAGE-mean step on a 1/{sample_div} RMAT sample ({n} nodes, {e} edges), "
+                      f"torch CPU, {torch.get_num_threads()} threads, {dt:.2f} s/step",
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(sample_div=args.cpu_sample_div * 2, steps=args.steps, warmup=args.warmup)
+    print(json.dumps({
+        "impl": "reference", "metric": "aggregated edges/sec per layer fwd+bwd", "value": cb["value"],
+        "unit": "GTEPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4: 3-layer SAGEConv(mean) 100->256->256->47 on products-shaped RMAT graph",
+                   "sample": cb["sample"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference (pure Python over keras.ops) cannot be imported without Keras; this is the "
+                "oracle's restatement of its path (oracle/reference_path.py) on the host cores",
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale-div", type=int, default=1, help="debug: shrink the workload by this factor")
+    ap.add_argument("--cpu-sample-div", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,207 @@
+/* kgb200.h - C ABI of libkgb200.so: the B200 (sm_100a) message-passing hot path behind
+ * keras-geometric's MessagePassing / GCNConv / GINConv / SAGEConv / GATv2Conv API.
+ *
+ * The reference (/root/reference, pure Python over keras.ops) has no FFI; the entry points
+ * below are what a native plugin for its hot path binds.  Each one cites the reference code
+ * it replaces (paths relative to /root/reference/src/keras_geometric/).
+ *
+ * Conventions
+ *  - every function returns 0 (KGB_OK) or a negative KGB_ERR_* code; kgb_last_error() returns a
+ *    thread-local message.  Nothing throws, allocates user-visible memory or synchronises.
+ *  - every pointer is a BORROWED DEVICE pointer owned by the caller (outputs and workspaces
+ *    included) unless its name ends in _host.  `device` is the CUDA ordinal the pointers live
+ *    on, `stream` the cudaStream_t to launch on (0 = legacy default stream).
+ *  - indices are int32, row pointers int64, data float32, row-major, leading dimension in
+ *    elements.  Edge lists use the reference's COO convention: row 0 = source j,
+ *    row 1 = target i; aggregation is segmented by target (layers/message_passing.py:191-212).
+ */
+#ifndef KGB200_H
+#define KGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* kgb_stream_t; /* cudaStream_t */
+
+enum {
+  KGB_OK = 0,
+  KGB_ERR_INVALID = -1,     /* bad argument */
+  KGB_ERR_CUDA = -2,        /* a CUDA runtime call / launch failed */
+  KGB_ERR_WORKSPACE = -3,   /* workspace too small */
+  KGB_ERR_UNSUPPORTED = -4  /* shape outside the compiled kernel set */
+};
+
+enum { KGB_OP_SUM = 0, KGB_OP_MEAN = 1, KGB_OP_MAX = 2, KGB_OP_MIN = 3 };
+enum { KGB_ACT_NONE = 0, KGB_ACT_RELU = 1 };
+
+/* status bits written by kgb_csr_build into *status (device int32) */
+enum { KGB_STATUS_OOB_INDEX = 1 };
+
+int kgb_version(void);
+const char* kgb_last_error(void);
+/* number of kernels this library has launched in the process so far (all threads) */
+int64_t kgb_launch_count(void);
+/* SM count, compute capability and L2 size of `device` (host-side query, cached). */
+int kgb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  COO -> CSR grouping (stable), degrees, optional appended self-loops.
+ * Replaces: utils/main.py:8-16 (add_self_loops), the implicit per-target grouping inside
+ * keras.ops.segment_sum/segment_max (aggregators.py:67-72,108,135), and the ones->segment_sum
+ * degree count (utils/main.py:23-24, aggregators.py:66-69).
+ *
+ * Edges e in [0,E) come from edge_index (int32 [2,E], row 0 = src, row 1 = dst); edges
+ * e in [E, E+n_loops) are the self-loops (e-E)->(e-E), appended last exactly like the
+ * reference.  by_source = 0 groups by target (CSR used by the forward), 1 groups by source
+ * (the transposed structure used by the backward).  Inside a segment edges keep their
+ * original order (what a sequential scatter on the CPU visits), so
+ *   perm   = argsort(key, stable)           int32 [E+n_loops]
+ *   col    = other_endpoint[perm]           int32 [E+n_loops]
+ *   deg    = bincount(key, n_seg)           int32 [n_seg]
+ *   rowptr = exclusive_cumsum(deg)          int64 [n_seg+1]
+ * bit-exactly.  Indices outside [0,n_seg) / [0,n_val) set KGB_STATUS_OOB_INDEX in *status
+ * (the edge is clamped to 0 so nothing faults); the caller decides when to read status.
+ * ------------------------------------------------------------------------------------- */
+size_t kgb_csr_build_workspace_bytes(int64_t n_edges_total, int64_t n_seg);
+int kgb_csr_build(int device, const int32_t* edge_index, int64_t E, int by_source,
+                  int64_t n_seg, int64_t n_val, int64_t n_loops,
+                  int64_t* rowptr, int32_t* col, int32_t* perm, int32_t* deg, int32_t* status,
+                  void* ws, size_t ws_bytes, kgb_stream_t stream);
+
+/* Hub table for load balance: every row with more than `threshold` edges is cut into chunks of
+ * `chunk` edges that are reduced independently and merged in chunk order (deterministic).
+ * counts[0] = n_hubs, counts[1] = n_chunks (device int32[2], zeroed by this call).
+ * Capacities: hub_* arrays hold max_hubs entries, chunk_hub holds max_chunks entries, where
+ * max_hubs = n_edges/threshold + 1 and max_chunks = n_edges/chunk + max_hubs + 1. */
+int kgb_csr_hubs(int device, const int64_t* rowptr, int64_t n_seg, int32_t threshold, int32_t chunk,
+                 int32_t* hub_row, int32_t* hub_chunk_base, int32_t* hub_nchunks, int32_t* chunk_hub,
+                 int64_t max_hubs, int64_t max_chunks, int32_t* counts, kgb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2  GCN symmetric normalisation.  Replaces utils/main.py:20-33.
+ *   dis[i] = (float(deg[i]) + 1e-12)^-0.5   (IEEE 1/sqrt, == torch.pow(.,-0.5) on the host)
+ *   w[e]   = dis[dst[e]] * dis[src[e]]      for e in COO order incl. the n_loops self-loops
+ * deg is the in-degree over targets including self-loops (from kgb_csr_build, by_source=0).
+ * `w` may be NULL (only dis wanted).
+ * ------------------------------------------------------------------------------------- */
+int kgb_gcn_norm(int device, const int32_t* deg, int64_t n_nodes, const int32_t* edge_index,
+                 int64_t E, int64_t n_loops, float* dis, float* w, kgb_stream_t stream);
+/* out[k] = in[perm[k]]  (bring COO-ordered edge weights into CSR / CSC slot order) */
+int kgb_permute_f32(int device, const float* in, const int32_t* perm, int64_t n, float* out,
+                    kgb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3/K4/K5/K9  destination-segmented gather-reduce (deterministic, no atomics).
+ * Replaces: ops.take + Sum/Mean/Max/MinAggregator.aggregate (layers/message_passing.py:195-212,
+ * layers/aggregators.py:56-167), the weighted GCN message (layers/gcn_conv.py:233-246) and its
+ * bias update (:266-272).  With col = perm and x = messages it is the generic
+ * Aggregator.aggregate(messages, target_idx, dim_size) (aggregators.py:24-39); over the
+ * by_source structure it is the backward of sum/mean.
+ *
+ *   r        = row_ids ? row_ids[s] : s                      for slot s in [0, n_rows)
+ *   red[s,:] = OP_{k in [rowptr[s], rowptr[s+1])}  edge_w[k] * src_scale[col[k]] * x[col[k], :]
+ *   MEAN     : red / max(float(deg), 1e-8)                   (aggregators.py:77-81)
+ *   MAX/MIN  : empty segment or +-inf result -> 0            (aggregators.py:108-112,162-167)
+ *   out[r,:] = act( out_scale[s] * red + addend_scale * addend[r,:] + bias )
+ * edge_w, src_scale, out_scale, addend, bias, row_ids, arg are optional (NULL).
+ * MAX/MIN additionally write arg[r,f]: the source row id of the unique extremum, -1 when the
+ * gradient is zero (empty / inf / nan), -2 when several edges tie (backward re-walks the row).
+ * hub_* / partial: optional hub table from kgb_csr_hubs plus a float workspace of
+ * kgb_gather_reduce_partial_bytes(); when absent every row is reduced by one lane group.
+ * ------------------------------------------------------------------------------------- */
+typedef struct kgb_gather_reduce_args {
+  const float* x;          /* [n_src_rows, F] gathered matrix                  */
+  int64_t ldx;
+  int64_t n_src_rows;
+  int32_t F;
+  int32_t op;              /* KGB_OP_*                                          */
+  const int64_t* rowptr;   /* [n_rows+1]                                        */
+  const int32_t* col;      /* [nnz] row ids into x                              */
+  int64_t n_rows;
+  const int32_t* row_ids;  /* optional [n_rows] output row of each CSR row      */
+  const float* edge_w;     /* optional [nnz] per-slot weight                    */
+  const float* src_scale;  /* optional [n_src_rows] per-gathered-row factor     */
+  const float* out_scale;  /* optional [n_rows] per-output-row factor           */
+  const float* addend;     /* optional [*, F] added after the reduction         */
+  int64_t ld_addend;
+  float addend_scale;
+  const float* bias;       /* optional [F]                                      */
+  int32_t act;             /* KGB_ACT_*                                         */
+  float* out;              /* [*, F]                                            */
+  int64_t ldo;
+  int32_t* arg;            /* optional [*, F] (MAX/MIN only), same ld as out    */
+  /* hub table (all NULL/0 when unused) */
+  const int32_t* hub_row;
+  const int32_t* hub_chunk_base;
+  const int32_t* hub_nchunks;
+  const int32_t* chunk_hub;
+  int32_t n_hubs;
+  int32_t n_chunks;
+  int32_t hub_threshold;
+  int32_t hub_chunk;
+  float* partial;          /* workspace, kgb_gather_reduce_partial_bytes()      */
+} kgb_gather_reduce_args;
+
+size_t kgb_gather_reduce_partial_bytes(int32_t n_chunks, int32_t F, int32_t op);
+int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t stream);
+
+/* Backward of MAX/MIN (torch.scatter_reduce(amax) semantics: the gradient is split evenly
+ * between tied maxima).  gx must be zero-initialised by the caller; accumulates
+ *   gx[arg[r,f], f] += g[r,f]                       (unique extremum)
+ *   gx[col[k],  f] += g[r,f] / n_ties               for every tied edge (arg == -2)
+ * `out` is the forward result, x the forward input.  Same CSR as the forward. */
+int kgb_gather_max_bwd(int device, const float* g, int64_t ldg, const int32_t* arg,
+                       const float* out, int64_t ldo, const float* x, int64_t ldx,
+                       const int64_t* rowptr, const int32_t* col, const int32_t* row_ids,
+                       int64_t n_rows, int32_t F, int32_t op, float* gx, int64_t ldgx,
+                       kgb_stream_t stream);
+
+/* out[r,:] = scale * src[idx[r],:]   (row gather: backward of the generic segment-sum w.r.t.
+ * materialised messages, and the halo "pack" step of the partitioned path). idx may be NULL
+ * (identity). */
+int kgb_gather_rows(int device, const float* src, int64_t lds, const int32_t* idx, int64_t n_out,
+                    int32_t F, float scale, float* out, int64_t ldo, kgb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K6  fused GATv2 edge kernel.  Replaces layers/gatv2_conv.py:241-264 (_gatv2_propagate edge
+ * part), :268-289 (_compute_attention), :291-311 (_softmax_by_target), :313-335
+ * (_aggregate_messages) and the bias add of :337-352.
+ *   s[k,h]   = sum_c att[h,c] * leaky_relu(hdst[i,h,c] + hsrc[col[k],h,c], slope)
+ *   alpha    = exp(s - max_i) / (sum_i exp(s - max_i) + 1e-10)     per target i and head h
+ *   out[i,h,:] = sum_k alpha[k,h] * hsrc[col[k],h,:]  (+ bias[h*C+c] when bias != NULL)
+ * One pass over the CSR with an online max/sum; rowmax/rowden ([n_dst,H]) are saved for the
+ * backward, which recomputes alpha instead of storing [nnz,H] tensors.
+ * ------------------------------------------------------------------------------------- */
+int kgb_gatv2_fwd(int device, const float* hsrc, const float* hdst, int64_t n_src, int64_t n_dst,
+                  int32_t H, int32_t C, const float* att, float slope,
+                  const int64_t* rowptr, const int32_t* col, const float* bias,
+                  float* out, float* rowmax, float* rowden, kgb_stream_t stream);
+/* Backward, pass 1 over the forward CSR (per target): g_hdst[i] (written), r[i,h] =
+ * sum_c g[i,h,c] * agg[i,h,c] (written, workspace [n_dst,H]) and the attention-vector
+ * gradient partials g_att_part [n_parts, H*C] (n_parts from kgb_gatv2_bwd_parts()).
+ * `agg` is the forward output WITHOUT bias. */
+int kgb_gatv2_bwd_parts(int device, int64_t n_dst, int32_t H, int32_t C);
+int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float* hsrc,
+                      const float* hdst, int64_t n_src, int64_t n_dst, int32_t H, int32_t C,
+                      const float* att, float slope, const int64_t* rowptr, const int32_t* col,
+                      const float* rowmax, const float* rowden,
+                      float* g_hdst, float* r, float* g_att_part, int32_t n_parts,
+                      kgb_stream_t stream);
+/* Backward, pass 2 over the transposed structure (per source): g_hsrc[j] (written). */
+int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float* hdst,
+                      int64_t n_src, int64_t n_dst, int32_t H, int32_t C, const float* att,
+                      float slope, const int64_t* colptr, const int32_t* row,
+                      const float* rowmax, const float* rowden, const float* r,
+                      float* g_hsrc, kgb_stream_t stream);
+/* out[f] = sum_p part[p,f]  in fixed order (deterministic reduction of partials). */
+int kgb_reduce_parts(int device, const float* part, int32_t n_parts, int32_t F, float* out,
+                     kgb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGB200_H */

@@ -1,0 +1,112 @@
+"""ctypes binding of libkgb200.so (the C ABI declared in include/kgb200.h).
+
+There is no CPU fallback: if the shared library cannot be loaded (or built with nvcc) every
+entry point raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+from . import _build
+
+OP_SUM, OP_MEAN, OP_MAX, OP_MIN = 0, 1, 2, 3
+OPS = {"sum": OP_SUM, "mean": OP_MEAN, "max": OP_MAX, "min": OP_MIN}
+ACT_NONE, ACT_RELU = 0, 1
+STATUS_OOB_INDEX = 1
+
+
+class KgbError(RuntimeError):
+    pass
+
+
+class GatherReduceArgs(Structure):
+    """Mirror of ``struct kgb_gather_reduce_args`` (include/kgb200.h)."""
+
+    _fields_ = [
+        ("x", c_void_p), ("ldx", c_int64), ("n_src_rows", c_int64), ("F", c_int32), ("op", c_int32),
+        ("rowptr", c_void_p), ("col", c_void_p), ("n_rows", c_int64), ("row_ids", c_void_p),
+        ("edge_w", c_void_p), ("src_scale", c_void_p), ("out_scale", c_void_p),
+        ("addend", c_void_p), ("ld_addend", c_int64), ("addend_scale", c_float),
+        ("bias", c_void_p), ("act", c_int32), ("out", c_void_p), ("ldo", c_int64), ("arg", c_void_p),
+        ("hub_row", c_void_p), ("hub_chunk_base", c_void_p), ("hub_nchunks", c_void_p),
+        ("chunk_hub", c_void_p), ("n_hubs", c_int32), ("n_chunks", c_int32),
+        ("hub_threshold", c_int32), ("hub_chunk", c_int32), ("partial", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every name declared in include/kgb200.h must appear here
+SIGNATURES = {
+    "kgb_version": (c_int, []),
+    "kgb_last_error": (c_char_p, []),
+    "kgb_launch_count": (c_int64, []),
+    "kgb_device_info": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int64)]),
+    "kgb_csr_build_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "kgb_csr_build": (c_int, [c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kgb_csr_hubs": (c_int, [c_int, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_int64, c_int64, c_void_p, c_void_p]),
+    "kgb_gcn_norm": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "kgb_permute_f32": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "kgb_gather_reduce_partial_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "kgb_gather_reduce": (c_int, [c_int, POINTER(GatherReduceArgs), c_void_p]),
+    "kgb_gather_max_bwd": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                   c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64,
+                                   c_void_p]),
+    "kgb_gather_rows": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_float, c_void_p, c_int64,
+                                c_void_p]),
+    "kgb_gatv2_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_float,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kgb_gatv2_bwd_parts": (c_int, [c_int, c_int64, c_int32, c_int32]),
+    "kgb_gatv2_bwd_dst": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+                                  c_int32, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_int32, c_void_p]),
+    "kgb_gatv2_bwd_src": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
+                                  c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "kgb_reduce_parts": (c_int, [c_int, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Load libkgb200.so (building it with nvcc if it is missing or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB
+        if build_if_missing and not _build.is_fresh():
+            try:
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                if not os.path.exists(path):
+                    raise RuntimeError(
+                        "keras_geometric_b200: libkgb200.so is not built and could not be compiled "
+                        f"({e}). There is no CPU fallback for the message-passing hot path.") from e
+        if not os.path.exists(path):
+            raise RuntimeError("keras_geometric_b200: libkgb200.so not found; run "
+                               "`python -m keras_geometric_b200._build`. There is no CPU fallback.")
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().kgb_last_error()
+        raise KgbError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,606 @@
+// K3/K4/K5/K9: destination-segmented gather-reduce for sm_100a (HBM-bound).
+//
+// Work decomposition
+//   * a "lane group" of G = pow2ceil(F/VEC) <= 32 lanes owns one output row; each lane keeps
+//     NCH vectors (VEC floats, 128-bit loads when VEC = 4) of the row in registers;
+//   * the group loads G column indices (and weights) with one coalesced access, prefetches the
+//     next index batch, and broadcasts them with warp shuffles; U = min(G, 8) independent
+//     feature-row loads are in flight per lane before the first add (memory-level parallelism);
+//   * edges are accumulated in CSR order, i.e. the order a sequential scatter visits them -
+//     results are deterministic (no atomics) and, for unweighted sums of non-hub rows,
+//     identical to the host reference;
+//   * rows above `hub_threshold` edges are cut into chunks of `hub_chunk` edges (scheduled first,
+//     they are the long tasks), reduced into a partial buffer and merged in chunk order by
+//     hub_finish_kernel;
+//   * persistent grid-stride over tasks, grid = min(tasks, SMs * 8 CTAs).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace kgb {
+
+struct GRP {
+  const float* x; int64_t ldx;
+  int F;
+  const int64_t* rowptr; const int32_t* col; int64_t n_rows;
+  const int32_t* row_ids;
+  const float* edge_w; const float* src_scale; const float* out_scale;
+  const float* addend; int64_t ld_addend; float addend_scale;
+  const float* bias; int act; int mean; int negate;
+  float* out; int64_t ldo; int32_t* arg;
+  const int32_t* hub_row; const int32_t* hub_chunk_base; const int32_t* hub_nchunks;
+  const int32_t* chunk_hub;
+  int n_hubs; int n_chunks; int hub_threshold; int hub_chunk;
+  float* partial; int32_t* partial_arg;
+};
+
+template <int VEC, int G, int NCH, bool IS_MAX>
+__device__ __forceinline__ void init_acc(float (&acc)[NCH][VEC], int32_t (&aidx)[NCH][VEC]) {
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      acc[ch][e] = IS_MAX ? -INFINITY : 0.f;
+      aidx[ch][e] = -1;
+    }
+}
+
+template <bool IS_MAX>
+__device__ __forceinline__ void accum(float& m, int32_t& a, float v, float w, int32_t c, bool negate) {
+  if constexpr (IS_MAX) {
+    const float val = negate ? -v : v;
+    if (val != val) {
+      m = val;  // NaN propagates like torch's amax
+    } else if (val > m) {
+      m = val;
+      a = c;
+    } else if (val == m) {
+      a = -2;  // tie: backward re-walks the row
+    }
+  } else {
+    m = __fadd_rn(m, __fmul_rn(w, v));  // mul then add, like message*w followed by segment_sum
+  }
+}
+
+// Reduce CSR slots [k0, k1) of one row into acc (all lanes of the group call this together).
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
+__device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k1, int gl,
+                                             unsigned gmask, const bool (&on)[NCH],
+                                             float (&acc)[NCH][VEC], int32_t (&aidx)[NCH][VEC]) {
+  constexpr int U = (G < 8) ? G : 8;
+  constexpr bool HAS_W = HAS_EW || HAS_SS;
+  const bool negate = p.negate != 0;
+  int64_t k = k0;
+  int32_t myc = 0;
+  float myw = 1.f;
+  if (k + gl < k1) {
+    myc = __ldg(p.col + k + gl);
+    if constexpr (HAS_EW) myw = __ldg(p.edge_w + k + gl);
+    if constexpr (HAS_SS) myw = __fmul_rn(myw, __ldg(p.src_scale + myc));
+  }
+  while (k < k1) {
+    const int64_t rem = k1 - k;
+    const int cnt = rem < G ? (int)rem : G;
+    const int64_t kn = k + G;
+    int32_t nc = 0;
+    float nw = 1.f;
+    if (kn + gl < k1) {  // prefetch the next index batch while this one is consumed
+      nc = __ldg(p.col + kn + gl);
+      if constexpr (HAS_EW) nw = __ldg(p.edge_w + kn + gl);
+      if constexpr (HAS_SS) nw = __fmul_rn(nw, __ldg(p.src_scale + nc));
+    }
+    for (int j = 0; j < cnt; j += U) {
+      float v[U][NCH][VEC];
+      float w[U];
+      int32_t c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        c[u] = __shfl_sync(gmask, myc, j + u, G);
+        w[u] = 1.f;
+        if constexpr (HAS_W) w[u] = __shfl_sync(gmask, myw, j + u, G);
+        const bool ok = (j + u) < cnt;
+        const float* rp = p.x + (int64_t)c[u] * p.ldx;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          if (ok && on[ch]) {
+            ld_vec<VEC>(rp + (gl + ch * G) * VEC, v[u][ch]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[u][ch][e] = 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if ((j + u) < cnt) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) accum<IS_MAX>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
+        }
+      }
+    }
+    myc = nc;
+    myw = nw;
+    k = kn;
+  }
+}
+
+template <int VEC, int G, int NCH, bool IS_MAX>
+__device__ __forceinline__ void epilogue(const GRP& p, int64_t slot, int64_t deg, int gl,
+                                         const bool (&on)[NCH], float (&acc)[NCH][VEC],
+                                         int32_t (&aidx)[NCH][VEC]) {
+  const int64_t row_out = p.row_ids ? (int64_t)__ldg(p.row_ids + slot) : slot;
+  float os = 1.f;
+  if (p.out_scale) os = __ldg(p.out_scale + slot);
+  const float den = fmaxf((float)deg, 1e-8f);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (!on[ch]) continue;
+    const int f0 = (gl + ch * G) * VEC;
+    float r[VEC];
+    int32_t a[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      r[e] = acc[ch][e];
+      a[e] = aidx[ch][e];
+      if constexpr (IS_MAX) {
+        if (p.negate) r[e] = -r[e];
+        if (isinf(r[e])) { r[e] = 0.f; a[e] = -1; }  // empty segment, or a genuine +-inf (reference quirk)
+        if (r[e] != r[e]) a[e] = -1;
+      }
+      if (p.mean) r[e] = __fdiv_rn(r[e], den);
+      if (p.out_scale) r[e] = __fmul_rn(r[e], os);
+    }
+    if (p.addend) {
+      float ad[VEC];
+      ld_vec<VEC>(p.addend + row_out * p.ld_addend + f0, ad);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) r[e] = __fadd_rn(__fmul_rn(p.addend_scale, ad[e]), r[e]);
+    }
+    if (p.bias) {
+      float b[VEC];
+      ld_vec<VEC>(p.bias + f0, b);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) r[e] = __fadd_rn(r[e], b[e]);
+    }
+    if (p.act == KGB_ACT_RELU) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) r[e] = (r[e] <= 0.f) ? 0.f : r[e];  // keeps NaN like torch.relu
+    }
+    st_vec<VEC>(p.out + row_out * p.ldo + f0, r);
+    if constexpr (IS_MAX) {
+      if (p.arg) st_vec_i<VEC>(p.arg + row_out * p.ldo + f0, a);
+    }
+  }
+}
+
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
+__global__ void __launch_bounds__(256) gather_reduce_kernel(const GRP p) {
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int gw = lane / G;
+  const unsigned gmask = group_mask(lane, G);
+  const int nv = p.F / VEC;
+  bool on[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) on[ch] = (gl + ch * G) < nv;
+
+  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
+  const int64_t n_tasks = (int64_t)p.n_chunks + p.n_rows;
+  const int64_t stride = (int64_t)gridDim.x * gpb;
+  for (int64_t t = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; t < n_tasks; t += stride) {
+    float acc[NCH][VEC];
+    int32_t aidx[NCH][VEC];
+    init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
+    if (t < p.n_chunks) {
+      // one chunk of a hub row -> raw partial
+      const int h = __ldg(p.chunk_hub + t);
+      const int64_t row = __ldg(p.hub_row + h);
+      const int64_t ci = t - __ldg(p.hub_chunk_base + h);
+      const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
+      const int64_t k0 = rs + ci * p.hub_chunk;
+      const int64_t k1 = (k0 + p.hub_chunk < re) ? k0 + p.hub_chunk : re;
+      reduce_range<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, k0, k1, gl, gmask, on, acc, aidx);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        if (!on[ch]) continue;
+        const int f0 = (gl + ch * G) * VEC;
+        st_vec<VEC>(p.partial + t * (int64_t)p.F + f0, acc[ch]);
+        if constexpr (IS_MAX) st_vec_i<VEC>(p.partial_arg + t * (int64_t)p.F + f0, aidx[ch]);
+      }
+    } else {
+      const int64_t s = t - p.n_chunks;
+      const int64_t rs = __ldg(p.rowptr + s), re = __ldg(p.rowptr + s + 1);
+      if (p.n_hubs > 0 && (re - rs) > p.hub_threshold) continue;  // merged by hub_finish_kernel
+      reduce_range<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, rs, re, gl, gmask, on, acc, aidx);
+      epilogue<VEC, G, NCH, IS_MAX>(p, s, re - rs, gl, on, acc, aidx);
+    }
+  }
+}
+
+// Merge the chunk partials of every hub row in chunk order, then run the epilogue.
+template <int VEC, int G, int NCH, bool IS_MAX>
+__global__ void __launch_bounds__(256) hub_finish_kernel(const GRP p) {
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int gw = lane / G;
+  const int nv = p.F / VEC;
+  bool on[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) on[ch] = (gl + ch * G) < nv;
+  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
+  for (int64_t h = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; h < p.n_hubs;
+       h += (int64_t)gridDim.x * gpb) {
+    float acc[NCH][VEC];
+    int32_t aidx[NCH][VEC];
+    init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
+    const int64_t row = __ldg(p.hub_row + h);
+    const int64_t base = __ldg(p.hub_chunk_base + h);
+    const int nch = __ldg(p.hub_nchunks + h);
+    for (int c = 0; c < nch; ++c) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        if (!on[ch]) continue;
+        const int f0 = (gl + ch * G) * VEC;
+        float v[VEC];
+        ld_vec<VEC>(p.partial + (base + c) * (int64_t)p.F + f0, v);
+        if constexpr (IS_MAX) {
+          int32_t pa[VEC];
+          ld_vec_i<VEC>(p.partial_arg + (base + c) * (int64_t)p.F + f0, pa);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            float& m = acc[ch][e];
+            if (v[e] != v[e]) m = v[e];
+            else if (v[e] > m) { m = v[e]; aidx[ch][e] = pa[e]; }
+            else if (v[e] == m && pa[e] != -1) aidx[ch][e] = -2;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[ch][e] = __fadd_rn(acc[ch][e], v[e]);
+        }
+      }
+    }
+    const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
+    epilogue<VEC, G, NCH, IS_MAX>(p, row, re - rs, gl, on, acc, aidx);
+  }
+}
+
+// ---- backward of max/min -------------------------------------------------------------------
+template <int VEC, int G, int NCH>
+__global__ void __launch_bounds__(256)
+gather_max_bwd_kernel(const float* __restrict__ g, int64_t ldg, const int32_t* __restrict__ arg,
+                      const float* __restrict__ out, int64_t ldo, const float* __restrict__ x,
+                      int64_t ldx, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                      const int32_t* __restrict__ row_ids, int64_t n_rows, int F,
+                      float* __restrict__ gx, int64_t ldgx) {
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int gw = lane / G;
+  const unsigned gmask = group_mask(lane, G);
+  const int nv = F / VEC;
+  bool on[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) on[ch] = (gl + ch * G) < nv;
+  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
+  for (int64_t s = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; s < n_rows;
+       s += (int64_t)gridDim.x * gpb) {
+    const int64_t r = row_ids ? (int64_t)__ldg(row_ids + s) : s;
+    float gv[NCH][VEC];
+    int32_t a[NCH][VEC];
+    bool tie = false;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { gv[ch][e] = 0.f; a[ch][e] = -1; }
+      if (!on[ch]) continue;
+      const int f0 = (gl + ch * G) * VEC;
+      ld_vec<VEC>(g + r * ldg + f0, gv[ch]);
+      ld_vec_i<VEC>(arg + r * ldo + f0, a[ch]);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        if (a[ch][e] >= 0) atomicAdd(gx + (int64_t)a[ch][e] * ldgx + f0 + e, gv[ch][e]);
+        tie |= (a[ch][e] == -2);
+      }
+    }
+    if (__ballot_sync(gmask, tie) & gmask) {
+      // torch.scatter_reduce(amax) backward: split g evenly over every edge attaining the extremum
+      float o[NCH][VEC];
+      float cnt[NCH][VEC];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { o[ch][e] = 0.f; cnt[ch][e] = 0.f; }
+        if (on[ch]) ld_vec<VEC>(out + r * ldo + (gl + ch * G) * VEC, o[ch]);
+      }
+      const int64_t rs = __ldg(rowptr + s), re = __ldg(rowptr + s + 1);
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int64_t k = rs; k < re; ++k) {
+          const int64_t c = __ldg(col + k);
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            if (!on[ch]) continue;
+            const int f0 = (gl + ch * G) * VEC;
+            float v[VEC];
+            ld_vec<VEC>(x + c * ldx + f0, v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+              if (a[ch][e] == -2 && v[e] == o[ch][e]) {
+                if (pass == 0) cnt[ch][e] += 1.f;
+                else atomicAdd(gx + c * ldgx + f0 + e, __fdiv_rn(gv[ch][e], cnt[ch][e]));
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int VEC, int G, int NCH>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __restrict__ idx,
+                   int64_t n_out, int F, float scale, float* __restrict__ out, int64_t ldo) {
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int gw = lane / G;
+  const int nv = F / VEC;
+  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
+  for (int64_t r = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; r < n_out;
+       r += (int64_t)gridDim.x * gpb) {
+    const int64_t s = idx ? (int64_t)__ldg(idx + r) : r;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if ((gl + ch * G) >= nv) continue;
+      const int f0 = (gl + ch * G) * VEC;
+      float v[VEC];
+      ld_vec<VEC>(src + s * lds + f0, v);
+      if (scale != 1.f) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v[e] = __fmul_rn(v[e], scale);
+      }
+      st_vec<VEC>(out + r * ldo + f0, v);
+    }
+  }
+}
+
+__global__ void permute_f32_kernel(const float* __restrict__ in, const int32_t* __restrict__ perm,
+                                   int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __ldg(in + __ldg(perm + i));
+}
+
+__global__ void reduce_parts_kernel(const float* __restrict__ part, int n_parts, int F, float* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  float s = 0.f;
+  for (int p = 0; p < n_parts; ++p) s = __fadd_rn(s, part[(int64_t)p * F + f]);
+  out[f] = s;
+}
+
+// ---- host-side dispatch ----------------------------------------------------------------------
+struct Shape {
+  int vec, g, nch;
+};
+
+// feature slab handled by one launch: at most 32 lanes * 4 chunks * VEC floats
+static Shape pick_shape(int F, bool can_vec4) {
+  Shape s;
+  s.vec = (can_vec4 && F % 4 == 0) ? 4 : 1;
+  const int nv = F / s.vec;
+  if (nv <= 32) {
+    s.g = pow2_ceil(nv);
+    s.nch = 1;
+  } else {
+    s.g = 32;
+    const int n = (int)ceil_div(nv, 32);
+    s.nch = n <= 2 ? 2 : 4;
+  }
+  return s;
+}
+
+static int grid_for(int device, int64_t tasks, int g) {
+  const int64_t gpb = 8 * (32 / g);
+  int64_t need = ceil_div(tasks, gpb);
+  const int64_t cap = (int64_t)sm_count(device) * 8;
+  if (need > cap) need = cap;
+  if (need < 1) need = 1;
+  return (int)need;
+}
+
+template <int VEC, int G, int NCH>
+static int launch_gr(int device, const GRP& p, bool is_max, cudaStream_t st) {
+  const int64_t tasks = (int64_t)p.n_chunks + p.n_rows;
+  const int grid = grid_for(device, tasks, G);
+  const bool ew = p.edge_w != nullptr, ss = p.src_scale != nullptr;
+  if (is_max) {
+    if (ew || ss) { set_error("max/min do not take edge weights"); return KGB_ERR_INVALID; }
+    gather_reduce_kernel<VEC, G, NCH, true, false, false><<<grid, 256, 0, st>>>(p);
+  } else if (ew && ss) {
+    gather_reduce_kernel<VEC, G, NCH, false, true, true><<<grid, 256, 0, st>>>(p);
+  } else if (ew) {
+    gather_reduce_kernel<VEC, G, NCH, false, true, false><<<grid, 256, 0, st>>>(p);
+  } else if (ss) {
+    gather_reduce_kernel<VEC, G, NCH, false, false, true><<<grid, 256, 0, st>>>(p);
+  } else {
+    gather_reduce_kernel<VEC, G, NCH, false, false, false><<<grid, 256, 0, st>>>(p);
+  }
+  KGB_CHECK_LAUNCH();
+  if (p.n_hubs > 0) {
+    const int hgrid = grid_for(device, p.n_hubs, G);
+    if (is_max) hub_finish_kernel<VEC, G, NCH, true><<<hgrid, 256, 0, st>>>(p);
+    else hub_finish_kernel<VEC, G, NCH, false><<<hgrid, 256, 0, st>>>(p);
+    KGB_CHECK_LAUNCH();
+  }
+  return KGB_OK;
+}
+
+#define KGB_DISPATCH_SHAPE(S, CALL)                                        \
+  do {                                                                     \
+    if ((S).vec == 4) {                                                    \
+      switch ((S).g * 8 + (S).nch) {                                       \
+        case 1 * 8 + 1: { constexpr int V = 4, G_ = 1, N_ = 1; CALL; } break;   \
+        case 2 * 8 + 1: { constexpr int V = 4, G_ = 2, N_ = 1; CALL; } break;   \
+        case 4 * 8 + 1: { constexpr int V = 4, G_ = 4, N_ = 1; CALL; } break;   \
+        case 8 * 8 + 1: { constexpr int V = 4, G_ = 8, N_ = 1; CALL; } break;   \
+        case 16 * 8 + 1: { constexpr int V = 4, G_ = 16, N_ = 1; CALL; } break; \
+        case 32 * 8 + 1: { constexpr int V = 4, G_ = 32, N_ = 1; CALL; } break; \
+        case 32 * 8 + 2: { constexpr int V = 4, G_ = 32, N_ = 2; CALL; } break; \
+        case 32 * 8 + 4: { constexpr int V = 4, G_ = 32, N_ = 4; CALL; } break; \
+        default: set_error("no kernel for shape"); return KGB_ERR_UNSUPPORTED;  \
+      }                                                                    \
+    } else {                                                               \
+      switch ((S).g * 8 + (S).nch) {                                       \
+        case 1 * 8 + 1: { constexpr int V = 1, G_ = 1, N_ = 1; CALL; } break;   \
+        case 2 * 8 + 1: { constexpr int V = 1, G_ = 2, N_ = 1; CALL; } break;   \
+        case 4 * 8 + 1: { constexpr int V = 1, G_ = 4, N_ = 1; CALL; } break;   \
+        case 8 * 8 + 1: { constexpr int V = 1, G_ = 8, N_ = 1; CALL; } break;   \
+        case 16 * 8 + 1: { constexpr int V = 1, G_ = 16, N_ = 1; CALL; } break; \
+        case 32 * 8 + 1: { constexpr int V = 1, G_ = 32, N_ = 1; CALL; } break; \
+        case 32 * 8 + 2: { constexpr int V = 1, G_ = 32, N_ = 2; CALL; } break; \
+        case 32 * 8 + 4: { constexpr int V = 1, G_ = 32, N_ = 4; CALL; } break; \
+        default: set_error("no kernel for shape"); return KGB_ERR_UNSUPPORTED;  \
+      }                                                                    \
+    }                                                                      \
+  } while (0)
+
+}  // namespace kgb
+
+using namespace kgb;
+
+extern "C" {
+
+size_t kgb_gather_reduce_partial_bytes(int32_t n_chunks, int32_t F, int32_t op) {
+  if (n_chunks <= 0) return 0;
+  size_t b = align_up((size_t)n_chunks * (size_t)F * sizeof(float), 256);
+  if (op == KGB_OP_MAX || op == KGB_OP_MIN) b *= 2;  // values + arg
+  return b;
+}
+
+int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(a != nullptr, "args is NULL");
+  KGB_REQUIRE(a->F > 0, "F must be positive (got %d)", a->F);
+  KGB_REQUIRE(a->n_rows >= 0, "n_rows < 0");
+  KGB_REQUIRE(a->op >= KGB_OP_SUM && a->op <= KGB_OP_MIN, "bad op %d", a->op);
+  if (a->n_rows == 0) return KGB_OK;
+  KGB_REQUIRE(a->x && a->rowptr && a->out, "x/rowptr/out must be non-NULL");
+  KGB_REQUIRE(a->ldx >= a->F && a->ldo >= a->F, "leading dimension smaller than F");
+  const bool hubs = a->n_hubs > 0 && a->n_chunks > 0;
+  if (hubs) {
+    KGB_REQUIRE(a->hub_row && a->hub_chunk_base && a->hub_nchunks && a->chunk_hub && a->partial,
+                "hub table given but a pointer is NULL");
+    KGB_REQUIRE(a->hub_chunk > 0 && a->hub_threshold >= a->hub_chunk, "bad hub threshold/chunk");
+  }
+  const bool is_max = (a->op == KGB_OP_MAX || a->op == KGB_OP_MIN);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  const bool can4 = aligned16(a->x) && aligned16(a->out) && (a->ldx % 4 == 0) && (a->ldo % 4 == 0) &&
+                    (!a->addend || (aligned16(a->addend) && a->ld_addend % 4 == 0)) &&
+                    (!a->bias || aligned16(a->bias)) && (!a->arg || aligned16(a->arg)) &&
+                    (!hubs || aligned16(a->partial));
+  const int vec = (can4 && a->F % 4 == 0) ? 4 : 1;
+  const int slab = 32 * 4 * vec;  // widest feature slab of one launch
+  for (int f0 = 0; f0 < a->F; f0 += slab) {
+    const int Fs = (a->F - f0 < slab) ? (a->F - f0) : slab;
+    GRP p;
+    p.x = a->x + f0; p.ldx = a->ldx; p.F = Fs;
+    p.rowptr = a->rowptr; p.col = a->col; p.n_rows = a->n_rows; p.row_ids = a->row_ids;
+    p.edge_w = a->edge_w; p.src_scale = a->src_scale; p.out_scale = a->out_scale;
+    p.addend = a->addend ? a->addend + f0 : nullptr; p.ld_addend = a->ld_addend;
+    p.addend_scale = a->addend_scale;
+    p.bias = a->bias ? a->bias + f0 : nullptr; p.act = a->act;
+    p.mean = (a->op == KGB_OP_MEAN); p.negate = (a->op == KGB_OP_MIN);
+    p.out = a->out + f0; p.ldo = a->ldo; p.arg = a->arg ? a->arg + f0 : nullptr;
+    p.hub_row = a->hub_row; p.hub_chunk_base = a->hub_chunk_base; p.hub_nchunks = a->hub_nchunks;
+    p.chunk_hub = a->chunk_hub;
+    p.n_hubs = hubs ? a->n_hubs : 0; p.n_chunks = hubs ? a->n_chunks : 0;
+    p.hub_threshold = a->hub_threshold; p.hub_chunk = a->hub_chunk;
+    p.partial = a->partial;
+    p.partial_arg = nullptr;
+    if (hubs && is_max)
+      p.partial_arg = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(a->partial) +
+                                                 align_up((size_t)a->n_chunks * (size_t)a->F * sizeof(float), 256));
+    // the partial buffer is reused by every slab (launches are stream-ordered)
+    Shape s = pick_shape(Fs, vec == 4);
+    int rc = KGB_OK;
+    KGB_DISPATCH_SHAPE(s, (rc = launch_gr<V, G_, N_>(device, p, is_max, st)));
+    if (rc != KGB_OK) return rc;
+  }
+  return KGB_OK;
+}
+
+int kgb_gather_max_bwd(int device, const float* g, int64_t ldg, const int32_t* arg, const float* out,
+                       int64_t ldo, const float* x, int64_t ldx, const int64_t* rowptr,
+                       const int32_t* col, const int32_t* row_ids, int64_t n_rows, int32_t F,
+                       int32_t op, float* gx, int64_t ldgx, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(op == KGB_OP_MAX || op == KGB_OP_MIN, "op must be MAX or MIN");
+  KGB_REQUIRE(F > 0 && n_rows >= 0, "bad sizes");
+  if (n_rows == 0) return KGB_OK;
+  KGB_REQUIRE(g && arg && out && x && rowptr && col && gx, "NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool can4 = aligned16(g) && aligned16(arg) && aligned16(out) && aligned16(x) && ldg % 4 == 0 &&
+                    ldo % 4 == 0 && ldx % 4 == 0;
+  const int vec = (can4 && F % 4 == 0) ? 4 : 1;
+  const int slab = 32 * 4 * vec;
+  for (int f0 = 0; f0 < F; f0 += slab) {
+    const int Fs = (F - f0 < slab) ? (F - f0) : slab;
+    Shape s = pick_shape(Fs, vec == 4);
+    const int grid = grid_for(device, n_rows, s.g);
+    KGB_DISPATCH_SHAPE(s, (gather_max_bwd_kernel<V, G_, N_><<<grid, 256, 0, st>>>(
+                              g + f0, ldg, arg + f0, out + f0, ldo, x + f0, ldx, rowptr, col, row_ids,
+                              n_rows, Fs, gx + f0, ldgx)));
+    KGB_CHECK_LAUNCH();
+  }
+  return KGB_OK;
+}
+
+int kgb_gather_rows(int device, const float* src, int64_t lds, const int32_t* idx, int64_t n_out,
+                    int32_t F, float scale, float* out, int64_t ldo, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(F > 0 && n_out >= 0, "bad sizes");
+  if (n_out == 0) return KGB_OK;
+  KGB_REQUIRE(src && out, "NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool can4 = aligned16(src) && aligned16(out) && lds % 4 == 0 && ldo % 4 == 0;
+  const int vec = (can4 && F % 4 == 0) ? 4 : 1;
+  const int slab = 32 * 4 * vec;
+  for (int f0 = 0; f0 < F; f0 += slab) {
+    const int Fs = (F - f0 < slab) ? (F - f0) : slab;
+    Shape s = pick_shape(Fs, vec == 4);
+    const int grid = grid_for(device, n_out, s.g);
+    KGB_DISPATCH_SHAPE(s, (gather_rows_kernel<V, G_, N_><<<grid, 256, 0, st>>>(src + f0, lds, idx, n_out, Fs,
+                                                                               scale, out + f0, ldo)));
+    KGB_CHECK_LAUNCH();
+  }
+  return KGB_OK;
+}
+
+int kgb_permute_f32(int device, const float* in, const int32_t* perm, int64_t n, float* out,
+                    kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  if (n <= 0) return KGB_OK;
+  KGB_REQUIRE(in && perm && out, "NULL pointer");
+  int64_t grid = ceil_div(n, 256);
+  const int64_t cap = (int64_t)sm_count(device) * 16;
+  if (grid > cap) grid = cap;
+  permute_f32_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(in, perm, n, out);
+  KGB_CHECK_LAUNCH();
+  return KGB_OK;
+}
+
+int kgb_reduce_parts(int device, const float* part, int32_t n_parts, int32_t F, float* out,
+                     kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(F > 0 && n_parts >= 0 && part && out, "bad arguments");
+  reduce_parts_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(part, n_parts, F, out);
+  KGB_CHECK_LAUNCH();
+  return KGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+"""Device-resident graph structure (CSR by target + CSC by source) and its cache.
+
+Replaces the reference's int32-cast cache keyed by ``id(edge_index)``
+(/root/reference/src/keras_geometric/layers/message_passing.py:257-266) and the implicit
+per-call grouping done inside ``keras.ops.segment_*``.  A structure is built once per
+``edge_index`` tensor by ``kgb_csr_build`` (include/kgb200.h) and reused by every layer,
+forward and backward.
+"""
+from __future__ import annotations
+
+import weakref
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+
+HUB_THRESHOLD = 512   # rows with more edges than this are cut into chunks ...
+HUB_CHUNK = 256       # ... of this many edges (see csrc/gather_reduce.cu)
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"keras_geometric_b200: {what} must live on a CUDA device "
+                           "(there is no CPU path; see keras_geometric_b200._lib)")
+
+
+class Csr:
+    """One orientation: ``rowptr`` int64 [n+1], ``col`` int32 [nnz] (the other endpoint),
+    ``perm`` int32 [nnz] (original edge id of each slot, stable), ``deg`` int32 [n]."""
+
+    __slots__ = ("n_rows", "n_cols", "nnz", "rowptr", "col", "perm", "deg", "hub_row", "hub_chunk_base",
+                 "hub_nchunks", "chunk_hub", "n_hubs", "n_chunks", "_inv_deg", "_partials", "_deg_f")
+
+    def __init__(self):
+        self._inv_deg = None
+        self._deg_f = None
+        self._partials = {}
+        self.n_hubs = 0
+        self.n_chunks = 0
+        self.hub_row = self.hub_chunk_base = self.hub_nchunks = self.chunk_hub = None
+
+    @property
+    def inv_deg(self) -> torch.Tensor:
+        """1 / max(deg, 1e-8) as float32 (the mean aggregator's divisor, aggregators.py:77-81)."""
+        if self._inv_deg is None:
+            self._inv_deg = 1.0 / torch.clamp(self.deg.to(torch.float32), min=1e-8)
+        return self._inv_deg
+
+    def partial(self, F: int, op: int) -> torch.Tensor | None:
+        if self.n_chunks == 0:
+            return None
+        nbytes = _lib.load().kgb_gather_reduce_partial_bytes(self.n_chunks, F, op)
+        key = nbytes
+        buf = self._partials.get(key)
+        if buf is None:
+            buf = torch.empty(nbytes // 4, dtype=torch.float32, device=self.rowptr.device)
+            self._partials = {key: buf}
+        return buf
+
+
+def build_csr(edge_index: torch.Tensor, n_seg: int, n_val: int, n_loops: int, by_source: bool) -> Csr:
+    """Run kgb_csr_build (+ hub table).  ``edge_index`` int32 [2,E] contiguous on CUDA."""
+    require_cuda(edge_index, "edge_index")
+    assert edge_index.dtype == torch.int32 and edge_index.is_contiguous() and edge_index.dim() == 2
+    lib = _lib.load()
+    dev = edge_index.device
+    E = int(edge_index.shape[1])
+    M = E + n_loops
+    c = Csr()
+    c.n_rows, c.n_cols, c.nnz = n_seg, n_val, M
+    c.rowptr = torch.empty(n_seg + 1, dtype=torch.int64, device=dev)
+    c.col = torch.empty(max(M, 1), dtype=torch.int32, device=dev)[:M]
+    c.perm = torch.empty(max(M, 1), dtype=torch.int32, device=dev)[:M]
+    c.deg = torch.empty(max(n_seg, 1), dtype=torch.int32, device=dev)[:n_seg]
+    meta = torch.zeros(4, dtype=torch.int32, device=dev)  # [status, n_hubs, n_chunks, -]
+    ws_bytes = lib.kgb_csr_build_workspace_bytes(M, n_seg)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    st = _stream(dev)
+    _lib.check(lib.kgb_csr_build(dev.index, edge_index.data_ptr(), E, int(by_source), n_seg, n_val, n_loops,
+                                 c.rowptr.data_ptr(), c.col.data_ptr(), c.perm.data_ptr(), c.deg.data_ptr(),
+                                 meta.data_ptr(), ws.data_ptr(), ws_bytes, st), "kgb_csr_build")
+    max_hubs = M // HUB_THRESHOLD + 1
+    max_chunks = M // HUB_CHUNK + max_hubs + 1
+    hub = torch.empty(3 * max_hubs + max_chunks, dtype=torch.int32, device=dev)
+    c.hub_row, c.hub_chunk_base, c.hub_nchunks = hub[:max_hubs], hub[max_hubs:2 * max_hubs], hub[2 * max_hubs:3 * max_hubs]
+    c.chunk_hub = hub[3 * max_hubs:]
+    _lib.check(lib.kgb_csr_hubs(dev.index, c.rowptr.data_ptr(), n_seg, HUB_THRESHOLD, HUB_CHUNK,
+                                c.hub_row.data_ptr(), c.hub_chunk_base.data_ptr(), c.hub_nchunks.data_ptr(),
+                                c.chunk_hub.data_ptr(), max_hubs, max_chunks, meta[1:].data_ptr(), st),
+               "kgb_csr_hubs")
+    status, n_hubs, n_chunks, _ = meta.tolist()  # the one host sync of a structure build
+    del ws
+    if status & _lib.STATUS_OOB_INDEX:
+        raise IndexError(f"edge_index contains node ids outside [0, {n_seg if not by_source else n_val}) / "
+                         f"[0, {n_val if not by_source else n_seg})")
+    assert n_hubs <= max_hubs and n_chunks <= max_chunks
+    c.n_hubs, c.n_chunks = int(n_hubs), int(n_chunks)
+    return c
+
+
+class GraphStructure:
+    """CSR (by target, forward) and lazily CSC (by source, backward) of one edge list.
+
+    ``n_dst`` target rows, ``n_src`` source rows (equal unless bipartite); ``n_loops`` self-loops
+    are appended after the real edges like ``add_self_loops`` does (utils/main.py:8-16)."""
+
+    def __init__(self, edge_index: torch.Tensor, n_dst: int, n_src: int | None = None, n_loops: int = 0):
+        n_src = n_dst if n_src is None else n_src
+        if edge_index.dtype != torch.int32 or not edge_index.is_contiguous():
+            edge_index = edge_index.to(torch.int32).contiguous()
+        self.edge_index = edge_index
+        self.n_dst, self.n_src, self.n_loops = int(n_dst), int(n_src), int(n_loops)
+        self.E = int(edge_index.shape[1])
+        self.nnz = self.E + self.n_loops
+        self.device = edge_index.device
+        self.csr = build_csr(edge_index, self.n_dst, self.n_src, self.n_loops, by_source=False)
+        self._csc = None
+        self._gcn = None
+        self._dst_sorted = None
+
+    @property
+    def csc(self) -> Csr:
+        if self._csc is None:
+            self._csc = build_csr(self.edge_index, self.n_src, self.n_dst, self.n_loops, by_source=True)
+        return self._csc
+
+    def gcn_norm(self):
+        """(dis [n_dst], w_coo [nnz]) of utils/main.py:20-33 via kgb_gcn_norm."""
+        if self._gcn is None:
+            if self.n_dst != self.n_src:
+                raise ValueError("GCN normalisation needs a square graph")
+            lib = _lib.load()
+            dis = torch.empty(self.n_dst, dtype=torch.float32, device=self.device)
+            w = torch.empty(max(self.nnz, 1), dtype=torch.float32, device=self.device)[:self.nnz]
+            _lib.check(lib.kgb_gcn_norm(self.device.index, self.csr.deg.data_ptr(), self.n_dst,
+                                        self.edge_index.data_ptr(), self.E, self.n_loops, dis.data_ptr(),
+                                        w.data_ptr(), _stream(self.device)), "kgb_gcn_norm")
+            self._gcn = (dis, w)
+        return self._gcn
+
+    def full_edge_index(self) -> torch.Tensor:
+        """edge_index with the self-loops materialised ([2, E + n_loops], int32)."""
+        if self.n_loops == 0:
+            return self.edge_index
+        loop = torch.arange(self.n_loops, dtype=torch.int32, device=self.device)
+        return torch.cat([self.edge_index, torch.stack([loop, loop])], dim=1)
+
+
+# ---- cache -------------------------------------------------------------------------------
+_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_CACHE_SIZE = 8
+
+
+def clear_cache() -> None:
+    _CACHE.clear()
+
+
+def get_graph(edge_index: torch.Tensor, n_dst: int, n_src: int | None = None, n_loops: int = 0) -> GraphStructure:
+    """Structure of ``edge_index``, cached on the identity of the tensor object.
+
+    The key is ``(id(tensor), _version, shape, sizes)`` and the entry holds a weak reference to
+    the tensor, so neither an in-place update nor a recycled address can return a stale
+    structure (the reference's ``id()`` cache has both problems)."""
+    n_src = n_dst if n_src is None else n_src
+    key = (id(edge_index), edge_index._version, tuple(edge_index.shape), edge_index.dtype, int(n_dst), int(n_src),
+           int(n_loops))
+    hit = _CACHE.get(key)
+    if hit is not None:
+        ref, g = hit
+        if ref() is edge_index:
+            _CACHE.move_to_end(key)
+            return g
+        del _CACHE[key]
+    g = GraphStructure(edge_index, n_dst, n_src, n_loops)
+    try:
+        _CACHE[key] = (weakref.ref(edge_index), g)
+    except TypeError:
+        return g
+    while len(_CACHE) > _CACHE_SIZE:
+        _CACHE.popitem(last=False)
+    return g

@@ -1,0 +1,345 @@
+"""torch.autograd wrappers around the C ABI (include/kgb200.h).
+
+Every function here launches hand-written sm_100a kernels from libkgb200.so on the current
+CUDA stream with borrowed ``data_ptr()``s.  No function has a CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from .graph import HUB_CHUNK, HUB_THRESHOLD, Csr, GraphStructure, _stream, require_cuda
+
+_ACT = {None: _lib.ACT_NONE, "linear": _lib.ACT_NONE, "relu": _lib.ACT_RELU}
+
+# When set to a list, every gather-reduce launch appends {label, start, end, bytes} with CUDA events
+# recorded on the launching stream (bench.py reads it for the per-kernel roofline).
+PROFILE = None
+_OP_NAMES = {0: "sum", 1: "mean", 2: "max", 3: "min"}
+
+
+def _algorithmic_bytes(nnz, n_rows, F, per_edge_extra, per_row_extra):
+    return nnz * (4 * F + 4 + per_edge_extra) + n_rows * (4 * F + per_row_extra) + (n_rows + 1) * 8
+
+
+def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    require_cuda(t, what)
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    if t.dim() == 2 and t.stride(1) != 1:
+        t = t.contiguous()
+    elif t.dim() != 2 and not t.is_contiguous():
+        t = t.contiguous()
+    return t
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def gather_reduce_raw(x: torch.Tensor, csr: Csr, op: int, *, col: torch.Tensor | None = None,
+                      edge_w=None, src_scale=None, out_scale=None, addend=None, addend_scale: float = 1.0,
+                      bias=None, act: int = 0, want_arg: bool = False, row_ids=None, out=None,
+                      n_out_rows: int | None = None):
+    """One kgb_gather_reduce launch (no autograd).  Returns ``(out, arg_or_None)``."""
+    lib = _lib.load()
+    require_cuda(x, "x")
+    F = int(x.shape[1])
+    dev = x.device
+    n_rows = csr.n_rows
+    n_out = n_rows if n_out_rows is None else n_out_rows
+    if out is None:
+        out = torch.empty((n_out, F), dtype=torch.float32, device=dev)
+    arg = torch.empty((out.shape[0], out.stride(0)), dtype=torch.int32, device=dev) if want_arg else None
+    if n_rows == 0 or F == 0:
+        return out, (arg[:, :F] if arg is not None else None)
+    a = _lib.GatherReduceArgs()
+    a.x, a.ldx, a.n_src_rows, a.F, a.op = x.data_ptr(), x.stride(0), x.shape[0], F, op
+    a.rowptr, a.col, a.n_rows = csr.rowptr.data_ptr(), (csr.col if col is None else col).data_ptr(), n_rows
+    a.row_ids = _ptr(row_ids)
+    a.edge_w, a.src_scale, a.out_scale = _ptr(edge_w), _ptr(src_scale), _ptr(out_scale)
+    a.addend = _ptr(addend)
+    a.ld_addend = addend.stride(0) if addend is not None else 0
+    a.addend_scale = float(addend_scale)
+    a.bias, a.act = _ptr(bias), act
+    a.out, a.ldo, a.arg = out.data_ptr(), out.stride(0), _ptr(arg)
+    partial = csr.partial(F, op)
+    if partial is not None:
+        a.hub_row, a.hub_chunk_base = csr.hub_row.data_ptr(), csr.hub_chunk_base.data_ptr()
+        a.hub_nchunks, a.chunk_hub = csr.hub_nchunks.data_ptr(), csr.chunk_hub.data_ptr()
+        a.n_hubs, a.n_chunks = csr.n_hubs, csr.n_chunks
+        a.hub_threshold, a.hub_chunk = HUB_THRESHOLD, HUB_CHUNK
+        a.partial = partial.data_ptr()
+    rec = None
+    if PROFILE is not None:
+        rec = {"start": torch.cuda.Event(enable_timing=True), "end": torch.cuda.Event(enable_timing=True)}
+        rec["start"].record(torch.cuda.current_stream(dev))
+    _lib.check(lib.kgb_gather_reduce(dev.index, ctypes.byref(a), _stream(dev)), "kgb_gather_reduce")
+    if rec is not None:
+        rec["end"].record(torch.cuda.current_stream(dev))
+        per_edge = (4 if edge_w is not None else 0) + (4 if src_scale is not None else 0)
+        per_row = (4 if out_scale is not None else 0) + (4 * F if addend is not None else 0) + (4 * F if want_arg else 0)
+        rec["bytes"] = _algorithmic_bytes(csr.nnz, n_rows, F, per_edge, per_row)
+        rec["label"] = (f"gather_reduce_{_OP_NAMES[op]}_F{F}" + ("_w" if per_edge else "")
+                        + ("_epi" if (addend is not None or bias is not None or act) else ""))
+        PROFILE.append(rec)
+    return out, (arg[:, :F] if arg is not None else None)
+
+
+def _max_bwd(g, arg, out, x, csr: Csr, col, op: int, n_src_rows: int):
+    lib = _lib.load()
+    F = int(g.shape[1])
+    gx = torch.zeros((n_src_rows, F), dtype=torch.float32, device=g.device)
+    if csr.n_rows and F:
+        _lib.check(lib.kgb_gather_max_bwd(g.device.index, g.data_ptr(), g.stride(0), arg.data_ptr(), out.data_ptr(),
+                                          out.stride(0), x.data_ptr(), x.stride(0), csr.rowptr.data_ptr(),
+                                          col.data_ptr(), None, csr.n_rows, F, op, gx.data_ptr(), gx.stride(0),
+                                          _stream(g.device)), "kgb_gather_max_bwd")
+    return gx
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor | None, scale: float = 1.0, out=None) -> torch.Tensor:
+    """out[r,:] = scale * src[idx[r],:] via kgb_gather_rows."""
+    lib = _lib.load()
+    require_cuda(src, "src")
+    n_out = int(idx.shape[0]) if idx is not None else int(src.shape[0])
+    F = int(src.shape[1])
+    if out is None:
+        out = torch.empty((n_out, F), dtype=torch.float32, device=src.device)
+    if n_out and F:
+        _lib.check(lib.kgb_gather_rows(src.device.index, src.data_ptr(), src.stride(0), _ptr(idx), n_out, F,
+                                       float(scale), out.data_ptr(), out.stride(0), _stream(src.device)),
+                   "kgb_gather_rows")
+    return out
+
+
+def permute_f32(w: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(perm.shape[0], dtype=torch.float32, device=w.device)
+    if perm.shape[0]:
+        _lib.check(lib.kgb_permute_f32(w.device.index, w.data_ptr(), perm.data_ptr(), perm.shape[0], out.data_ptr(),
+                                       _stream(w.device)), "kgb_permute_f32")
+    return out
+
+
+class _GatherReduce(torch.autograd.Function):
+    """out = act(scale_out * OP_k(w_k * x[col_k]) + addend_scale * addend + bias)."""
+
+    @staticmethod
+    def forward(ctx, x, addend, bias, graph: GraphStructure, op_name: str, weight, addend_scale, act):
+        op = _lib.OPS[op_name]
+        x = _f32c(x, "x")
+        csr = graph.csr
+        kw = {}
+        ctx.weight_kind = None
+        if weight is not None:
+            if op in (_lib.OP_MAX, _lib.OP_MIN):
+                raise ValueError("max/min aggregation does not take edge weights")
+            if isinstance(weight, str) and weight == "gcn":
+                dis, _ = graph.gcn_norm()
+                kw = {"src_scale": dis, "out_scale": dis}
+                ctx.weight_kind = "gcn"
+            else:
+                w = _f32c(weight, "edge weight").reshape(-1)
+                if w.shape[0] != graph.nnz:
+                    raise ValueError(f"edge weight has {w.shape[0]} entries, graph has {graph.nnz} edges")
+                kw = {"edge_w": permute_f32(w, csr.perm)}
+                ctx.weight_kind = "edge"
+                ctx.w_coo = w
+        addend_c = _f32c(addend, "addend") if addend is not None else None
+        bias_c = _f32c(bias, "bias") if bias is not None else None
+        is_max = op in (_lib.OP_MAX, _lib.OP_MIN)
+        if is_max and (addend is not None or bias is not None or act not in (None, "linear")):
+            raise ValueError("max/min aggregation cannot be fused with an epilogue (ties are detected on the raw result)")
+        out, arg = gather_reduce_raw(x, csr, op, addend=addend_c, addend_scale=addend_scale, bias=bias_c,
+                                     act=_ACT[act], want_arg=is_max, **kw)
+        ctx.graph, ctx.op, ctx.act, ctx.addend_scale = graph, op, act, float(addend_scale)
+        ctx.has_addend, ctx.has_bias = addend is not None, bias is not None
+        ctx.n_src = int(x.shape[0])
+        saved = []
+        if is_max:
+            saved = [x, arg]
+        if is_max or act == "relu":
+            saved.append(out)
+        ctx.save_for_backward(*saved)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        graph, op = ctx.graph, ctx.op
+        g = _f32c(g, "grad")
+        saved = list(ctx.saved_tensors)
+        is_max = op in (_lib.OP_MAX, _lib.OP_MIN)
+        out = saved[-1] if (is_max or ctx.act == "relu") else None
+        if ctx.act == "relu":
+            g = g * (out > 0)
+        g_addend = (g * ctx.addend_scale if ctx.addend_scale != 1.0 else g) if ctx.has_addend else None
+        g_bias = g.sum(dim=0) if ctx.has_bias else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            if is_max:
+                x, arg = saved[0], saved[1]
+                gx = _max_bwd(g, arg, out, x, graph.csr, graph.csr.col, op, ctx.n_src)
+            else:
+                csc = graph.csc
+                kw = {}
+                if ctx.weight_kind == "gcn":
+                    dis, _ = graph.gcn_norm()
+                    kw = {"src_scale": dis, "out_scale": dis}
+                elif ctx.weight_kind == "edge":
+                    kw = {"edge_w": permute_f32(ctx.w_coo, csc.perm)}
+                if op == _lib.OP_MEAN:
+                    kw["src_scale"] = graph.csr.inv_deg
+                gx, _ = gather_reduce_raw(g, csc, _lib.OP_SUM, **kw)
+        return gx, g_addend, g_bias, None, None, None, None, None
+
+
+def gather_reduce(x, graph: GraphStructure, op: str = "sum", *, weight=None, addend=None,
+                  addend_scale: float = 1.0, bias=None, act=None) -> torch.Tensor:
+    """Fused gather + segmented reduction over ``graph`` (K3/K4, backward K5).
+
+    Equivalent to the reference's ``take(x, src)`` -> message -> ``Aggregator.aggregate`` chain
+    (layers/message_passing.py:195-212) without materialising any [E, F] tensor.
+    ``weight``: None, ``"gcn"`` (symmetric normalisation, utils/main.py:20-33) or a COO-ordered
+    [nnz] tensor."""
+    if op not in _lib.OPS:
+        raise ValueError(f"Invalid aggregator: {op}. Available aggregators: {list(_lib.OPS)}")
+    return _GatherReduce.apply(x, addend, bias, graph, op, weight, addend_scale, act)
+
+
+class _SegmentReduce(torch.autograd.Function):
+    """Generic Aggregator.aggregate over materialised messages [E, F'] (K9)."""
+
+    @staticmethod
+    def forward(ctx, messages, graph: GraphStructure, op_name: str):
+        op = _lib.OPS[op_name]
+        m = _f32c(messages, "messages")
+        csr = graph.csr
+        is_max = op in (_lib.OP_MAX, _lib.OP_MIN)
+        out, arg = gather_reduce_raw(m, csr, op, col=csr.perm, want_arg=is_max)
+        ctx.graph, ctx.op, ctx.n_msg = graph, op, int(m.shape[0])
+        ctx.save_for_backward(*([m, arg, out] if is_max else []))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        graph, op = ctx.graph, ctx.op
+        g = _f32c(g, "grad")
+        if op in (_lib.OP_MAX, _lib.OP_MIN):
+            m, arg, out = ctx.saved_tensors
+            return _max_bwd(g, arg, out, m, graph.csr, graph.csr.perm, op, ctx.n_msg), None, None
+        if op == _lib.OP_MEAN:
+            g = g * graph.csr.inv_deg.unsqueeze(1)
+        dst = graph.full_edge_index()[1]
+        return gather_rows(g, dst), None, None
+
+
+def segment_reduce(messages, graph: GraphStructure, op: str = "sum") -> torch.Tensor:
+    """``Aggregator.aggregate(messages, target_idx, dim_size)`` (layers/aggregators.py:24-39) for
+    sum/mean/max/min over a prebuilt structure; messages are in the graph's COO edge order."""
+    if op not in _lib.OPS:
+        raise ValueError(f"Invalid aggregator: {op}. Available aggregators: {list(_lib.OPS)}")
+    return _SegmentReduce.apply(messages, graph, op)
+
+
+class _TakeRows(torch.autograd.Function):
+    """x[idx] with idx one row of a graph's edge list (``ops.take`` of the reference,
+    layers/message_passing.py:195-196).  Backward is the segmented sum over the matching
+    structure (deterministic), not an atomic scatter."""
+
+    @staticmethod
+    def forward(ctx, x, graph: GraphStructure, which: str):
+        x = _f32c(x, "x")
+        idx = graph.full_edge_index()[0 if which == "src" else 1]
+        ctx.graph, ctx.which, ctx.n = graph, which, int(x.shape[0])
+        return gather_rows(x, idx)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        g = _f32c(g, "grad")
+        s = ctx.graph.csc if ctx.which == "src" else ctx.graph.csr
+        gx, _ = gather_reduce_raw(g, s, _lib.OP_SUM, col=s.perm)
+        return gx, None, None
+
+
+def take_rows(x, graph: GraphStructure, which: str = "src") -> torch.Tensor:
+    """Materialise the per-edge rows x[src] / x[dst] ([nnz, F]) for the generic message path."""
+    return _TakeRows.apply(x, graph, which)
+
+
+class _GatV2(torch.autograd.Function):
+    """Fused GATv2 attention + aggregation over a graph structure (K6)."""
+
+    @staticmethod
+    def forward(ctx, h_src, h_dst, att, bias, graph: GraphStructure, H: int, C: int, slope: float):
+        lib = _lib.load()
+        same = h_src is h_dst
+        h_src = _f32c(h_src, "h_src").contiguous()
+        h_dst = h_src if same else _f32c(h_dst, "h_dst").contiguous()
+        att_c = _f32c(att, "att").contiguous()
+        bias_c = _f32c(bias, "bias").contiguous() if bias is not None else None
+        dev = h_src.device
+        n_src, n_dst = int(h_src.shape[0]), int(h_dst.shape[0])
+        csr = graph.csr
+        out = torch.empty((n_dst, H * C), dtype=torch.float32, device=dev)
+        rowmax = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
+        rowden = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
+        _lib.check(lib.kgb_gatv2_fwd(dev.index, h_src.data_ptr(), h_dst.data_ptr(), n_src, n_dst, H, C,
+                                     att_c.data_ptr(), float(slope), csr.rowptr.data_ptr(), csr.col.data_ptr(),
+                                     _ptr(bias_c), out.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(),
+                                     _stream(dev)), "kgb_gatv2_fwd")
+        ctx.graph, ctx.H, ctx.C, ctx.slope, ctx.same = graph, H, C, float(slope), same
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(h_src, h_dst, att_c, out, rowmax, rowden, *([bias_c] if bias is not None else []))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        saved = ctx.saved_tensors
+        h_src, h_dst, att_c, out, rowmax, rowden = saved[:6]
+        g = _f32c(g, "grad").contiguous()
+        H, C, graph = ctx.H, ctx.C, ctx.graph
+        dev = g.device
+        n_src, n_dst = int(h_src.shape[0]), int(h_dst.shape[0])
+        agg = out - saved[6] if ctx.has_bias else out
+        csr, csc = graph.csr, graph.csc
+        st = _stream(dev)
+        n_parts = lib.kgb_gatv2_bwd_parts(dev.index, n_dst, H, C)
+        if n_parts <= 0:
+            raise _lib.KgbError("kgb_gatv2_bwd_parts: unsupported shape")
+        g_hdst = torch.empty_like(h_dst)
+        r = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
+        part = torch.empty((n_parts, H * C), dtype=torch.float32, device=dev)
+        _lib.check(lib.kgb_gatv2_bwd_dst(dev.index, g.data_ptr(), agg.data_ptr(), h_src.data_ptr(), h_dst.data_ptr(),
+                                         n_src, n_dst, H, C, att_c.data_ptr(), ctx.slope, csr.rowptr.data_ptr(),
+                                         csr.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(),
+                                         g_hdst.data_ptr(), r.data_ptr(), part.data_ptr(), n_parts, st),
+                   "kgb_gatv2_bwd_dst")
+        g_att = torch.empty(H * C, dtype=torch.float32, device=dev)
+        _lib.check(lib.kgb_reduce_parts(dev.index, part.data_ptr(), n_parts, H * C, g_att.data_ptr(), st),
+                   "kgb_reduce_parts")
+        g_hsrc = torch.empty_like(h_src)
+        _lib.check(lib.kgb_gatv2_bwd_src(dev.index, g.data_ptr(), h_src.data_ptr(), h_dst.data_ptr(), n_src, n_dst,
+                                         H, C, att_c.data_ptr(), ctx.slope, csc.rowptr.data_ptr(),
+                                         csc.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(), r.data_ptr(),
+                                         g_hsrc.data_ptr(), st), "kgb_gatv2_bwd_src")
+        g_bias = g.sum(dim=0) if ctx.has_bias else None
+        if ctx.same:
+            return g_hsrc + g_hdst, None, g_att, g_bias, None, None, None, None
+        return g_hsrc, g_hdst, g_att, g_bias, None, None, None, None
+
+
+def gatv2_aggregate(h_src, h_dst, att, graph: GraphStructure, heads: int, channels: int,
+                    negative_slope: float = 0.2, bias=None) -> torch.Tensor:
+    """Attention logits, per-target softmax and weighted aggregation of GATv2 in one kernel
+    (reference: layers/gatv2_conv.py:241-335).  ``h_*`` are [N, H*C], ``att`` has H*C entries;
+    returns [n_dst, H*C] (+ bias when given)."""
+    return _GatV2.apply(h_src, h_dst, att.reshape(-1), bias, graph, int(heads), int(channels), float(negative_slope))

@@ -1,0 +1,485 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI, via ctypes) against the CPU oracle
+and the committed golden vectors.  Bit-exact for integer/index work and for max/min values;
+float32 results within rtol 1e-5 (atol 1e-5 x the output scale) of the oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import reference_path as ref
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def close(got, want, rtol=RTOL, atol_scale=1e-5, msg=""):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    want = want.detach().cpu().numpy() if isinstance(want, torch.Tensor) else np.asarray(want)
+    assert got.shape == want.shape, f"{msg}: shape {got.shape} vs {want.shape}"
+    finite = np.abs(want[np.isfinite(want)])
+    scale = float(finite.max()) if finite.size else 1.0
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol_scale * max(scale, 1e-30), err_msg=msg, equal_nan=True)
+
+
+def cuda(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def rand_graph(rng, n_dst, n_src, e, hub=None):
+    src = rng.integers(0, n_src, e)
+    dst = rng.integers(0, max(n_dst - 2, 1), e)  # last rows stay empty
+    if hub:
+        dst[:hub] = 1
+    return np.stack([src, dst]).astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------- K1 / K2
+@pytest.mark.parametrize("n,e,loops", [(1, 0, 0), (1, 5, 1), (7, 0, 7), (50, 400, 0), (50, 400, 50),
+                                       (300, 5000, 300), (70000, 300000, 70000), (5, 100000, 0)])
+def test_csr_build_bit_exact(n, e, loops):
+    from keras_geometric_b200.graph import GraphStructure
+    rng = np.random.default_rng(n * 7 + e)
+    ei = np.stack([rng.integers(0, n, e), rng.integers(0, n, e)]).astype(np.int32)
+    g = GraphStructure(cuda(ei), n, n, loops)
+    full = ei if not loops else np.concatenate([ei, np.stack([np.arange(loops), np.arange(loops)]).astype(np.int32)], 1)
+    for by_source, s in ((False, g.csr), (True, g.csc)):
+        rowptr, col, perm, deg = ref.stable_csr(full, n, by_source)
+        np.testing.assert_array_equal(s.rowptr.cpu().numpy(), rowptr)
+        np.testing.assert_array_equal(s.deg.cpu().numpy(), deg)
+        np.testing.assert_array_equal(s.perm.cpu().numpy(), perm)
+        np.testing.assert_array_equal(s.col.cpu().numpy(), col)
+
+
+def test_csr_build_power_law_and_hubs():
+    from keras_geometric_b200.graph import GraphStructure, HUB_THRESHOLD
+    rng = np.random.default_rng(5)
+    n, e = 20000, 600000
+    dst = np.minimum((rng.pareto(1.2, e) * 3).astype(np.int64), n - 1)
+    ei = np.stack([rng.integers(0, n, e), dst]).astype(np.int32)
+    g = GraphStructure(cuda(ei), n, n, 0)
+    rowptr, col, perm, deg = ref.stable_csr(ei, n)
+    np.testing.assert_array_equal(g.csr.perm.cpu().numpy(), perm)
+    np.testing.assert_array_equal(g.csr.col.cpu().numpy(), col)
+    n_hubs = int((deg > HUB_THRESHOLD).sum())
+    assert g.csr.n_hubs == n_hubs and n_hubs > 0
+    hub_rows = sorted(g.csr.hub_row[:n_hubs].cpu().tolist())
+    assert hub_rows == sorted(np.nonzero(deg > HUB_THRESHOLD)[0].tolist())
+
+
+def test_csr_out_of_range_raises():
+    from keras_geometric_b200.graph import GraphStructure
+    ei = np.array([[0, 1, 9], [1, 2, 0]], np.int32)
+    with pytest.raises(IndexError):
+        GraphStructure(cuda(ei), 3, 3, 0)
+    ei = np.array([[0, 1, 2], [1, -1, 0]], np.int32)
+    with pytest.raises(IndexError):
+        GraphStructure(cuda(ei), 3, 3, 0)
+
+
+def test_utils_golden_bit_exact():
+    import keras_geometric_b200 as kg
+    g = load_golden("utils")
+    n = g["params"]["N"]
+    wl = kg.add_self_loops(g["edge_index"], n)
+    np.testing.assert_array_equal(wl.cpu().numpy(), g["with_loops"])
+    np.testing.assert_array_equal(kg.compute_gcn_normalization(wl, n).cpu().numpy(), g["gcn_norm"])
+    np.testing.assert_array_equal(kg.compute_gcn_normalization(g["edge_index"], n).cpu().numpy(), g["gcn_norm_noloop"])
+
+
+def test_gcn_norm_large_bit_exact():
+    import keras_geometric_b200 as kg
+    rng = np.random.default_rng(11)
+    n, e = 5000, 200000
+    ei = np.stack([rng.integers(0, n, e), np.minimum((rng.pareto(1.1, e) * 2).astype(np.int64), n - 1)]).astype(np.int32)
+    want = ref.compute_gcn_normalization(torch.from_numpy(ei), n).numpy()
+    np.testing.assert_array_equal(kg.compute_gcn_normalization(ei, n).cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------ K3 / K4 / K5
+@pytest.mark.parametrize("F", [1, 3, 7, 16, 32, 64, 100, 128, 256, 516, 1030])
+@pytest.mark.parametrize("op", ["sum", "mean", "max", "min"])
+def test_gather_reduce_vs_oracle(F, op):
+    from keras_geometric_b200 import ops
+    from keras_geometric_b200.graph import GraphStructure
+    rng = np.random.default_rng(F * 13 + len(op))
+    n_dst, n_src, e = 211, 157, 6000
+    ei = rand_graph(rng, n_dst, n_src, e, hub=2500)  # row 1 is a hub -> chunked path
+    x = np.round(rng.standard_normal((n_src, F)), 1).astype(np.float32)  # rounding forces max ties
+    R = rng.standard_normal((n_dst, F)).astype(np.float32)
+    graph = GraphStructure(cuda(ei), n_dst, n_src, 0)
+    assert graph.csr.n_hubs >= 1
+    xg = cuda(x).requires_grad_(True)
+    out = ops.gather_reduce(xg, graph, op)
+    xo = torch.from_numpy(x).requires_grad_(True)
+    want = ref.propagate((torch.zeros(n_dst, F), xo), torch.from_numpy(ei), op)
+    if op in ("max", "min"):
+        np.testing.assert_array_equal(out.detach().cpu().numpy(), want.detach().numpy())
+    else:
+        close(out, want, msg=f"{op} F={F}")
+    (gx,) = torch.autograd.grad((out * cuda(R)).sum(), [xg])
+    (gw,) = torch.autograd.grad((want * torch.from_numpy(R)).sum(), [xo])
+    close(gx, gw, msg=f"grad {op} F={F}")
+
+
+def test_unweighted_sum_matches_host_order_bitwise():
+    """Non-hub rows accumulate in CSR (= original edge) order, like the sequential host scatter."""
+    from keras_geometric_b200 import ops
+    from keras_geometric_b200.graph import GraphStructure
+    rng = np.random.default_rng(2)
+    n, e, F = 500, 6000, 64
+    ei = np.stack([rng.integers(0, n, e), rng.integers(0, n, e)]).astype(np.int32)
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    graph = GraphStructure(cuda(ei), n, n, 0)
+    assert graph.csr.n_hubs == 0
+    out = ops.gather_reduce(cuda(x), graph, "sum").cpu().numpy()
+    want = ref.aggregate("sum", torch.from_numpy(x[ei[0]]), torch.from_numpy(ei[1]), n).numpy()
+    np.testing.assert_array_equal(out, want)
+
+
+def test_gather_reduce_special_values_and_determinism():
+    from keras_geometric_b200 import ops
+    from keras_geometric_b200.graph import GraphStructure
+    rng = np.random.default_rng(9)
+    n, e, F = 40, 300, 8
+    ei = rand_graph(rng, n, n, e)
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    x[3, 2] = np.inf
+    x[5, 1] = -np.inf
+    x[7, 4] = np.nan
+    graph = GraphStructure(cuda(ei), n, n, 0)
+    for op in ["sum", "mean", "max", "min"]:
+        a = ops.gather_reduce(cuda(x), graph, op).cpu().numpy()
+        b = ops.gather_reduce(cuda(x), graph, op).cpu().numpy()
+        np.testing.assert_array_equal(a, b)  # run-to-run identical
+        want = ref.propagate(torch.from_numpy(x), torch.from_numpy(ei), op).numpy()
+        np.testing.assert_allclose(a, want, rtol=1e-5, atol=1e-6, equal_nan=True)
+
+
+def test_fused_epilogue_and_gcn_weights():
+    from keras_geometric_b200 import ops
+    from keras_geometric_b200.graph import GraphStructure
+    rng = np.random.default_rng(4)
+    n, e, F = 300, 4000, 48
+    ei = rand_graph(rng, n, n, e, hub=700)
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    ad = rng.standard_normal((n, F)).astype(np.float32)
+    b = rng.standard_normal(F).astype(np.float32)
+    R = rng.standard_normal((n, F)).astype(np.float32)
+    graph = GraphStructure(cuda(ei), n, n, n)  # with self-loops
+    xg, ag, bg = cuda(x).requires_grad_(True), cuda(ad).requires_grad_(True), cuda(b).requires_grad_(True)
+    out = ops.gather_reduce(xg, graph, "sum", weight="gcn", addend=ag, addend_scale=1.5, bias=bg, act="relu")
+    xo, ao, bo = (torch.from_numpy(t).requires_grad_(True) for t in (x, ad, b))
+    full = ref.add_self_loops(torch.from_numpy(ei), n)
+    w = ref.compute_gcn_normalization(full, n)
+    agg = ref.aggregate("sum", xo[full[0].long()] * w[:, None], full[1], n)
+    want = torch.relu(agg + 1.5 * ao + bo)
+    close(out, want, msg="fused fwd")
+    got = torch.autograd.grad((out * cuda(R)).sum(), [xg, ag, bg])
+    exp = torch.autograd.grad((want * torch.from_numpy(R)).sum(), [xo, ao, bo])
+    for a_, b_, nm in zip(got, exp, ["x", "addend", "bias"]):
+        close(a_, b_, rtol=1e-4, msg="fused grad " + nm)
+    # explicit COO edge weights take the edge_w path
+    wv = rng.random(e + n).astype(np.float32)
+    out2 = ops.gather_reduce(cuda(x), graph, "sum", weight=cuda(wv))
+    want2 = ref.aggregate("sum", torch.from_numpy(x)[full[0].long()] * torch.from_numpy(wv)[:, None], full[1], n)
+    close(out2, want2, msg="edge_w fwd")
+
+
+def test_aggregator_kats_on_device():
+    """The reference's hand-computed KATs (tests/test_message_passing.py:54-155) through the product."""
+    from keras_geometric_b200 import MessagePassing
+    idx = np.array([0, 0, 1], np.int32)
+    r = MessagePassing(aggregator="mean").aggregate(np.array([[1, 2], [3, 4], [5, 6]], np.float32), idx, num_nodes=3)
+    np.testing.assert_allclose(r.cpu().numpy(), [[2, 3], [5, 6], [0, 0]], rtol=1e-5)
+    r = MessagePassing(aggregator="max").aggregate(np.array([[1, 5], [3, 2], [2, 4]], np.float32), idx, num_nodes=3)
+    np.testing.assert_array_equal(r.cpu().numpy(), [[3, 5], [2, 4], [0, 0]])
+    r = MessagePassing(aggregator="sum").aggregate(np.array([[1, 2], [3, 4], [5, 6]], np.float32), idx, num_nodes=3)
+    np.testing.assert_allclose(r.cpu().numpy()[0], [4, 6], rtol=1e-5)
+    r = MessagePassing(aggregator="min").aggregate(np.array([[1, 5], [3, 2], [2, 4]], np.float32), idx, num_nodes=3)
+    np.testing.assert_array_equal(r.cpu().numpy()[0], [1, 2])
+    r = MessagePassing(aggregator="std").aggregate(np.array([[1, 2], [3, 4], [5, 6], [7, 8]], np.float32),
+                                                   np.array([0, 0, 1, 1], np.int32), num_nodes=2)
+    np.testing.assert_allclose(r.cpu().numpy(), [[1, 1], [1, 1]], rtol=1e-5)
+    lyr = MessagePassing(aggregator="mean")
+    assert tuple(lyr.propagate(x=np.zeros((0, 8), np.float32), edge_index=np.zeros((2, 0), np.int32)).shape) == (0, 8)
+    out = lyr.propagate(x=np.random.randn(5, 8).astype(np.float32), edge_index=np.zeros((2, 0), np.int32))
+    np.testing.assert_array_equal(out.cpu().numpy(), np.zeros((5, 8), np.float32))
+    for v in (1e10, 1e-10):
+        o = lyr.aggregate(np.full((100, 10), v, np.float32), np.zeros(100, np.int32), num_nodes=1).cpu().numpy()
+        assert np.isfinite(o).all()
+
+
+def test_golden_aggregators_and_message_passing():
+    from keras_geometric_b200 import MessagePassing
+    from keras_geometric_b200.layers import AggregatorFactory
+    g = load_golden("aggregators")
+    n = int(g["dim_size"])
+    for name in ["mean", "max", "sum", "min", "std"]:
+        out = AggregatorFactory.create(name).aggregate(g["messages"], g["target_idx"], n)
+        np.testing.assert_allclose(out.cpu().numpy(), g["out_" + name], rtol=1e-5, atol=1e-6, equal_nan=True)
+        m = cuda(g["messages_finite"]).requires_grad_(True)
+        o = AggregatorFactory.create(name).aggregate(m, cuda(g["target_idx"]), n)
+        (gr,) = torch.autograd.grad((o * cuda(g["R"])).sum(), [m])
+        close(gr, g["grad_" + name], msg="agg grad " + name)
+    np.testing.assert_array_equal(
+        AggregatorFactory.create("max").aggregate(g["messages"], g["target_idx"], n).cpu().numpy(), g["out_max"])
+    g = load_golden("message_passing")
+    for name in ["mean", "max", "sum", "min", "std"]:
+        x = cuda(g["x"]).requires_grad_(True)
+        out = MessagePassing(aggregator=name).propagate(x=x, edge_index=cuda(g["edge_index"]))
+        close(out, g["out_" + name], msg="propagate " + name)
+        (gx,) = torch.autograd.grad((out * cuda(g["R_" + name])).sum(), [x])
+        close(gx, g["grad_x_" + name], msg="propagate grad " + name)
+    out = MessagePassing(aggregator="sum").propagate(x=(g["bip_x_target"], g["x"]), edge_index=g["bip_edge_index"])
+    close(out, g["bip_out_sum"], msg="bipartite")
+
+
+def test_user_subclass_generic_path():
+    """Overridden hooks force the materialised path (reference tests/test_message_passing.py:256-312)."""
+    from keras_geometric_b200 import MessagePassing
+
+    class Custom(MessagePassing):
+        def message(self, x_i, x_j, **kwargs):
+            return x_j * 2.0 + x_i
+
+        def update(self, aggregated, x=None):
+            return aggregated + x
+
+    rng = np.random.default_rng(8)
+    n, e, F = 30, 200, 6
+    ei = rand_graph(rng, n, n, e)
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    xg = cuda(x).requires_grad_(True)
+    out = Custom(aggregator="mean")([xg, ei])
+    xo = torch.from_numpy(x).requires_grad_(True)
+    want = ref.propagate(xo, torch.from_numpy(ei), "mean", lambda xi, xj: xj * 2.0 + xi, lambda a, x0: a + x0)
+    close(out, want, msg="custom fwd")
+    (gx,) = torch.autograd.grad(out.sum(), [xg])
+    (gw,) = torch.autograd.grad(want.sum(), [xo])
+    close(gx, gw, msg="custom grad")
+
+
+# --------------------------------------------------------------------------------- conv layers
+def _grads(out, R, params):
+    return torch.autograd.grad((out * cuda(R)).sum(), params, allow_unused=True)
+
+
+def _check_grads(grads, g, names, rtol=1e-4):
+    for nm, gr in zip(names, grads):
+        want = g["grad_" + nm]
+        got = gr if gr is not None else torch.zeros(want.shape)
+        close(got.reshape(want.shape), want, rtol=rtol, atol_scale=2e-5, msg="grad " + nm)
+
+
+def _set(p, arr):
+    with torch.no_grad():
+        p.copy_(cuda(arr))
+
+
+@pytest.mark.parametrize("tag", ["default", "nonorm", "noloops_nobias", "E2layout"])
+def test_golden_gcn(tag):
+    from keras_geometric_b200 import GCNConv
+    g = load_golden("gcn_" + tag)
+    layer = GCNConv(**g["params"])
+    x = cuda(g["x"]).requires_grad_(True)
+    layer.build([tuple(g["x"].shape), tuple(g["edge_index"].shape)])
+    layer.built = True
+    _set(layer.kernel, g["w_kernel"])
+    params, names = [x, layer.kernel], ["x", "kernel"]
+    if "w_bias" in g:
+        _set(layer.bias, g["w_bias"])
+        params.append(layer.bias); names.append("bias")
+    out = layer([x, g["edge_index"]])
+    close(out, g["out"], msg="gcn fwd " + tag)
+    _check_grads(_grads(out, g["R"], params), g, names)
+
+
+@pytest.mark.parametrize("tag", ["mean", "max", "sum", "min", "std", "pooling", "mean_noroot_norm", "mean_linear"])
+def test_golden_sage(tag):
+    from keras_geometric_b200 import SAGEConv
+    g = load_golden("sage_" + tag)
+    layer = SAGEConv(**g["params"])
+    x = cuda(g["x"]).requires_grad_(True)
+    layer.build([tuple(g["x"].shape), tuple(g["edge_index"].shape)])
+    layer.built = True
+    _set(layer.lin_neigh.kernel, g["w_lin_neigh"])
+    params, names = [x, layer.lin_neigh.kernel], ["x", "lin_neigh"]
+    if "w_lin_self" in g:
+        _set(layer.lin_self.kernel, g["w_lin_self"]); params.append(layer.lin_self.kernel); names.append("lin_self")
+    if "w_pool_kernel" in g:
+        _set(layer.pool_mlp.kernel, g["w_pool_kernel"]); _set(layer.pool_mlp.bias, g["w_pool_bias"])
+        params += [layer.pool_mlp.kernel, layer.pool_mlp.bias]; names += ["pool_kernel", "pool_bias"]
+    if "w_bias" in g:
+        _set(layer.bias, g["w_bias"]); params.append(layer.bias); names.append("bias")
+    out = layer([x, g["edge_index"]])
+    close(out, g["out"], msg="sage fwd " + tag)
+    _check_grads(_grads(out, g["R"], params), g, names)
+
+
+def test_sage_reordered_fused_path():
+    """output_dim < input_dim with a linear aggregator: aggregate after lin_neigh, epilogue fused."""
+    from keras_geometric_b200 import SAGEConv
+    rng = np.random.default_rng(21)
+    n, e, fin, fout = 400, 5000, 40, 12
+    ei = rand_graph(rng, n, n, e, hub=900)
+    x = rng.standard_normal((n, fin)).astype(np.float32)
+    wn, ws = (rng.standard_normal((fin, fout)).astype(np.float32) * 0.3 for _ in range(2))
+    b = rng.standard_normal(fout).astype(np.float32)
+    R = rng.standard_normal((n, fout)).astype(np.float32)
+    for aggr in ("mean", "sum"):
+        layer = SAGEConv(fout, aggregator=aggr)
+        layer.build([(n, fin), (2, e)]); layer.built = True
+        _set(layer.lin_neigh.kernel, wn); _set(layer.lin_self.kernel, ws); _set(layer.bias, b)
+        xg = cuda(x).requires_grad_(True)
+        out = layer([xg, ei])
+        ts = [torch.from_numpy(t).requires_grad_(True) for t in (x, wn, ws, b)]
+        want = ref.sage_conv(ts[0], torch.from_numpy(ei), ts[1], ts[2], ts[3], aggr, torch.relu)
+        close(out, want, rtol=1e-4, msg="sage reorder " + aggr)
+        got = torch.autograd.grad((out * cuda(R)).sum(), [xg, layer.lin_neigh.kernel, layer.lin_self.kernel, layer.bias])
+        exp = torch.autograd.grad((want * torch.from_numpy(R)).sum(), ts)
+        for a_, b_ in zip(got, exp):
+            close(a_, b_, rtol=1e-4, atol_scale=2e-5, msg="sage reorder grad")
+
+
+@pytest.mark.parametrize("tag", ["sum", "mean_eps", "max"])
+def test_golden_gin(tag):
+    from keras_geometric_b200 import GINConv
+    g = load_golden("gin_" + tag)
+    layer = GINConv(**g["params"])
+    x = cuda(g["x"]).requires_grad_(True)
+    layer.build([tuple(g["x"].shape), tuple(g["edge_index"].shape)])
+    layer.built = True
+    dense = [l for l in layer.mlp.layers if hasattr(l, "kernel")]
+    params, names = [x], ["x"]
+    for i, d in enumerate(dense):
+        _set(d.kernel, g[f"w_mlp{i}_kernel"]); _set(d.bias, g[f"w_mlp{i}_bias"])
+        params += [d.kernel, d.bias]; names += [f"mlp{i}_kernel", f"mlp{i}_bias"]
+    if "w_eps" in g:
+        _set(layer.eps, g["w_eps"]); params.append(layer.eps); names.append("eps")
+    out = layer([x, g["edge_index"]])
+    close(out, g["out"], msg="gin fwd " + tag)
+    _check_grads(_grads(out, g["R"], params), g, names)
+
+
+@pytest.mark.parametrize("tag", ["h4c16", "h8c8", "h1c3", "h2c5_mean", "h3c4_noloops"])
+def test_golden_gatv2(tag):
+    from keras_geometric_b200 import GATv2Conv
+    g = load_golden("gatv2_" + tag)
+    layer = GATv2Conv(**g["params"])
+    x = cuda(g["x"]).requires_grad_(True)
+    layer.build([tuple(g["x"].shape), tuple(g["edge_index"].shape)])
+    layer.built = True
+    _set(layer.linear_transform.kernel, g["w_linear_transform"]); _set(layer.att, g["w_att"])
+    params, names = [x, layer.linear_transform.kernel, layer.att], ["x", "linear_transform", "att"]
+    if "w_bias" in g:
+        _set(layer.bias, g["w_bias"]); params.append(layer.bias); names.append("bias")
+    out = layer([x, g["edge_index"]])
+    close(out, g["out"], msg="gat fwd " + tag)
+    _check_grads(_grads(out, g["R"], params), g, names)
+
+
+@pytest.mark.parametrize("H,C", [(1, 1), (1, 64), (2, 7), (4, 32), (8, 8), (3, 20), (1, 256), (16, 4), (2, 160)])
+def test_gatv2_kernel_vs_oracle(H, C):
+    from keras_geometric_b200 import ops
+    from keras_geometric_b200.graph import GraphStructure
+    rng = np.random.default_rng(H * 100 + C)
+    n, e = 150, 2500
+    ei = rand_graph(rng, n, n, e, hub=600)
+    h = (rng.standard_normal((n, H * C)) * 0.7).astype(np.float32)
+    att = (rng.standard_normal((1, H, C)) * 0.5).astype(np.float32)
+    b = rng.standard_normal(H * C).astype(np.float32)
+    R = rng.standard_normal((n, H * C)).astype(np.float32)
+    graph = GraphStructure(cuda(ei), n, n, n)
+    hg, ag, bg = cuda(h).requires_grad_(True), cuda(att).requires_grad_(True), cuda(b).requires_grad_(True)
+    out = ops.gatv2_aggregate(hg, hg, ag, graph, H, C, 0.2, bg)
+    ho, ao, bo = (torch.from_numpy(t).requires_grad_(True) for t in (h, att, b))
+    want = ref.gatv2_conv(ho, torch.from_numpy(ei), torch.eye(H * C), ao, bo, H, True, 0.2, True)
+    close(out, want, msg=f"gat H={H} C={C}")
+    got = torch.autograd.grad((out * cuda(R)).sum(), [hg, ag, bg])
+    exp = torch.autograd.grad((want * torch.from_numpy(R)).sum(), [ho, ao, bo])
+    for a_, b_, nm in zip(got, exp, ["h", "att", "bias"]):
+        close(a_, b_, rtol=1e-4, atol_scale=2e-5, msg=f"gat grad {nm} H={H} C={C}")
+
+
+def test_gatv2_bipartite_and_dropout_path():
+    from keras_geometric_b200 import GATv2Conv
+    rng = np.random.default_rng(3)
+    xt, xs = rng.standard_normal((9, 6)).astype(np.float32), rng.standard_normal((20, 6)).astype(np.float32)
+    ei = np.stack([rng.integers(0, 20, 50), rng.integers(0, 9, 50)]).astype(np.int32)
+    layer = GATv2Conv(5, heads=2)
+    out = layer.propagate(x=(xt, xs), edge_index=ei)
+    assert tuple(out.shape) == (9, 10)
+    want = None
+    w, att, b = layer.linear_transform.kernel.detach().cpu(), layer.att.detach().cpu(), layer.bias.detach().cpu()
+    hi, hj = torch.from_numpy(xt) @ w, torch.from_numpy(xs) @ w
+    src, dst = torch.from_numpy(ei[0]).long(), torch.from_numpy(ei[1]).long()
+    z = torch.nn.functional.leaky_relu(hi[dst].reshape(-1, 2, 5) + hj[src].reshape(-1, 2, 5), 0.2)
+    s = (z * att).sum(-1)
+    from oracle import keras_ops as kops
+    m = kops.segment_max(s, dst, 9)
+    p = torch.exp(s - m[dst])
+    alpha = p / (kops.segment_sum(p, dst, 9)[dst] + 1e-10)
+    want = kops.segment_sum((alpha.unsqueeze(-1) * hj[src].reshape(-1, 2, 5)).reshape(-1, 10), dst, 9) + b
+    close(out, want, msg="gat bipartite")
+    # dropout path: same expectation when the rate is tiny and training, shape/finite only otherwise
+    lyr = GATv2Conv(4, heads=2, dropout=0.5)
+    o = lyr([rng.standard_normal((20, 6)).astype(np.float32), np.stack([ei[0], ei[0]])], training=True)
+    assert tuple(o.shape) == (20, 8) and torch.isfinite(o).all()
+
+
+def test_layer_reuse_cache_and_inplace_update():
+    """One layer, many graphs (reference tests/unit/test_error_handling.py:335-356) + in-place edits."""
+    from keras_geometric_b200 import GCNConv
+    rng = np.random.default_rng(17)
+    layer = GCNConv(5)
+    for n, e in [(10, 30), (25, 100), (7, 12)]:
+        x = rng.standard_normal((n, 4)).astype(np.float32)
+        ei = np.stack([rng.integers(0, n, e), rng.integers(0, n, e)]).astype(np.int32)
+        out = layer([x, ei])
+        want = ref.gcn_conv(torch.from_numpy(x), torch.from_numpy(ei), layer.kernel.detach().cpu(), layer.bias.detach().cpu())
+        close(out, want, rtol=1e-4, msg="reuse")
+    n = 12
+    x = cuda(rng.standard_normal((n, 4)).astype(np.float32))
+    ei = cuda(np.stack([rng.integers(0, n, 40), rng.integers(0, n, 40)]).astype(np.int32))
+    a = layer([x, ei]).clone()
+    ei[1, :20] = 0  # in-place mutation must invalidate the cached structure
+    b = layer([x, ei])
+    want = ref.gcn_conv(x.cpu(), ei.cpu(), layer.kernel.detach().cpu(), layer.bias.detach().cpu())
+    close(b, want, rtol=1e-4, msg="after in-place edit")
+    assert not torch.allclose(a, b)
+
+
+def test_full_size_properties_products_slice():
+    """Size-independent checks at a scale the oracle cannot reach quickly: linearity of sum,
+    mean(ones) == [deg>0], sum(ones) == in-degree (exact integers), permutation invariance of max."""
+    from keras_geometric_b200 import ops
+    from keras_geometric_b200.graph import GraphStructure
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    n, e, F = 200_000, 5_000_000, 100
+    dst = (torch.rand(e, device="cuda", generator=gen) ** 3 * n).long().clamp_(max=n - 1)
+    src = torch.randint(0, n, (e,), device="cuda", generator=gen)
+    ei = torch.stack([src, dst]).to(torch.int32)
+    graph = GraphStructure(ei, n, n, 0)
+    assert graph.csr.n_hubs > 0
+    ones = torch.ones((n, F), device="cuda")
+    deg = torch.bincount(dst, minlength=n).to(torch.float32)
+    s = ops.gather_reduce(ones, graph, "sum")
+    assert torch.equal(s, deg[:, None].expand(n, F))
+    m = ops.gather_reduce(ones, graph, "mean")
+    assert torch.equal(m, (deg > 0).float()[:, None].expand(n, F))
+    x = torch.randn((n, F), device="cuda", generator=gen)
+    y = torch.randn((n, F), device="cuda", generator=gen)
+    lhs = ops.gather_reduce(x + y, graph, "sum")
+    rhs = ops.gather_reduce(x, graph, "sum") + ops.gather_reduce(y, graph, "sum")
+    assert torch.allclose(lhs, rhs, rtol=1e-4, atol=1e-3)
+    perm = torch.randperm(e, device="cuda", generator=gen)
+    graph2 = GraphStructure(ei[:, perm].contiguous(), n, n, 0)
+    assert torch.equal(ops.gather_reduce(x, graph, "max"), ops.gather_reduce(x, graph2, "max"))
+    # transposed structure: <A x, y> == <x, A^T y>
+    xr = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad((ops.gather_reduce(xr, graph, "sum") * y).sum(), [xr])
+    ref_dot = (ops.gather_reduce(x, graph, "sum") * y).sum()
+    assert torch.allclose((gx * x).sum(), ref_dot, rtol=1e-4)
