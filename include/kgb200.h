@@ -144,6 +144,9 @@ typedef struct kgb_gather_reduce_args {
   int32_t hub_threshold;
   int32_t hub_chunk;
   float* partial;          /* workspace, kgb_gather_reduce_partial_bytes()      */
+  int32_t* work;           /* optional int32[2], ZERO on entry and left zero on exit: dynamic task
+                              queue (load balance on skewed graphs).  One buffer must not be shared
+                              by launches that can overlap in time.  NULL = static striding.     */
 } kgb_gather_reduce_args;
 
 size_t kgb_gather_reduce_partial_bytes(int32_t n_chunks, int32_t F, int32_t op);

@@ -34,6 +34,7 @@ class GatherReduceArgs(Structure):
         ("hub_row", c_void_p), ("hub_chunk_base", c_void_p), ("hub_nchunks", c_void_p),
         ("chunk_hub", c_void_p), ("n_hubs", c_int32), ("n_chunks", c_int32),
         ("hub_threshold", c_int32), ("hub_chunk", c_int32), ("partial", c_void_p),
+        ("work", c_void_p),
     ]
 
 
@@ -85,8 +86,8 @@ def load(build_if_missing: bool = True):
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB
-        if build_if_missing and not _build.is_fresh():
+        path = os.environ.get("KGB200_LIB") or _build.LIB  # KGB200_LIB: tuning builds of the same ABI
+        if path == _build.LIB and build_if_missing and not _build.is_fresh():
             try:
                 _build.build()
             except Exception as e:  # noqa: BLE001

@@ -1,18 +1,23 @@
 // K3/K4/K5/K9: destination-segmented gather-reduce for sm_100a (HBM-bound).
 //
 // Work decomposition
-//   * a "lane group" of G = pow2ceil(F/VEC) <= 32 lanes owns one output row; each lane keeps
+//   * a "lane group" of G = pow2ceil(F/VEC) <= 32 lanes covers one feature row; each lane keeps
 //     NCH vectors (VEC floats, 128-bit loads when VEC = 4) of the row in registers;
-//   * the group loads G column indices (and weights) with one coalesced access, prefetches the
-//     next index batch, and broadcasts them with warp shuffles; U = min(G, 8) independent
-//     feature-row loads are in flight per lane before the first add (memory-level parallelism);
+//   * a task is a block of G consecutive CSR rows.  The group loads the G+1 row pointers once and
+//     then WALKS THE BLOCK'S CONTIGUOUS EDGE RANGE: column indices (and weights) are fetched G at
+//     a time with one coalesced access (the next batch is prefetched), broadcast with shuffles, and
+//     U = 8/NCH feature-row loads per lane are in flight regardless of where row boundaries fall.
+//     Row boundaries only decide when the accumulator is flushed through the epilogue, so short
+//     rows (the common case in power-law graphs) no longer serialise three dependent memory
+//     round trips each - the first version of this kernel did and sat at 19 % DRAM utilisation
+//     (profiles/r01_gather_reduce_v1_raw.csv);
 //   * edges are accumulated in CSR order, i.e. the order a sequential scatter visits them -
 //     results are deterministic (no atomics) and, for unweighted sums of non-hub rows,
 //     identical to the host reference;
-//   * rows above `hub_threshold` edges are cut into chunks of `hub_chunk` edges (scheduled first,
-//     they are the long tasks), reduced into a partial buffer and merged in chunk order by
-//     hub_finish_kernel;
-//   * persistent grid-stride over tasks, grid = min(tasks, SMs * 8 CTAs).
+//   * rows above `hub_threshold` edges are skipped by the walk; they are cut into chunks of
+//     `hub_chunk` edges (scheduled first, they are the long tasks), reduced into a partial buffer
+//     and merged in chunk order by hub_finish_kernel;
+//   * persistent grid-stride over tasks, grid = min(tasks, SMs * resident CTAs).
 #include <math.h>
 
 #include "common.cuh"
@@ -32,6 +37,7 @@ struct GRP {
   const int32_t* chunk_hub;
   int n_hubs; int n_chunks; int hub_threshold; int hub_chunk;
   float* partial; int32_t* partial_arg;
+  int32_t* work;  // [2] zero on entry: dynamic task queue head + finished-CTA count (self-resetting)
 };
 
 template <int VEC, int G, int NCH, bool IS_MAX>
@@ -45,7 +51,7 @@ __device__ __forceinline__ void init_acc(float (&acc)[NCH][VEC], int32_t (&aidx)
     }
 }
 
-template <bool IS_MAX>
+template <bool IS_MAX, bool HAS_W = true>
 __device__ __forceinline__ void accum(float& m, int32_t& a, float v, float w, int32_t c, bool negate) {
   if constexpr (IS_MAX) {
     const float val = negate ? -v : v;
@@ -58,8 +64,45 @@ __device__ __forceinline__ void accum(float& m, int32_t& a, float v, float w, in
       a = -2;  // tie: backward re-walks the row
     }
   } else {
-    m = __fadd_rn(m, __fmul_rn(w, v));  // mul then add, like message*w followed by segment_sum
+    if constexpr (HAS_W) m = __fadd_rn(m, __fmul_rn(w, v));  // mul then add, like message*w then segment_sum
+    else m = __fadd_rn(m, v);
   }
+}
+
+
+// Load the feature rows of U consecutive slots of the current index batch.  Slots past the end of the
+// batch carry index 0 (a valid row) and are simply never accumulated, so the loads need no predicate.
+template <int VEC, int G, int NCH, int U, bool HAS_W>
+__device__ __forceinline__ void load_batch_full(const GRP& p, int32_t myc, float myw, int j, int gl, unsigned gmask,
+                                                const bool (&on)[NCH], float (&v)[U][NCH][VEC], float (&w)[U],
+                                                int32_t (&c)[U]) {
+  // Lanes beyond the row width re-read the row's first vector (same sector as lane 0, no extra traffic)
+  // so every load is unconditional: a predicated load would make v loop-carried and spill.
+  int loff[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) loff[ch] = on[ch] ? (gl + ch * G) * VEC : 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    c[u] = __shfl_sync(gmask, myc, j + u, G);
+    w[u] = 1.f;
+    if constexpr (HAS_W) w[u] = __shfl_sync(gmask, myw, j + u, G);
+    const float* rp = p.x + (int64_t)c[u] * p.ldx;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) ld_vec<VEC>(rp + loff[ch], v[u][ch]);
+  }
+}
+
+// Lanes whose `on` is false accumulate harmless duplicates; they are never stored.
+template <int VEC, int NCH, int U, bool IS_MAX, bool HAS_W>
+__device__ __forceinline__ void accum_all(float (&acc)[NCH][VEC], int32_t (&aidx)[NCH][VEC],
+                                          const float (&v)[U][NCH][VEC], const float (&w)[U], const int32_t (&c)[U],
+                                          const bool (&on)[NCH], bool negate) {
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) accum<IS_MAX, HAS_W>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
 }
 
 // Reduce CSR slots [k0, k1) of one row into acc (all lanes of the group call this together).
@@ -67,7 +110,8 @@ template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
 __device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k1, int gl,
                                              unsigned gmask, const bool (&on)[NCH],
                                              float (&acc)[NCH][VEC], int32_t (&aidx)[NCH][VEC]) {
-  constexpr int U = (G < 8) ? G : 8;
+  constexpr int UMAX = (8 / NCH) < 1 ? 1 : (8 / NCH);
+  constexpr int U = (G < UMAX) ? G : UMAX;
   constexpr bool HAS_W = HAS_EW || HAS_SS;
   const bool negate = p.negate != 0;
   int64_t k = k0;
@@ -89,34 +133,24 @@ __device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k
       if constexpr (HAS_EW) nw = __ldg(p.edge_w + kn + gl);
       if constexpr (HAS_SS) nw = __fmul_rn(nw, __ldg(p.src_scale + nc));
     }
+#pragma unroll 1
     for (int j = 0; j < cnt; j += U) {
       float v[U][NCH][VEC];
       float w[U];
       int32_t c[U];
+      load_batch_full<VEC, G, NCH, U, HAS_W>(p, myc, myw, j, gl, gmask, on, v, w, c);
+      if (j + U <= cnt) {  // group-uniform: a full batch needs no predication
+        accum_all<VEC, NCH, U, IS_MAX, HAS_W>(acc, aidx, v, w, c, on, negate);
+      } else {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        c[u] = __shfl_sync(gmask, myc, j + u, G);
-        w[u] = 1.f;
-        if constexpr (HAS_W) w[u] = __shfl_sync(gmask, myw, j + u, G);
-        const bool ok = (j + u) < cnt;
-        const float* rp = p.x + (int64_t)c[u] * p.ldx;
+        for (int u = 0; u < U; ++u) {
+          if ((j + u) < cnt) {
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          if (ok && on[ch]) {
-            ld_vec<VEC>(rp + (gl + ch * G) * VEC, v[u][ch]);
-          } else {
+            for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) v[u][ch][e] = 0.f;
+              for (int e = 0; e < VEC; ++e)
+                accum<IS_MAX, HAS_W>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
           }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if ((j + u) < cnt) {
-#pragma unroll
-          for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) accum<IS_MAX>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
         }
       }
     }
@@ -133,6 +167,8 @@ __device__ __forceinline__ void epilogue(const GRP& p, int64_t slot, int64_t deg
   const int64_t row_out = p.row_ids ? (int64_t)__ldg(p.row_ids + slot) : slot;
   float os = 1.f;
   if (p.out_scale) os = __ldg(p.out_scale + slot);
+  // mean: sum / max(count, 1e-8) with a true IEEE division like the reference (aggregators.py:77-81);
+  // it runs once per row and element, not per edge
   const float den = fmaxf((float)deg, 1e-8f);
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
@@ -175,9 +211,162 @@ __device__ __forceinline__ void epilogue(const GRP& p, int64_t slot, int64_t deg
   }
 }
 
+// Walk the contiguous edge range of CSR rows [ra, rb) of the block starting at row r0 (group-uniform
+// arguments).  my_hi holds rowptr[r0 + gl + 1] for lane gl of the group.
 template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
-__global__ void __launch_bounds__(256) gather_reduce_kernel(const GRP p) {
+__device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int rb, int64_t k0, int64_t k1,
+                                          int64_t my_hi, int gl, unsigned gmask, const bool (&on)[NCH]) {
+  constexpr int UMAX = (8 / NCH) < 1 ? 1 : (8 / NCH);
+  constexpr int U = (G < UMAX) ? G : UMAX;
+  constexpr bool HAS_W = HAS_EW || HAS_SS;
+  const bool negate = p.negate != 0;
+  float acc[NCH][VEC];
+  int32_t aidx[NCH][VEC];
+  init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
+  int cur = ra;
+  int64_t cur_start = k0;
+  int64_t cur_end = __shfl_sync(gmask, my_hi, cur, G);
+  int64_t k = k0;
+  int32_t myc = 0;
+  float myw = 1.f;
+  if (k + gl < k1) {
+    myc = __ldg(p.col + k + gl);
+    if constexpr (HAS_EW) myw = __ldg(p.edge_w + k + gl);
+    if constexpr (HAS_SS) myw = __fmul_rn(myw, __ldg(p.src_scale + myc));
+  }
+  while (k < k1) {
+    const int64_t rem = k1 - k;
+    const int cnt = rem < G ? (int)rem : G;
+    const int64_t kn = k + G;
+    int32_t nc = 0;
+    float nw = 1.f;
+    if (kn + gl < k1) {  // prefetch the next index batch while this one is consumed
+      nc = __ldg(p.col + kn + gl);
+      if constexpr (HAS_EW) nw = __ldg(p.edge_w + kn + gl);
+      if constexpr (HAS_SS) nw = __fmul_rn(nw, __ldg(p.src_scale + nc));
+    }
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += U) {
+      float v[U][NCH][VEC];
+      float w[U];
+      int32_t c[U];
+      const int64_t kk0 = k + j;
+      load_batch_full<VEC, G, NCH, U, HAS_W>(p, myc, myw, j, gl, gmask, on, v, w, c);
+      if (j + U <= cnt && kk0 + U <= cur_end) {
+        // fast path (group-uniform): a full batch that lies inside the current row
+        accum_all<VEC, NCH, U, IS_MAX, HAS_W>(acc, aidx, v, w, c, on, negate);
+        continue;
+      }
+      // distribute the (up to U) loaded edges over the rows they belong to
+      const int valid = (cnt - j) < U ? (cnt - j) : U;
+      int done = 0;
+      while (true) {
+        const int64_t left = cur_end - (kk0 + done);  // edges of the current row still ahead
+        const int lim = (left < (int64_t)(valid - done)) ? done + (int)left : valid;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (u >= done && u < lim) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+              for (int e = 0; e < VEC; ++e)
+                accum<IS_MAX, HAS_W>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
+          }
+        }
+        done = lim;
+        if (done >= valid) break;
+        // the current row is complete: flush it and move to the next one
+        epilogue<VEC, G, NCH, IS_MAX>(p, r0 + cur, cur_end - cur_start, gl, on, acc, aidx);
+        init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
+        ++cur;
+        cur_start = cur_end;
+        cur_end = __shfl_sync(gmask, my_hi, cur, G);
+      }
+    }
+    myc = nc;
+    myw = nw;
+    k = kn;
+  }
+  // rows that end exactly at k1 (the last one with edges, then any empty rows)
+  while (cur < rb) {
+    epilogue<VEC, G, NCH, IS_MAX>(p, r0 + cur, cur_end - cur_start, gl, on, acc, aidx);
+    init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
+    ++cur;
+    cur_start = cur_end;
+    if (cur < rb) cur_end = __shfl_sync(gmask, my_hi, cur, G);
+  }
+}
+
+
+// Rows handed out per queue fetch (one atomic per warp per UNIT_ROWS rows).
+constexpr int UNIT_ROWS = 128;
+
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
+__device__ __forceinline__ void do_chunk(const GRP& p, int64_t t, int gl, unsigned gmask, const bool (&on)[NCH]) {
+  // one chunk of a hub row -> raw partial
+  float acc[NCH][VEC];
+  int32_t aidx[NCH][VEC];
+  init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
+  const int h = __ldg(p.chunk_hub + t);
+  const int64_t row = __ldg(p.hub_row + h);
+  const int64_t ci = t - __ldg(p.hub_chunk_base + h);
+  const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
+  const int64_t k0 = rs + ci * p.hub_chunk;
+  const int64_t k1 = (k0 + p.hub_chunk < re) ? k0 + p.hub_chunk : re;
+  reduce_range<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, k0, k1, gl, gmask, on, acc, aidx);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (!on[ch]) continue;
+    const int f0 = (gl + ch * G) * VEC;
+    st_vec<VEC>(p.partial + t * (int64_t)p.F + f0, acc[ch]);
+    if constexpr (IS_MAX) st_vec_i<VEC>(p.partial_arg + t * (int64_t)p.F + f0, aidx[ch]);
+  }
+}
+
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
+__device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, int gw, unsigned gmask,
+                                             const bool (&on)[NCH]) {
+  // a block of G consecutive rows: lane gl holds rowptr[r0+gl], rowptr[r0+gl+1]
+  const int64_t left = p.n_rows - r0;
+  const int nr = left < G ? (int)left : G;
+  int64_t my_lo = 0, my_hi = 0;
+  if (gl < nr) {
+    my_lo = __ldg(p.rowptr + r0 + gl);
+    my_hi = __ldg(p.rowptr + r0 + gl + 1);
+  }
+  const bool is_hub = (p.n_hubs > 0) && (gl < nr) && ((my_hi - my_lo) > p.hub_threshold);
+  const unsigned hubmask = (__ballot_sync(gmask, is_hub) & gmask) >> (gw * G);  // group-relative bits
+  int cur = 0;
+  while (cur < nr) {
+    const unsigned m = hubmask >> cur;
+    const int seg_end = m ? cur + __ffs(m) - 1 : nr;  // first hub row at or after cur
+    if (seg_end > cur) {
+      const int64_t k0 = __shfl_sync(gmask, my_lo, cur, G);
+      const int64_t k1 = __shfl_sync(gmask, my_hi, seg_end - 1, G);
+      walk_rows<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, r0, cur, seg_end, k0, k1, my_hi, gl, gmask, on);
+    }
+    cur = seg_end + 1;  // the hub row (if any) is written by hub_finish_kernel
+  }
+}
+
+// resident CTAs per SM the register allocation is tuned for (8 float4 loads in flight per lane)
+#ifndef KGB_GR_MINB_WIDE
+#define KGB_GR_MINB_WIDE 3  // VEC == 4 and G >= 16: the HBM-bound shapes
+#endif
+#ifndef KGB_GR_MINB_NARROW
+#define KGB_GR_MINB_NARROW 4
+#endif
+
+// Tasks: first the hub chunks (the long ones), then units of UNIT_ROWS consecutive rows.  They are
+// handed out by a global queue (one atomicAdd per warp and unit) because static striding correlates
+// with the id structure of power-law graphs (RMAT: the degree depends on the low id bits), which left
+// 27 % of the SM-cycles idle in the first version.  Which warp computes a row never changes the
+// result, so the output stays deterministic.
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
+__global__ void __launch_bounds__(256, ((VEC == 4 && G >= 16) ? KGB_GR_MINB_WIDE : KGB_GR_MINB_NARROW))
+gather_reduce_kernel(const GRP p) {
   constexpr int GPW = 32 / G;
+  constexpr int BPU = UNIT_ROWS / G;  // row blocks per unit
   const int lane = threadIdx.x & 31;
   const int gl = lane % G;
   const int gw = lane / G;
@@ -187,35 +376,41 @@ __global__ void __launch_bounds__(256) gather_reduce_kernel(const GRP p) {
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) on[ch] = (gl + ch * G) < nv;
 
-  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
-  const int64_t n_tasks = (int64_t)p.n_chunks + p.n_rows;
-  const int64_t stride = (int64_t)gridDim.x * gpb;
-  for (int64_t t = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; t < n_tasks; t += stride) {
-    float acc[NCH][VEC];
-    int32_t aidx[NCH][VEC];
-    init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
-    if (t < p.n_chunks) {
-      // one chunk of a hub row -> raw partial
-      const int h = __ldg(p.chunk_hub + t);
-      const int64_t row = __ldg(p.hub_row + h);
-      const int64_t ci = t - __ldg(p.hub_chunk_base + h);
-      const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
-      const int64_t k0 = rs + ci * p.hub_chunk;
-      const int64_t k1 = (k0 + p.hub_chunk < re) ? k0 + p.hub_chunk : re;
-      reduce_range<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, k0, k1, gl, gmask, on, acc, aidx);
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        if (!on[ch]) continue;
-        const int f0 = (gl + ch * G) * VEC;
-        st_vec<VEC>(p.partial + t * (int64_t)p.F + f0, acc[ch]);
-        if constexpr (IS_MAX) st_vec_i<VEC>(p.partial_arg + t * (int64_t)p.F + f0, aidx[ch]);
-      }
+  const int64_t chunk_units = ((int64_t)p.n_chunks + GPW - 1) / GPW;
+  const int64_t row_units = (p.n_rows + UNIT_ROWS - 1) / UNIT_ROWS;
+  const int64_t n_units = chunk_units + row_units;
+  const int64_t wpb = blockDim.x >> 5;
+  int64_t u = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5);  // static fallback when no queue is given
+  while (true) {
+    if (p.work) {
+      __syncwarp();
+      int32_t t = 0;
+      if (lane == 0) t = atomicAdd(p.work, 1);
+      u = __shfl_sync(0xffffffffu, t, 0);
+    }
+    if (u >= n_units) break;
+    if (u < chunk_units) {
+      const int64_t t = u * GPW + gw;
+      if (t < p.n_chunks) do_chunk<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, t, gl, gmask, on);
     } else {
-      const int64_t s = t - p.n_chunks;
-      const int64_t rs = __ldg(p.rowptr + s), re = __ldg(p.rowptr + s + 1);
-      if (p.n_hubs > 0 && (re - rs) > p.hub_threshold) continue;  // merged by hub_finish_kernel
-      reduce_range<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, rs, re, gl, gmask, on, acc, aidx);
-      epilogue<VEC, G, NCH, IS_MAX>(p, s, re - rs, gl, on, acc, aidx);
+      const int64_t base = (u - chunk_units) * UNIT_ROWS;
+      for (int b = gw; b < BPU; b += GPW) {
+        const int64_t r0 = base + (int64_t)b * G;
+        if (r0 < p.n_rows) do_row_block<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, r0, gl, gw, gmask, on);
+      }
+    }
+    if (!p.work) u += (int64_t)gridDim.x * wpb;
+  }
+  if (p.work) {  // the last CTA to finish re-arms the queue for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const int done = atomicAdd(p.work + 1, 1);
+      if (done == (int)gridDim.x - 1) {
+        p.work[0] = 0;
+        p.work[1] = 0;
+        __threadfence();
+      }
     }
   }
 }
@@ -414,8 +609,11 @@ static int grid_for(int device, int64_t tasks, int g) {
 
 template <int VEC, int G, int NCH>
 static int launch_gr(int device, const GRP& p, bool is_max, cudaStream_t st) {
-  const int64_t tasks = (int64_t)p.n_chunks + p.n_rows;
-  const int grid = grid_for(device, tasks, G);
+  // one warp per queue unit at a time; enough CTAs to fill every SM at the tuned residency
+  const int64_t units = ceil_div((int64_t)p.n_chunks, 32 / G) + ceil_div(p.n_rows, (int64_t)UNIT_ROWS);
+  int64_t need = ceil_div(units, 8);
+  const int64_t cap = (int64_t)sm_count(device) * 4;
+  const int grid = (int)(need > cap ? cap : (need < 1 ? 1 : need));
   const bool ew = p.edge_w != nullptr, ss = p.src_scale != nullptr;
   if (is_max) {
     if (ew || ss) { set_error("max/min do not take edge weights"); return KGB_ERR_INVALID; }
@@ -521,6 +719,7 @@ int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t 
     p.n_hubs = hubs ? a->n_hubs : 0; p.n_chunks = hubs ? a->n_chunks : 0;
     p.hub_threshold = a->hub_threshold; p.hub_chunk = a->hub_chunk;
     p.partial = a->partial;
+    p.work = a->work;
     p.partial_arg = nullptr;
     if (hubs && is_max)
       p.partial_arg = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(a->partial) +

@@ -1,0 +1,179 @@
+"""1-D node-partitioned message passing: halo plan + exchange (one process per GPU).
+
+The reference is single-process (no distributed code at all); this module is the
+multi-GPU extension named by the north star.  Rank r owns a contiguous range of target nodes
+with ALL their in-edges, their feature rows and their output rows.  Before each aggregation
+the feature rows of remote sources ("halo") are fetched:
+
+    send_buf = kgb_gather_rows(x_local, send_idx)              (pack, K7)
+    all_to_all_single(x_ext[n_local:], send_buf)               (NCCL over NVLink / NVSwitch)
+    out      = kgb_gather_reduce(x_ext, local CSR)             (columns remapped to [local | halo])
+
+and in the backward the halo gradients travel the reverse way and are summed into the owners'
+rows by a deterministic segmented sum (kgb_gather_reduce over the CSR of send_idx), not by
+atomics.  Degrees (mean / GCN normalisation) need no communication: every in-edge of an owned
+target is local.  The conv layers accept a ``PartitionedGraph`` in place of ``edge_index``.
+
+Works with any torch.distributed backend (tests use gloo on the CPU for the plan logic; the
+exchange of CUDA tensors needs NCCL).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+from torch.autograd.function import once_differentiable
+
+
+def partition_bounds(n_global: int, world: int) -> list:
+    """Contiguous, balanced node ranges: rank r owns [b[r], b[r+1])."""
+    base, extra = divmod(int(n_global), int(world))
+    b = [0]
+    for r in range(world):
+        b.append(b[-1] + base + (1 if r < extra else 0))
+    return b
+
+
+class HaloPlan:
+    """Pure index logic of the exchange (device-agnostic; unit-tested with gloo on the CPU).
+
+    Built from the edges whose TARGET this rank owns (global ids).  Attributes:
+      n_local, n_halo       owned rows / distinct remote source rows
+      col_local  [E_loc]    source ids remapped to [0, n_local) U [n_local, n_local+n_halo)
+      dst_local  [E_loc]    target ids minus the range start
+      halo_global [n_halo]  sorted global ids of the halo rows (grouped by owner because ranges are contiguous)
+      recv_counts [world]   rows this rank receives from each peer   (sum = n_halo)
+      send_counts [world]   rows this rank sends to each peer
+      send_idx [n_send]     local row ids to pack, grouped by destination peer
+    """
+
+    def __init__(self, src_global: torch.Tensor, dst_global: torch.Tensor, n_global: int, rank: int, world: int,
+                 group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.bounds = partition_bounds(n_global, world)
+        lo, hi = self.bounds[rank], self.bounds[rank + 1]
+        self.lo, self.hi = lo, hi
+        self.n_local = hi - lo
+        dev = src_global.device
+        src = src_global.long()
+        dst = dst_global.long()
+        if dst.numel() and (int(dst.min()) < lo or int(dst.max()) >= hi):
+            raise ValueError(f"rank {rank} was given edges whose target is outside its range [{lo}, {hi})")
+        remote = (src < lo) | (src >= hi)
+        halo_global = torch.unique(src[remote])  # sorted
+        self.halo_global = halo_global
+        self.n_halo = int(halo_global.numel())
+        col = src - lo
+        if self.n_halo:
+            pos = torch.searchsorted(halo_global, src[remote])
+            col[remote] = self.n_local + pos
+        self.col_local = col.to(torch.int32)
+        self.dst_local = (dst - lo).to(torch.int32)
+        bnd = torch.tensor(self.bounds, device=dev, dtype=torch.long)
+        owner = torch.bucketize(halo_global, bnd[1:], right=True) if self.n_halo else halo_global
+        self.recv_counts = torch.bincount(owner, minlength=world).tolist() if self.n_halo else [0] * world
+        # tell every owner which of its rows I need
+        recv_c = torch.tensor(self.recv_counts, device=dev, dtype=torch.long)
+        send_c = torch.empty_like(recv_c)
+        if world > 1:
+            dist.all_to_all_single(send_c, recv_c, group=group)
+        else:
+            send_c.copy_(recv_c)
+        self.send_counts = send_c.tolist()
+        want = torch.empty(int(sum(self.send_counts)), device=dev, dtype=torch.long)
+        if world > 1:
+            dist.all_to_all_single(want, halo_global.contiguous(), output_split_sizes=self.send_counts,
+                                   input_split_sizes=self.recv_counts, group=group)
+        self.send_idx = (want - lo).to(torch.int32)
+        if want.numel() and (int(self.send_idx.min()) < 0 or int(self.send_idx.max()) >= self.n_local):
+            raise RuntimeError("halo plan: a peer requested a row this rank does not own")
+        self.n_send = int(self.send_idx.numel())
+
+    def edge_index_local(self) -> torch.Tensor:
+        return torch.stack([self.col_local, self.dst_local]).contiguous()
+
+
+class PartitionedGraph:
+    """Halo plan + device structures of one rank.  Pass it to SAGEConv / GCNConv instead of
+    ``edge_index``; ``x`` is then this rank's [n_local, F] slice of the node features."""
+
+    def __init__(self, src_global, dst_global, n_global: int, rank: int | None = None, world: int | None = None,
+                 group=None, n_loops_local: bool = False):
+        from .graph import GraphStructure, build_csr
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.plan = HaloPlan(src_global, dst_global, n_global, rank, world, group)
+        p = self.plan
+        self.n_local, self.n_halo, self.n_ext = p.n_local, p.n_halo, p.n_local + p.n_halo
+        self.group, self.world, self.rank = group, world, rank
+        self.n_global = int(n_global)
+        ei = p.edge_index_local()
+        # self-loops i->i are local edges on the owned rows (ids [0, n_local) in both spaces)
+        self.graph = GraphStructure(ei, self.n_local, self.n_ext, self.n_local if n_loops_local else 0)
+        # deterministic backward of the pack: CSR of send_idx (which packed rows came from local row r)
+        if p.n_send:
+            s_ei = torch.stack([torch.zeros_like(p.send_idx), p.send_idx]).contiguous()
+            self.send_csr = build_csr(s_ei, self.n_local, 1, 0, by_source=False)
+        else:
+            self.send_csr = None
+        self._dis_ext = None
+
+    # ---- forward/backward exchange ------------------------------------------------------------
+    def exchange(self, x_local: torch.Tensor) -> torch.Tensor:
+        """[n_local, F] -> [n_local + n_halo, F] (autograd-aware)."""
+        return _HaloExchange.apply(x_local, self)
+
+    def exchange_vector(self, v_local: torch.Tensor) -> torch.Tensor:
+        """Per-node scalar (e.g. GCN dis) -> [n_ext]; no autograd."""
+        return _exchange_fwd(v_local.reshape(-1, 1).contiguous(), self).reshape(-1)
+
+    def gcn_dis_ext(self) -> torch.Tensor:
+        """deg^-1/2 for local rows followed by the halo rows' values (fetched once per graph)."""
+        if self._dis_ext is None:
+            from . import _lib
+            from .graph import _stream
+            lib = _lib.load()
+            dis = torch.empty(self.n_local, dtype=torch.float32, device=self.graph.device)
+            _lib.check(lib.kgb_gcn_norm(self.graph.device.index, self.graph.csr.deg.data_ptr(), self.n_local, None,
+                                        0, 0, dis.data_ptr(), None, _stream(self.graph.device)), "kgb_gcn_norm")
+            self._dis_ext = (dis, self.exchange_vector(dis))
+        return self._dis_ext
+
+
+def _exchange_fwd(x_local: torch.Tensor, pg: PartitionedGraph) -> torch.Tensor:
+    from . import ops
+    p = pg.plan
+    F = int(x_local.shape[1])
+    x_ext = torch.empty((pg.n_ext, F), dtype=x_local.dtype, device=x_local.device)
+    x_ext[:pg.n_local].copy_(x_local)
+    if pg.world > 1 and (p.n_send or p.n_halo or True):
+        send = ops.gather_rows(x_local, p.send_idx) if p.n_send else x_local.new_empty((0, F))
+        dist.all_to_all_single(x_ext[pg.n_local:], send, output_split_sizes=p.recv_counts,
+                               input_split_sizes=p.send_counts, group=pg.group)
+    return x_ext
+
+
+class _HaloExchange(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_local, pg: PartitionedGraph):
+        ctx.pg = pg
+        return _exchange_fwd(x_local.contiguous(), pg)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_ext):
+        from . import _lib, ops
+        pg = ctx.pg
+        p = pg.plan
+        g_ext = g_ext.contiguous()
+        g_local = g_ext[:pg.n_local].clone()
+        if pg.world > 1:
+            F = int(g_ext.shape[1])
+            back = torch.empty((p.n_send, F), dtype=g_ext.dtype, device=g_ext.device)
+            dist.all_to_all_single(back, g_ext[pg.n_local:].contiguous(), output_split_sizes=p.send_counts,
+                                   input_split_sizes=p.recv_counts, group=pg.group)
+            if p.n_send:
+                add, _ = ops.gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm)
+                g_local += add
+        return g_local, None

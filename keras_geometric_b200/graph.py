@@ -34,7 +34,7 @@ class Csr:
     ``perm`` int32 [nnz] (original edge id of each slot, stable), ``deg`` int32 [n]."""
 
     __slots__ = ("n_rows", "n_cols", "nnz", "rowptr", "col", "perm", "deg", "hub_row", "hub_chunk_base",
-                 "hub_nchunks", "chunk_hub", "n_hubs", "n_chunks", "_inv_deg", "_partials", "_deg_f")
+                 "hub_nchunks", "chunk_hub", "n_hubs", "n_chunks", "_inv_deg", "_partials", "_deg_f", "_work")
 
     def __init__(self):
         self._inv_deg = None
@@ -43,6 +43,15 @@ class Csr:
         self.n_hubs = 0
         self.n_chunks = 0
         self.hub_row = self.hub_chunk_base = self.hub_nchunks = self.chunk_hub = None
+        self._work = {}
+
+    def work(self, stream_id: int) -> torch.Tensor:
+        """Task-queue counters of kgb_gather_reduce (zero between launches), one pair per stream."""
+        w = self._work.get(stream_id)
+        if w is None:
+            w = torch.zeros(2, dtype=torch.int32, device=self.rowptr.device)
+            self._work[stream_id] = w
+        return w
 
     @property
     def inv_deg(self) -> torch.Tensor:

@@ -116,6 +116,9 @@ class GCNConv(MessagePassing):
             raise ValueError("GCNConv expects inputs to be a list/tuple of [node_features, edge_index]")
         x = to_device_tensor(inputs[0], torch.float32, "node features")
         src_obj = inputs[1]
+        from ..dist import PartitionedGraph
+        if isinstance(src_obj, PartitionedGraph):
+            return self._call_partitioned(x, src_obj, training)
         edge_index = src_obj if isinstance(src_obj, torch.Tensor) and src_obj.is_cuda and src_obj.dtype == torch.int32 \
             and src_obj.dim() == 2 and src_obj.shape[0] == 2 else self._canonical_cached(src_obj)
         num_nodes = int(x.shape[0])
@@ -145,6 +148,21 @@ class GCNConv(MessagePassing):
                                                    size=(num_nodes, num_nodes), training=training))
         aggregated = ops.segment_reduce(messages, graph, "sum")
         return self.post_update(x, self.update(aggregated, x=x))
+
+    def _call_partitioned(self, x, pg, training=None):
+        """1-D node partition: transform locally, exchange the (narrow) transformed halo rows, aggregate.
+        ``pg`` must have been built with ``n_loops_local=self.add_self_loops``."""
+        if self.dropout_rate > 0 and training:
+            raise NotImplementedError("partitioned GCNConv does not support message dropout")
+        if bool(pg.graph.n_loops) != bool(self.add_self_loops):
+            raise ValueError("PartitionedGraph(n_loops_local=...) must match GCNConv(add_self_loops=...)")
+        kernel, bias = value_of(self.kernel), value_of(self.bias) if self.use_bias else None
+        h_ext = pg.exchange(torch.matmul(x, kernel))
+        weight = None
+        if self.normalize:
+            dis_local, dis_ext = pg.gcn_dis_ext()
+            weight = (dis_ext, dis_local)
+        return ops.gather_reduce(h_ext, pg.graph, "sum", weight=weight, bias=bias)
 
     def _canonical_cached(self, edge_index):
         key = (id(edge_index), getattr(edge_index, "_version", None))

@@ -129,6 +129,9 @@ class SAGEConv(MessagePassing):
             raise ValueError("SAGEConv expects inputs to be a list/tuple of [node_features, edge_index]")
         x = to_device_tensor(inputs[0], torch.float32, "node features")
         src_obj = inputs[1]
+        from ..dist import PartitionedGraph
+        if isinstance(src_obj, PartitionedGraph):
+            return self._call_partitioned(x, src_obj, training)
         if isinstance(src_obj, torch.Tensor) and src_obj.is_cuda and src_obj.dtype == torch.int32 \
                 and src_obj.dim() == 2 and src_obj.shape[0] == 2:
             edge_index = src_obj
@@ -172,6 +175,38 @@ class SAGEConv(MessagePassing):
             if self.activation is not None:
                 out = self.activation(out)
         if self.normalize:  # ops.normalize(axis=-1, order=2): x / max(||x||, 1e-12)
+            out = out / torch.clamp(torch.linalg.vector_norm(out, ord=2, dim=-1, keepdim=True), min=1e-12)
+        return out
+
+    def _call_partitioned(self, x, pg, training=None):
+        """Same layer on a 1-D node partition: ``x`` is this rank's [n_local, F] slice, halo rows are
+        exchanged (at the narrower of the two widths for linear aggregators) before the aggregation."""
+        if not self.built:
+            self.build([tuple(x.shape), (2, 0)])
+            self.built = True
+        if self.actual_aggregator not in ("mean", "sum", "max", "min") or (self.dropout_rate > 0 and training):
+            raise NotImplementedError("partitioned SAGEConv supports mean/sum/max/min without dropout")
+        w_neigh = value_of(self.lin_neigh.kernel)
+        w_self = value_of(self.lin_self.kernel) if (self.root_weight and self.lin_self is not None) else None
+        bias = value_of(self.bias) if (self.use_bias and self.bias is not None) else None
+        act_is_relu = self._activation_id == "relu"
+        act_is_none = self._activation_id in (None, "linear")
+        linear_agg = self.actual_aggregator in ("mean", "sum")
+        if linear_agg and self.output_dim < int(x.shape[1]) and (act_is_relu or act_is_none):
+            z_ext = pg.exchange(torch.matmul(x, w_neigh))
+            root = torch.matmul(x, w_self) if w_self is not None else None
+            out = ops.gather_reduce(z_ext, pg.graph, self.actual_aggregator, addend=root, bias=bias,
+                                    act="relu" if act_is_relu else None)
+        else:
+            aggregated = ops.gather_reduce(pg.exchange(x), pg.graph, self.actual_aggregator)
+            out = torch.matmul(aggregated, w_neigh)
+            if w_self is not None:
+                out = torch.matmul(x, w_self) + out
+            if bias is not None:
+                out = out + bias
+            if self.activation is not None:
+                out = self.activation(out)
+        if self.normalize:
             out = out / torch.clamp(torch.linalg.vector_norm(out, ord=2, dim=-1, keepdim=True), min=1e-12)
         return out
 

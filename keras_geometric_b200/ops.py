@@ -73,6 +73,7 @@ def gather_reduce_raw(x: torch.Tensor, csr: Csr, op: int, *, col: torch.Tensor |
         a.n_hubs, a.n_chunks = csr.n_hubs, csr.n_chunks
         a.hub_threshold, a.hub_chunk = HUB_THRESHOLD, HUB_CHUNK
         a.partial = partial.data_ptr()
+    a.work = csr.work(_stream(dev)).data_ptr()
     rec = None
     if PROFILE is not None:
         rec = {"start": torch.cuda.Event(enable_timing=True), "end": torch.cuda.Event(enable_timing=True)}
@@ -141,7 +142,12 @@ class _GatherReduce(torch.autograd.Function):
             if isinstance(weight, str) and weight == "gcn":
                 dis, _ = graph.gcn_norm()
                 kw = {"src_scale": dis, "out_scale": dis}
-                ctx.weight_kind = "gcn"
+                ctx.weight_kind = "scales"
+                ctx.scales = (dis, dis)
+            elif isinstance(weight, tuple):  # (per-source-row scale [n_src], per-target-row scale [n_dst])
+                kw = {"src_scale": weight[0], "out_scale": weight[1]}
+                ctx.weight_kind = "scales"
+                ctx.scales = (weight[0], weight[1])
             else:
                 w = _f32c(weight, "edge weight").reshape(-1)
                 if w.shape[0] != graph.nnz:
@@ -187,9 +193,8 @@ class _GatherReduce(torch.autograd.Function):
             else:
                 csc = graph.csc
                 kw = {}
-                if ctx.weight_kind == "gcn":
-                    dis, _ = graph.gcn_norm()
-                    kw = {"src_scale": dis, "out_scale": dis}
+                if ctx.weight_kind == "scales":  # transposed: targets are gathered, sources are written
+                    kw = {"src_scale": ctx.scales[1], "out_scale": ctx.scales[0]}
                 elif ctx.weight_kind == "edge":
                     kw = {"edge_w": permute_f32(ctx.w_coo, csc.perm)}
                 if op == _lib.OP_MEAN:
@@ -204,7 +209,8 @@ def gather_reduce(x, graph: GraphStructure, op: str = "sum", *, weight=None, add
 
     Equivalent to the reference's ``take(x, src)`` -> message -> ``Aggregator.aggregate`` chain
     (layers/message_passing.py:195-212) without materialising any [E, F] tensor.
-    ``weight``: None, ``"gcn"`` (symmetric normalisation, utils/main.py:20-33) or a COO-ordered
+    ``weight``: None, ``"gcn"`` (symmetric normalisation, utils/main.py:20-33), a
+    ``(src_scale [n_src], dst_scale [n_dst])`` pair (w_e = dst_scale[i] * src_scale[j]) or a COO-ordered
     [nnz] tensor."""
     if op not in _lib.OPS:
         raise ValueError(f"Invalid aggregator: {op}. Available aggregators: {list(_lib.OPS)}")
