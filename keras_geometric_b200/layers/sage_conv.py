@@ -160,22 +160,43 @@ class SAGEConv(MessagePassing):
                    and type(self).message is SAGEConv.message and self._uses_default("aggregate", "update"))
         if reorder:
             graph = get_graph(edge_index, num_nodes, num_nodes, 0)
-            z = torch.matmul(x, w_neigh)
-            root = torch.matmul(x, w_self) if w_self is not None else None
-            out = ops.gather_reduce(z, graph, self.actual_aggregator, addend=root, bias=bias,
-                                    act="relu" if act_is_relu else None)
+            out = self._aggregate_after_transform(x, graph, w_neigh, w_self, bias, act_is_relu)
         else:
             aggregated = self.aggregate_neighbors(x, edge_index, num_nodes, training=training)
-            out = torch.matmul(aggregated, w_neigh)
-            if w_self is not None:
-                x_self = Dropout(self.dropout_rate)(x, training=True) if dropping else x
-                out = torch.matmul(x_self, w_self) + out
-            if bias is not None:
-                out = out + bias
-            if self.activation is not None:
-                out = self.activation(out)
+            out = self._dense_update(aggregated, x, w_neigh, w_self, bias, dropping)
         if self.normalize:  # ops.normalize(axis=-1, order=2): x / max(||x||, 1e-12)
             out = out / torch.clamp(torch.linalg.vector_norm(out, ord=2, dim=-1, keepdim=True), min=1e-12)
+        return out
+
+    def _aggregate_after_transform(self, x, graph, w_neigh, w_self, bias, act_is_relu, exchange=None):
+        """mean/sum commute with lin_neigh: transform first (narrower rows to gather), then ONE kernel does
+        aggregate + root term + bias + ReLU.  The width is padded to a multiple of 4 floats so the gather
+        uses 128-bit loads; the pad columns are exact zeros and are sliced off."""
+        fout = int(w_neigh.shape[1])
+        pad = (-fout) % 4
+        if pad:
+            w_neigh = torch.nn.functional.pad(w_neigh, (0, pad))
+            w_self = torch.nn.functional.pad(w_self, (0, pad)) if w_self is not None else None
+            bias = torch.nn.functional.pad(bias, (0, pad)) if bias is not None else None
+        z = torch.matmul(x, w_neigh)
+        if exchange is not None:
+            z = exchange(z)
+        root = torch.matmul(x, w_self) if w_self is not None else None
+        out = ops.gather_reduce(z, graph, self.actual_aggregator, addend=root, bias=bias,
+                                act="relu" if act_is_relu else None)
+        return out[:, :fout] if pad else out
+
+    def _dense_update(self, aggregated, x, w_neigh, w_self, bias, dropping=False):
+        """act(lin_self(x) + lin_neigh(agg) + b) (sage_conv.py:411-433) as two accumulating GEMMs."""
+        if bias is not None:
+            out = torch.addmm(bias, aggregated, w_neigh)
+        else:
+            out = torch.matmul(aggregated, w_neigh)
+        if w_self is not None:
+            x_self = Dropout(self.dropout_rate)(x, training=True) if dropping else x
+            out = torch.addmm(out, x_self, w_self)
+        if self.activation is not None:
+            out = self.activation(out)
         return out
 
     def _call_partitioned(self, x, pg, training=None):
@@ -193,19 +214,10 @@ class SAGEConv(MessagePassing):
         act_is_none = self._activation_id in (None, "linear")
         linear_agg = self.actual_aggregator in ("mean", "sum")
         if linear_agg and self.output_dim < int(x.shape[1]) and (act_is_relu or act_is_none):
-            z_ext = pg.exchange(torch.matmul(x, w_neigh))
-            root = torch.matmul(x, w_self) if w_self is not None else None
-            out = ops.gather_reduce(z_ext, pg.graph, self.actual_aggregator, addend=root, bias=bias,
-                                    act="relu" if act_is_relu else None)
+            out = self._aggregate_after_transform(x, pg.graph, w_neigh, w_self, bias, act_is_relu, exchange=pg.exchange)
         else:
             aggregated = ops.gather_reduce(pg.exchange(x), pg.graph, self.actual_aggregator)
-            out = torch.matmul(aggregated, w_neigh)
-            if w_self is not None:
-                out = torch.matmul(x, w_self) + out
-            if bias is not None:
-                out = out + bias
-            if self.activation is not None:
-                out = self.activation(out)
+            out = self._dense_update(aggregated, x, w_neigh, w_self, bias)
         if self.normalize:
             out = out / torch.clamp(torch.linalg.vector_norm(out, ord=2, dim=-1, keepdim=True), min=1e-12)
         return out
