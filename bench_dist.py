@@ -10,9 +10,13 @@ import torch
 import torch.distributed as dist
 
 
+NODE_WEIGHT = 24  # cost of one node (dense transforms) in units of one edge (gather), measured on C4
+
+
 def edge_balanced_bounds(dst: torch.Tensor, n_global: int, world: int) -> list:
-    """Contiguous node ranges holding ~equal numbers of in-edges (RMAT ids are heavily skewed)."""
-    deg = torch.bincount(dst.long(), minlength=n_global)
+    """Contiguous node ranges of ~equal cost = in-edges + NODE_WEIGHT * nodes (RMAT ids are heavily skewed,
+    so equal node counts would give one rank most of the edges and equal edge counts most of the GEMM rows)."""
+    deg = torch.bincount(dst.long(), minlength=n_global) + NODE_WEIGHT
     cum = torch.cumsum(deg, 0)
     total = int(cum[-1])
     targets = torch.tensor([total * r // world for r in range(1, world)], device=dst.device)

@@ -204,6 +204,26 @@ int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float
 int kgb_reduce_parts(int device, const float* part, int32_t n_parts, int32_t F, float* out,
                      kgb_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K8  dense node-feature transform on the tensor cores (tcgen05.mma, TMEM accumulators, TMA operands).
+ * Replaces ops.matmul (layers/gcn_conv.py:233,335) and layers.Dense (layers/sage_conv.py:201-221,
+ * layers/gin_conv.py:133-156, layers/gatv2_conv.py:95-101).
+ *   D = alpha * op(A) * op(B) + beta * C          fp32 in / fp32 out, fp32-accurate
+ * (each fp32 operand is split in-kernel into three bf16 terms; five product bands, fp32 accumulate).
+ *   KGB_GEMM_NN: A [M,K] row-major (lda), B [K,N] row-major (ldb)            forward  X * W
+ *   KGB_GEMM_NT: A [M,K] row-major (lda), B stored [N,K] row-major (ldb)     dX = G * W^T
+ *   KGB_GEMM_TN: A stored [K,M] row-major (lda), B [K,N] row-major (ldb)     dW = X^T * G
+ * C/D are [M,N] row-major with leading dimension ldd; C may alias D, may be NULL when beta == 0.
+ * L >= 1 batches with element strides batch_a/b/d (used to split the long reduction of dW).
+ * All pointers 16-byte aligned, all leading dimensions / batch strides multiples of 4 floats.
+ * ------------------------------------------------------------------------------------- */
+enum { KGB_GEMM_NN = 0, KGB_GEMM_NT = 1, KGB_GEMM_TN = 2 };
+size_t kgb_dense_gemm_workspace_bytes(int mode, int M, int N, int K, int L);
+int kgb_dense_gemm(int device, int mode, const float* A, int64_t lda, int64_t batch_a, const float* B,
+                   int64_t ldb, int64_t batch_b, const float* C, float* D, int64_t ldd, int64_t batch_d,
+                   int M, int N, int K, int L, float alpha, float beta, void* ws, size_t ws_bytes,
+                   kgb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

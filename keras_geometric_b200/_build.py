@@ -24,6 +24,20 @@ NVCC_FLAGS = [
 ]
 
 
+def _cutlass_include() -> str | None:
+    """CuTe/CUTLASS header tree vendored in the image (used by the tcgen05 GEMM templates only)."""
+    import sysconfig
+    cands = []
+    for base in {sysconfig.get_paths().get("purelib"), sysconfig.get_paths().get("platlib")}:
+        if base:
+            cands += [os.path.join(base, "flashinfer", "data", "cutlass", "include"),
+                      os.path.join(base, "tilelang", "3rdparty", "cutlass", "include")]
+    for c in cands:
+        if os.path.exists(os.path.join(c, "cutlass", "gemm", "collective", "builders", "sm100_9xBF16_umma_builder.inl")):
+            return c
+    return None
+
+
 def _nvcc() -> str:
     cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(cand):
@@ -47,6 +61,28 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def _file_digest(src: str, cmd) -> str:
+    import re
+    h = hashlib.sha256()
+    deps, todo = [], [src]
+    while todo:  # transitive closure of the quoted includes that live in csrc/ or include/
+        f = todo.pop()
+        if f in deps:
+            continue
+        deps.append(f)
+        with open(f) as fh:
+            for inc in re.findall(r'#include\s+"([^"]+)"', fh.read()):
+                for base in (CSRC, INCLUDE):
+                    cand = os.path.join(base, inc)
+                    if os.path.exists(cand):
+                        todo.append(cand)
+    for f in sorted(deps):
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(cmd).encode())
+    return h.hexdigest()
+
+
 def is_fresh() -> bool:
     stamp = LIB + ".sha256"
     if not (os.path.exists(LIB) and os.path.exists(stamp)):
@@ -64,12 +100,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        extra = []
+        if os.path.basename(src).startswith("dense_gemm_") and not src.endswith("_api.cu"):
+            inc = _cutlass_include()
+            if inc is None:
+                raise RuntimeError("CUTLASS/CuTe headers not found (flashinfer/data/cutlass/include)")
+            extra = ["--expt-relaxed-constexpr", "-I", inc]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        if os.path.exists(obj) and os.path.exists(obj + ".sha"):  # per-object cache: the GEMM templates take minutes
+            with open(obj + ".sha") as fh:
+                if fh.read() == _file_digest(src, cmd):
+                    return obj
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             print(r.stderr)
+        with open(obj + ".sha", "w") as fh:
+            fh.write(_file_digest(src, cmd))
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, len(_sources()))) as ex:

@@ -68,7 +68,12 @@ SIGNATURES = {
                                   c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
     "kgb_reduce_parts": (c_int, [c_int, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "kgb_dense_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "kgb_dense_gemm": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
+                               c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
+                               c_size_t, c_void_p]),
 }
+GEMM_NN, GEMM_NT, GEMM_TN = 0, 1, 2
 
 _lock = threading.Lock()
 _lib = None

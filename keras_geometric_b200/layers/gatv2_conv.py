@@ -105,8 +105,8 @@ class GATv2Conv(MessagePassing):
         if self.linear_transform is None:
             raise RuntimeError("Linear transform layer not built")
         w = value_of(self.linear_transform.kernel)
-        h_i = torch.matmul(x_i, w)
-        h_j = h_i if x_i is x_j else torch.matmul(x_j, w)
+        h_i = ops.linear(x_i, w)
+        h_j = h_i if x_i is x_j else ops.linear(x_j, w)
         graph = get_graph(edge_index, n, n_src, n_loops)
         att = value_of(self.att)
         bias = value_of(self.bias) if (self.use_bias and self.bias is not None) else None

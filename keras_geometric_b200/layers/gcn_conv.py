@@ -137,7 +137,7 @@ class GCNConv(MessagePassing):
         self._current_training = training
         fast = (not dropping) and type(self).message is GCNConv.message and type(self).update is GCNConv.update
         if fast:
-            h = torch.matmul(x, kernel)  # dense transform once per node (tensor-core path: K8)
+            h = ops.linear(x, kernel)  # dense transform once per node on the tensor cores (K8)
             return ops.gather_reduce(h, graph, "sum", weight="gcn" if self.normalize else None, bias=bias)
         # per-edge path: dropout on the transformed messages (gcn_conv.py:238-242) or user overrides
         w = graph.gcn_norm()[1] if self.normalize else torch.ones(graph.nnz, dtype=x.dtype, device=x.device)
@@ -157,7 +157,7 @@ class GCNConv(MessagePassing):
         if bool(pg.graph.n_loops) != bool(self.add_self_loops):
             raise ValueError("PartitionedGraph(n_loops_local=...) must match GCNConv(add_self_loops=...)")
         kernel, bias = value_of(self.kernel), value_of(self.bias) if self.use_bias else None
-        h_ext = pg.exchange(torch.matmul(x, kernel))
+        h_ext = pg.exchange(ops.linear(x, kernel))
         weight = None
         if self.normalize:
             dis_local, dis_ext = pg.gcn_dis_ext()

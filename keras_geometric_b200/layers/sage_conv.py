@@ -178,23 +178,22 @@ class SAGEConv(MessagePassing):
             w_neigh = torch.nn.functional.pad(w_neigh, (0, pad))
             w_self = torch.nn.functional.pad(w_self, (0, pad)) if w_self is not None else None
             bias = torch.nn.functional.pad(bias, (0, pad)) if bias is not None else None
-        z = torch.matmul(x, w_neigh)
+        z = ops.linear(x, w_neigh)
         if exchange is not None:
             z = exchange(z)
-        root = torch.matmul(x, w_self) if w_self is not None else None
+        root = ops.linear(x, w_self) if w_self is not None else None
         out = ops.gather_reduce(z, graph, self.actual_aggregator, addend=root, bias=bias,
                                 act="relu" if act_is_relu else None)
         return out[:, :fout] if pad else out
 
     def _dense_update(self, aggregated, x, w_neigh, w_self, bias, dropping=False):
         """act(lin_self(x) + lin_neigh(agg) + b) (sage_conv.py:411-433) as two accumulating GEMMs."""
-        if bias is not None:
-            out = torch.addmm(bias, aggregated, w_neigh)
-        else:
-            out = torch.matmul(aggregated, w_neigh)
+        out = ops.linear(aggregated, w_neigh)
         if w_self is not None:
             x_self = Dropout(self.dropout_rate)(x, training=True) if dropping else x
-            out = torch.addmm(out, x_self, w_self)
+            out = ops.linear(x_self, w_self, addend=out)  # accumulates in the GEMM epilogue (beta = 1)
+        if bias is not None:
+            out = out + bias
         if self.activation is not None:
             out = self.activation(out)
         return out

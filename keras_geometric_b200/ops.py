@@ -349,3 +349,104 @@ def gatv2_aggregate(h_src, h_dst, att, graph: GraphStructure, heads: int, channe
     (reference: layers/gatv2_conv.py:241-335).  ``h_*`` are [N, H*C], ``att`` has H*C entries;
     returns [n_dst, H*C] (+ bias when given)."""
     return _GatV2.apply(h_src, h_dst, att.reshape(-1), bias, graph, int(heads), int(channels), float(negative_slope))
+
+
+# ------------------------------------------------------------------------------------------ K8
+_GEMM_WS = {}
+
+
+def _gemm_ws(dev):
+    ws = _GEMM_WS.get(dev)
+    if ws is None:
+        ws = torch.empty(_lib.load().kgb_dense_gemm_workspace_bytes(0, 0, 0, 0, 1), dtype=torch.uint8, device=dev)
+        _GEMM_WS[dev] = ws
+    return ws
+
+
+def _gemm_ok(*tensors) -> bool:
+    for t in tensors:
+        if t is None:
+            continue
+        if t.dtype != torch.float32 or not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
+            return False
+        if t.data_ptr() % 16 or t.stride(0) % 4 or t.shape[1] % 4:
+            return False
+    return True
+
+
+def dense_gemm(mode: int, a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, c=None, out=None,
+               beta: float = 0.0, alpha: float = 1.0, L: int = 1, batch=(0, 0, 0)) -> torch.Tensor:
+    """One kgb_dense_gemm launch (tcgen05, fp32-accurate).  ``a``/``b`` are the stored operands of ``mode``."""
+    lib = _lib.load()
+    dev = a.device
+    if out is None:
+        out = torch.empty((M, N) if L == 1 else (L, M, N), dtype=torch.float32, device=dev)
+    ws = _gemm_ws(dev)
+    ldd = out.stride(-2)
+    _lib.check(lib.kgb_dense_gemm(dev.index, mode, a.data_ptr(), a.stride(0), batch[0], b.data_ptr(), b.stride(0),
+                                  batch[1], _ptr(c), out.data_ptr(), ldd, batch[2], M, N, K, L, float(alpha),
+                                  float(beta), ws.data_ptr(), ws.numel(), _stream(dev)), "kgb_dense_gemm")
+    return out
+
+
+_SPLIT_ROWS = 8192  # rows of the long (node) dimension reduced by one CTA column in dW = X^T G
+
+
+class _Linear(torch.autograd.Function):
+    """out = x @ w (+ addend) on the tensor cores (K8); falls back to torch.matmul (cuBLAS, on the GPU) only for
+    shapes the TMA alignment rules exclude (a dimension not divisible by 4)."""
+
+    @staticmethod
+    def forward(ctx, x, w, addend):
+        x = _f32c(x, "x")
+        w = _f32c(w, "w")
+        ctx.fast = _gemm_ok(x, w, addend) and x.shape[0] > 0
+        if ctx.fast:
+            M, K, N = int(x.shape[0]), int(x.shape[1]), int(w.shape[1])
+            out = dense_gemm(_lib.GEMM_NN, x, w, M, N, K, c=addend, beta=1.0 if addend is not None else 0.0)
+        else:
+            out = torch.matmul(x, w)
+            if addend is not None:
+                out = out + addend
+        ctx.save_for_backward(x, w)
+        ctx.has_addend = addend is not None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = _f32c(g, "grad")
+        if g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
+            g = g.contiguous()
+        gx = gw = None
+        M, K, N = int(x.shape[0]), int(x.shape[1]), int(w.shape[1])
+        fast = ctx.fast and _gemm_ok(g)
+        if ctx.needs_input_grad[0]:
+            gx = dense_gemm(_lib.GEMM_NT, g, w, M, K, N) if fast else torch.matmul(g, w.t())
+        if ctx.needs_input_grad[1]:
+            if fast:
+                # dW[K,N] = X^T G: the reduction runs over the M nodes; cut it into slices that become the batch
+                # mode of one launch, then add the partials in slice order (deterministic, no atomics)
+                S = _SPLIT_ROWS
+                L, rem = divmod(M, S)
+                parts = torch.empty((L + (1 if rem else 0), K, N), dtype=torch.float32, device=x.device)
+                if L:
+                    dense_gemm(_lib.GEMM_TN, x, g, K, N, S, out=parts[:L], L=L,
+                               batch=(S * x.stride(0), S * g.stride(0), K * N))
+                if rem:
+                    dense_gemm(_lib.GEMM_TN, x[L * S:], g[L * S:], K, N, rem, out=parts[L])
+                if parts.shape[0] == 1:
+                    gw = parts[0]
+                else:
+                    gw = torch.empty((K, N), dtype=torch.float32, device=x.device)
+                    _lib.check(_lib.load().kgb_reduce_parts(x.device.index, parts.data_ptr(), parts.shape[0], K * N,
+                                                            gw.data_ptr(), _stream(x.device)), "kgb_reduce_parts")
+            else:
+                gw = torch.matmul(x.t(), g)
+        return gx, gw, (g if ctx.has_addend else None)
+
+
+def linear(x, w, addend=None) -> torch.Tensor:
+    """x @ w (+ addend) - the dense node-feature transform of every conv layer (K8)."""
+    return _Linear.apply(x, w, addend)

@@ -483,3 +483,24 @@ def test_full_size_properties_products_slice():
     (gx,) = torch.autograd.grad((ops.gather_reduce(xr, graph, "sum") * y).sum(), [xr])
     ref_dot = (ops.gather_reduce(x, graph, "sum") * y).sum()
     assert torch.allclose((gx * x).sum(), ref_dot, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------- K8
+@pytest.mark.parametrize("M,K,N", [(1, 4, 4), (300, 100, 256), (5000, 256, 48), (20001, 48, 256), (70000, 64, 64),
+                                   (513, 12, 7), (1000, 1433, 16)])
+def test_linear_tensor_core_gemm(M, K, N):
+    """X @ W (+ addend) and its two gradient GEMMs vs float64; shapes with a dimension not divisible by 4 take the
+    library fallback on the GPU and must agree as well."""
+    from keras_geometric_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(M + K + N)
+    x = torch.randn((M, K), device="cuda", generator=gen, requires_grad=True)
+    w = (torch.randn((K, N), device="cuda", generator=gen) * 0.2).requires_grad_(True)
+    ad = torch.randn((M, N), device="cuda", generator=gen, requires_grad=True)
+    R = torch.randn((M, N), device="cuda", generator=gen)
+    out = ops.linear(x, w, addend=ad)
+    gx, gw, gad = torch.autograd.grad((out * R).sum(), [x, w, ad])
+    x64, w64 = x.detach().double(), w.detach().double()
+    close(out, (x64 @ w64 + ad.detach().double()).float(), rtol=1e-5, atol_scale=2e-6, msg="gemm fwd")
+    close(gx, (R.double() @ w64.t()).float(), rtol=1e-5, atol_scale=2e-6, msg="gemm dX")
+    close(gw, (x64.t() @ R.double()).float(), rtol=1e-5, atol_scale=2e-6, msg="gemm dW")
+    close(gad, R, msg="gemm d addend")
