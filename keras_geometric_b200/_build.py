@@ -55,9 +55,9 @@ def _digest() -> str:
     files.append(os.path.join(INCLUDE, "kgb200.h"))
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())  # location-independent: the tree is copied to the GPU box
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS).replace(ROOT, "<root>").encode())
     return h.hexdigest()
 
 
@@ -79,7 +79,12 @@ def _file_digest(src: str, cmd) -> str:
     for f in sorted(deps):
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(cmd).encode())
+    import sysconfig
+    norm = " ".join(cmd).replace(ROOT, "<root>")
+    for base in {sysconfig.get_paths().get("purelib"), sysconfig.get_paths().get("platlib")}:
+        if base:
+            norm = norm.replace(base, "<site>")
+    h.update(norm.encode())
     return h.hexdigest()
 
 
@@ -97,6 +102,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = _nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
+    # one builder at a time (several ranks may import the package at once)
+    import fcntl
+    lock = open(os.path.join(OBJ_DIR, ".lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and is_fresh():
+            return LIB
+        return _build_locked(nvcc, force, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc: str, force: bool, verbose: bool) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
@@ -122,10 +141,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(_sources()))) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs
+    tmp = LIB + ".tmp"
+    cmd = [nvcc, "-shared", "-o", tmp] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)  # atomic: a concurrent loader never sees a half-written library
     with open(LIB + ".sha256", "w") as fh:
         fh.write(_digest())
     return LIB

@@ -122,7 +122,18 @@ class PartitionedGraph:
     # ---- forward/backward exchange ------------------------------------------------------------
     def exchange(self, x_local: torch.Tensor) -> torch.Tensor:
         """[n_local, F] -> [n_local + n_halo, F] (autograd-aware)."""
-        return _HaloExchange.apply(x_local, self)
+        return _HaloExchange.apply(x_local, self, False)
+
+    def exchange_start(self, x_local: torch.Tensor) -> torch.Tensor:
+        """Like ``exchange`` but the all-to-all is left in flight on NCCL's stream so that work which does not
+        need the halo rows (the root-weight GEMM) overlaps it.  Call ``exchange_finish`` before the first use of
+        the returned tensor's halo rows."""
+        return _HaloExchange.apply(x_local, self, True)
+
+    def exchange_finish(self) -> None:
+        w, self._pending = getattr(self, "_pending", None), None
+        if w is not None:
+            w.wait()  # orders the current stream after the collective
 
     def exchange_vector(self, v_local: torch.Tensor) -> torch.Tensor:
         """Per-node scalar (e.g. GCN dis) -> [n_ext]; no autograd."""
@@ -141,24 +152,28 @@ class PartitionedGraph:
         return self._dis_ext
 
 
-def _exchange_fwd(x_local: torch.Tensor, pg: PartitionedGraph) -> torch.Tensor:
+def _exchange_fwd(x_local: torch.Tensor, pg: PartitionedGraph, in_flight: bool = False) -> torch.Tensor:
     from . import ops
     p = pg.plan
     F = int(x_local.shape[1])
     x_ext = torch.empty((pg.n_ext, F), dtype=x_local.dtype, device=x_local.device)
-    x_ext[:pg.n_local].copy_(x_local)
-    if pg.world > 1 and (p.n_send or p.n_halo or True):
+    if pg.world > 1:
         send = ops.gather_rows(x_local, p.send_idx) if p.n_send else x_local.new_empty((0, F))
-        dist.all_to_all_single(x_ext[pg.n_local:], send, output_split_sizes=p.recv_counts,
-                               input_split_sizes=p.send_counts, group=pg.group)
+        work = dist.all_to_all_single(x_ext[pg.n_local:], send, output_split_sizes=p.recv_counts,
+                                      input_split_sizes=p.send_counts, group=pg.group, async_op=in_flight)
+        if in_flight:
+            pg.exchange_finish()
+            pg._pending = work
+            pg._pending_send = send  # keep the packed buffer alive until the collective has consumed it
+    x_ext[:pg.n_local].copy_(x_local)
     return x_ext
 
 
 class _HaloExchange(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_local, pg: PartitionedGraph):
+    def forward(ctx, x_local, pg: PartitionedGraph, in_flight: bool = False):
         ctx.pg = pg
-        return _exchange_fwd(x_local.contiguous(), pg)
+        return _exchange_fwd(x_local.contiguous(), pg, in_flight)
 
     @staticmethod
     @once_differentiable
@@ -176,4 +191,4 @@ class _HaloExchange(torch.autograd.Function):
             if p.n_send:
                 add, _ = ops.gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm)
                 g_local += add
-        return g_local, None
+        return g_local, None, None

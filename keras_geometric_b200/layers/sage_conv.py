@@ -180,8 +180,10 @@ class SAGEConv(MessagePassing):
             bias = torch.nn.functional.pad(bias, (0, pad)) if bias is not None else None
         z = ops.linear(x, w_neigh)
         if exchange is not None:
-            z = exchange(z)
+            z = exchange[0](z)          # halo all-to-all left in flight ...
         root = ops.linear(x, w_self) if w_self is not None else None
+        if exchange is not None:
+            exchange[1]()               # ... while the root transform runs
         out = ops.gather_reduce(z, graph, self.actual_aggregator, addend=root, bias=bias,
                                 act="relu" if act_is_relu else None)
         return out[:, :fout] if pad else out
@@ -213,10 +215,18 @@ class SAGEConv(MessagePassing):
         act_is_none = self._activation_id in (None, "linear")
         linear_agg = self.actual_aggregator in ("mean", "sum")
         if linear_agg and self.output_dim < int(x.shape[1]) and (act_is_relu or act_is_none):
-            out = self._aggregate_after_transform(x, pg.graph, w_neigh, w_self, bias, act_is_relu, exchange=pg.exchange)
+            out = self._aggregate_after_transform(x, pg.graph, w_neigh, w_self, bias, act_is_relu,
+                                                   exchange=(pg.exchange_start, pg.exchange_finish))
         else:
-            aggregated = ops.gather_reduce(pg.exchange(x), pg.graph, self.actual_aggregator)
-            out = self._dense_update(aggregated, x, w_neigh, w_self, bias)
+            x_ext = pg.exchange_start(x)                      # all-to-all in flight ...
+            root = ops.linear(x, w_self) if w_self is not None else None   # ... behind the root transform
+            pg.exchange_finish()
+            aggregated = ops.gather_reduce(x_ext, pg.graph, self.actual_aggregator)
+            out = ops.linear(aggregated, w_neigh, addend=root)
+            if bias is not None:
+                out = out + bias
+            if self.activation is not None:
+                out = self.activation(out)
         if self.normalize:
             out = out / torch.clamp(torch.linalg.vector_norm(out, ord=2, dim=-1, keepdim=True), min=1e-12)
         return out
