@@ -179,10 +179,26 @@ int kgb_gather_rows(int device, const float* src, int64_t lds, const int32_t* id
  * One pass over the CSR with an online max/sum; rowmax/rowden ([n_dst,H]) are saved for the
  * backward, which recomputes alpha instead of storing [nnz,H] tensors.
  * ------------------------------------------------------------------------------------- */
+/* Hub table of the structure a GATv2 kernel walks (from kgb_csr_hubs) + its workspaces.  Optional:
+ * NULL (or n_hubs == 0) makes one lane group reduce every row whole. */
+typedef struct kgb_hub_table {
+  const int32_t* hub_row;
+  const int32_t* hub_chunk_base;
+  const int32_t* hub_nchunks;
+  const int32_t* chunk_hub;
+  int32_t n_hubs;
+  int32_t n_chunks;
+  int32_t threshold;
+  int32_t chunk;
+  float* partial;   /* kgb_gatv2_partial_bytes(n_chunks, H, C) bytes                              */
+  int32_t* work;    /* optional int32[64], zero on entry / left zero: dynamic task queue scratch */
+} kgb_hub_table;
+size_t kgb_gatv2_partial_bytes(int32_t n_chunks, int32_t H, int32_t C);
+
 int kgb_gatv2_fwd(int device, const float* hsrc, const float* hdst, int64_t n_src, int64_t n_dst,
                   int32_t H, int32_t C, const float* att, float slope,
                   const int64_t* rowptr, const int32_t* col, const float* bias,
-                  float* out, float* rowmax, float* rowden, kgb_stream_t stream);
+                  float* out, float* rowmax, float* rowden, const kgb_hub_table* hubs, kgb_stream_t stream);
 /* Backward, pass 1 over the forward CSR (per target): g_hdst[i] (written), r[i,h] =
  * sum_c g[i,h,c] * agg[i,h,c] (written, workspace [n_dst,H]) and the attention-vector
  * gradient partials g_att_part [n_parts, H*C] (n_parts from kgb_gatv2_bwd_parts()).
@@ -193,13 +209,13 @@ int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float*
                       const float* att, float slope, const int64_t* rowptr, const int32_t* col,
                       const float* rowmax, const float* rowden,
                       float* g_hdst, float* r, float* g_att_part, int32_t n_parts,
-                      kgb_stream_t stream);
+                      const kgb_hub_table* hubs, kgb_stream_t stream);
 /* Backward, pass 2 over the transposed structure (per source): g_hsrc[j] (written). */
 int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float* hdst,
                       int64_t n_src, int64_t n_dst, int32_t H, int32_t C, const float* att,
                       float slope, const int64_t* colptr, const int32_t* row,
                       const float* rowmax, const float* rowden, const float* r,
-                      float* g_hsrc, kgb_stream_t stream);
+                      float* g_hsrc, const kgb_hub_table* hubs, kgb_stream_t stream);
 /* out[f] = sum_p part[p,f]  in fixed order (deterministic reduction of partials). */
 int kgb_reduce_parts(int device, const float* part, int32_t n_parts, int32_t F, float* out,
                      kgb_stream_t stream);

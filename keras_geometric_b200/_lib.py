@@ -38,6 +38,14 @@ class GatherReduceArgs(Structure):
     ]
 
 
+class HubTable(Structure):
+    """Mirror of ``struct kgb_hub_table`` (include/kgb200.h)."""
+
+    _fields_ = [("hub_row", c_void_p), ("hub_chunk_base", c_void_p), ("hub_nchunks", c_void_p),
+                ("chunk_hub", c_void_p), ("n_hubs", c_int32), ("n_chunks", c_int32), ("threshold", c_int32),
+                ("chunk", c_int32), ("partial", c_void_p), ("work", c_void_p)]
+
+
 # name -> (restype, argtypes); every name declared in include/kgb200.h must appear here
 SIGNATURES = {
     "kgb_version": (c_int, []),
@@ -58,15 +66,17 @@ SIGNATURES = {
                                    c_void_p]),
     "kgb_gather_rows": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_float, c_void_p, c_int64,
                                 c_void_p]),
+    "kgb_gatv2_partial_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "kgb_gatv2_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_float,
-                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(HubTable),
+                              c_void_p]),
     "kgb_gatv2_bwd_parts": (c_int, [c_int, c_int64, c_int32, c_int32]),
     "kgb_gatv2_bwd_dst": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
                                   c_int32, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_int32, c_void_p]),
+                                  c_void_p, c_void_p, c_int32, POINTER(HubTable), c_void_p]),
     "kgb_gatv2_bwd_src": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
                                   c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p]),
+                                  POINTER(HubTable), c_void_p]),
     "kgb_reduce_parts": (c_int, [c_int, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "kgb_dense_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "kgb_dense_gemm": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,

@@ -60,8 +60,9 @@ __device__ __forceinline__ void accum(float& m, int32_t& a, float v, float w, in
     } else if (val > m) {
       m = val;
       a = c;
-    } else if (val == m) {
-      a = -2;  // tie: backward re-walks the row
+    } else if (val == m && c != a) {
+      a = -2;  // tie between different sources: backward re-walks the row.  Parallel edges from the same
+               // source are not a tie: their even shares add up to the whole gradient on that one row.
     }
   } else {
     if constexpr (HAS_W) m = __fadd_rn(m, __fmul_rn(w, v));  // mul then add, like message*w then segment_sum
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(256) hub_finish_kernel(const GRP p) {
             float& m = acc[ch][e];
             if (v[e] != v[e]) m = v[e];
             else if (v[e] > m) { m = v[e]; aidx[ch][e] = pa[e]; }
-            else if (v[e] == m && pa[e] != -1) aidx[ch][e] = -2;
+            else if (v[e] == m && pa[e] != -1 && pa[e] != aidx[ch][e]) aidx[ch][e] = -2;
           }
         } else {
 #pragma unroll

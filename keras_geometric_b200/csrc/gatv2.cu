@@ -11,8 +11,13 @@
 // each edge costs one row gather.  m and l are saved per (row, head); the backward recomputes
 // alpha from them instead of storing [nnz, H] tensors.
 // Backward: pass 1 walks the forward CSR (per target: g_hdst, r, d att), pass 2 walks the
-// transposed structure (per source: g_hsrc).  No atomics; d att goes through per-CTA partials
-// that are summed in fixed order.
+// transposed structure (per source: g_hsrc).  No float atomics; d att goes through per-CTA
+// partials that are summed in fixed order.
+//
+// Scheduling (all three kernels): rows above the hub threshold are cut into chunks whose partial
+// softmax states (m, l, acc) / partial gradient sums are merged in chunk order by a finish kernel;
+// chunks first, then 64-row units, handed out by a self-resetting atomic queue (power-law graphs:
+// a static stride correlates with the id structure, and one 10^5-edge row would serialise a warp).
 #include <math.h>
 
 #include "common.cuh"
@@ -30,6 +35,12 @@ struct GatP {
   // backward
   const float* g; const float* agg; const float* r_in;
   float* g_hdst; float* r_out; float* g_att_part; float* g_hsrc;
+  // hub table of the structure being walked + workspaces
+  const int32_t* hub_row; const int32_t* hub_chunk_base; const int32_t* hub_nchunks; const int32_t* chunk_hub;
+  int n_hubs; int n_chunks; int hub_threshold; int hub_chunk;
+  float* partial;  // fwd: acc [n_chunks,HC] | m [n_chunks,H] | l [n_chunks,H];  bwd: sums [n_chunks,HC]
+  int32_t* work;   // [2 * gridDim.y] zero on entry (queue head, finished CTAs) or NULL
+  int64_t n_rows;  // rows of the walked structure
 };
 
 template <int LPH>
@@ -39,245 +50,383 @@ __device__ __forceinline__ float head_sum(float v, unsigned gmask) {
   return v;
 }
 
+constexpr int GAT_UNIT_ROWS = 64;
+
+// Hands (chunk | row) tasks to the lane groups of the CTA; see the header comment.
+template <int G, class FC, class FR>
+__device__ __forceinline__ void gat_schedule(const GatP& p, FC&& on_chunk, FR&& on_row) {
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gw = lane / G;
+  const int64_t chunk_units = ((int64_t)p.n_chunks + GPW - 1) / GPW;
+  const int64_t row_units = (p.n_rows + GAT_UNIT_ROWS - 1) / GAT_UNIT_ROWS;
+  const int64_t n_units = chunk_units + row_units;
+  const int64_t wpb = blockDim.x >> 5;
+  int32_t* work = p.work ? p.work + 2 * blockIdx.y : nullptr;
+  int64_t u = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5);
+  while (true) {
+    if (work) {
+      __syncwarp();
+      int32_t t = 0;
+      if (lane == 0) t = atomicAdd(work, 1);
+      u = __shfl_sync(0xffffffffu, t, 0);
+    }
+    if (u >= n_units) break;
+    if (u < chunk_units) {
+      const int64_t t = u * GPW + gw;
+      if (t < p.n_chunks) {
+        const int h = __ldg(p.chunk_hub + t);
+        const int64_t row = __ldg(p.hub_row + h);
+        const int64_t ci = t - __ldg(p.hub_chunk_base + h);
+        const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
+        const int64_t k0 = rs + ci * p.hub_chunk;
+        const int64_t k1 = (k0 + p.hub_chunk < re) ? k0 + p.hub_chunk : re;
+        on_chunk(t, row, k0, k1, ci == 0);
+      }
+    } else {
+      const int64_t base = (u - chunk_units) * GAT_UNIT_ROWS;
+      const int64_t lim = (base + GAT_UNIT_ROWS < p.n_rows) ? base + GAT_UNIT_ROWS : p.n_rows;
+      for (int64_t row = base + gw; row < lim; row += GPW) {
+        const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
+        if (p.n_hubs > 0 && (re - rs) > p.hub_threshold) continue;  // merged by the finish kernel
+        on_row(row, rs, re);
+      }
+    }
+    if (!work) u += (int64_t)gridDim.x * wpb;
+  }
+}
+
+__device__ __forceinline__ void gat_queue_reset(const GatP& p) {
+  if (p.work) {  // the last CTA of this head block re-arms the queue for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int32_t* work = p.work + 2 * blockIdx.y;
+      __threadfence();
+      const int done = atomicAdd(work + 1, 1);
+      if (done == (int)gridDim.x - 1) {
+        work[0] = 0;
+        work[1] = 0;
+        __threadfence();
+      }
+    }
+  }
+}
+
+// Per-lane constants shared by all kernels.
 template <int VEC, int LPH, int CC, int HPG>
-struct Lay {
+struct LaneCtx {
   static constexpr int G = LPH * HPG;
-  static constexpr int GPW = 32 / G;
+  int gl, head;
+  unsigned gmask;
+  bool on[CC];
+  int off[CC];   // element offset inside an [H*C] row (0 for inactive lanes: loads stay unconditional)
+  float a[CC][VEC];
+  __device__ __forceinline__ void init(const GatP& p) {
+    const int lane = threadIdx.x & 31;
+    gl = lane % G;
+    gmask = group_mask(lane, G);
+    head = blockIdx.y * HPG + gl / LPH;
+#pragma unroll
+    for (int cc = 0; cc < CC; ++cc) {
+      const int c0 = ((gl % LPH) + cc * LPH) * VEC;
+      on[cc] = (head < p.H) && (c0 < p.C);
+      off[cc] = on[cc] ? head * p.C + c0 : 0;
+      ld_vec<VEC>(p.att + off[cc], a[cc]);
+      if (!on[cc]) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a[cc][e] = 0.f;  // inactive lanes contribute nothing to the logits
+      }
+    }
+  }
 };
 
 // ------------------------------------------------------------------------------------ forward
 template <int VEC, int LPH, int CC, int HPG>
-__global__ void __launch_bounds__(256) gatv2_fwd_kernel(const GatP p) {
-  using L = Lay<VEC, LPH, CC, HPG>;
-  constexpr int G = L::G, GPW = L::GPW;
+__device__ __forceinline__ void gat_fwd_range(const GatP& p, const LaneCtx<VEC, LPH, CC, HPG>& L, int64_t row,
+                                              int64_t k0, int64_t k1, float& m, float& l, float (&acc)[CC][VEC]) {
+  constexpr int G = LPH * HPG;
   constexpr int U = (G < 4) ? G : 4;
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % G, gw = lane / G;
-  const unsigned gmask = group_mask(lane, G);
-  const int head = blockIdx.y * HPG + gl / LPH;
   const int HC = p.H * p.C;
-  bool on[CC];
-  int off[CC];
-  float a[CC][VEC];
+  float hi[CC][VEC];
 #pragma unroll
   for (int cc = 0; cc < CC; ++cc) {
-    const int c0 = ((gl % LPH) + cc * LPH) * VEC;
-    on[cc] = (head < p.H) && (c0 < p.C);
-    off[cc] = head * p.C + c0;
+    ld_vec<VEC>(p.hdst + row * HC + L.off[cc], hi[cc]);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) a[cc][e] = 0.f;
-    if (on[cc]) ld_vec<VEC>(p.att + off[cc], a[cc]);
+    for (int e = 0; e < VEC; ++e) acc[cc][e] = 0.f;
   }
-  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
-  for (int64_t row = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; row < p.n_dst;
-       row += (int64_t)gridDim.x * gpb) {
-    float hi[CC][VEC], acc[CC][VEC];
+  m = -INFINITY;
+  l = 0.f;
+  int64_t k = k0;
+  int32_t myc = (k + L.gl < k1) ? __ldg(p.col + k + L.gl) : 0;
+  while (k < k1) {
+    const int64_t rem = k1 - k;
+    const int cnt = rem < G ? (int)rem : G;
+    const int64_t kn = k + G;
+    const int32_t nc = (kn + L.gl < k1) ? __ldg(p.col + kn + L.gl) : 0;
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += U) {
+      float v[U][CC][VEC];
+      float s[U];
 #pragma unroll
-    for (int cc = 0; cc < CC; ++cc) {
+      for (int u = 0; u < U; ++u) {
+        const int32_t c = __shfl_sync(L.gmask, myc, j + u, G);  // slots past cnt carry row 0: loaded, never used
+        const float* rp = p.hsrc + (int64_t)c * HC;
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) { hi[cc][e] = 0.f; acc[cc][e] = 0.f; }
-      if (on[cc]) ld_vec<VEC>(p.hdst + row * HC + off[cc], hi[cc]);
-    }
-    float m = -INFINITY, l = 0.f;
-    const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
-    int64_t k = rs;
-    int32_t myc = (k + gl < re) ? __ldg(p.col + k + gl) : 0;
-    while (k < re) {
-      const int64_t rem = re - k;
-      const int cnt = rem < G ? (int)rem : G;
-      const int64_t kn = k + G;
-      const int32_t nc = (kn + gl < re) ? __ldg(p.col + kn + gl) : 0;
-      for (int j = 0; j < cnt; j += U) {
-        float v[U][CC][VEC];
-        float s[U];
+        for (int cc = 0; cc < CC; ++cc) ld_vec<VEC>(rp + L.off[cc], v[u][cc]);
+      }
+      float mb = m;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int32_t c = __shfl_sync(gmask, myc, j + u, G);
-          const bool ok = (j + u) < cnt;
-          const float* rp = p.hsrc + (int64_t)c * HC;
-#pragma unroll
-          for (int cc = 0; cc < CC; ++cc) {
-            if (ok && on[cc]) ld_vec<VEC>(rp + off[cc], v[u][cc]);
-            else {
-#pragma unroll
-              for (int e = 0; e < VEC; ++e) v[u][cc][e] = 0.f;
-            }
-          }
-        }
-        float mb = m;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          float part = 0.f;
-#pragma unroll
-          for (int cc = 0; cc < CC; ++cc)
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-              const float z = hi[cc][e] + v[u][cc][e];
-              part = fmaf(a[cc][e], z > 0.f ? z : z * p.slope, part);
-            }
-          s[u] = head_sum<LPH>(part, gmask);
-          if ((j + u) < cnt) mb = fmaxf(mb, s[u]);
-        }
-        const float scale = (m == -INFINITY) ? 0.f : expf(m - mb);
-        l *= scale;
+      for (int u = 0; u < U; ++u) {
+        float part = 0.f;
 #pragma unroll
         for (int cc = 0; cc < CC; ++cc)
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) acc[cc][e] *= scale;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if ((j + u) < cnt) {
-            const float pe = expf(s[u] - mb);
-            l += pe;
-#pragma unroll
-            for (int cc = 0; cc < CC; ++cc)
-#pragma unroll
-              for (int e = 0; e < VEC; ++e) acc[cc][e] = fmaf(pe, v[u][cc][e], acc[cc][e]);
+          for (int e = 0; e < VEC; ++e) {
+            const float z = hi[cc][e] + v[u][cc][e];
+            part = fmaf(L.a[cc][e], z > 0.f ? z : z * p.slope, part);
           }
+        s[u] = head_sum<LPH>(part, L.gmask);
+        if ((j + u) < cnt) mb = fmaxf(mb, s[u]);
+      }
+      const float scale = (m == -INFINITY) ? 0.f : expf(m - mb);
+      l *= scale;
+#pragma unroll
+      for (int cc = 0; cc < CC; ++cc)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[cc][e] *= scale;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if ((j + u) < cnt) {
+          const float pe = expf(s[u] - mb);
+          l += pe;
+#pragma unroll
+          for (int cc = 0; cc < CC; ++cc)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[cc][e] = fmaf(pe, v[u][cc][e], acc[cc][e]);
         }
-        m = mb;
       }
-      myc = nc;
-      k = kn;
+      m = mb;
     }
-    const float den = l + 1e-10f;
+    myc = nc;
+    k = kn;
+  }
+}
+
+template <int VEC, int LPH, int CC, int HPG>
+__device__ __forceinline__ void gat_fwd_store(const GatP& p, const LaneCtx<VEC, LPH, CC, HPG>& L, int64_t row, float m,
+                                              float l, float (&acc)[CC][VEC]) {
+  const int HC = p.H * p.C;
+  const float den = l + 1e-10f;
 #pragma unroll
-    for (int cc = 0; cc < CC; ++cc) {
-      if (!on[cc]) continue;
-      float o[VEC];
+  for (int cc = 0; cc < CC; ++cc) {
+    if (!L.on[cc]) continue;
+    float o[VEC];
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) o[e] = __fdiv_rn(acc[cc][e], den);
-      if (p.bias) {
-        float b[VEC];
-        ld_vec<VEC>(p.bias + off[cc], b);
+    for (int e = 0; e < VEC; ++e) o[e] = __fdiv_rn(acc[cc][e], den);
+    if (p.bias) {
+      float b[VEC];
+      ld_vec<VEC>(p.bias + L.off[cc], b);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) o[e] += b[e];
+      for (int e = 0; e < VEC; ++e) o[e] += b[e];
+    }
+    st_vec<VEC>(p.out + row * HC + L.off[cc], o);
+  }
+  if (L.head < p.H && (L.gl % LPH) == 0) {
+    p.rowmax[row * p.H + L.head] = m;
+    p.rowden[row * p.H + L.head] = l;
+  }
+}
+
+template <int VEC, int LPH, int CC, int HPG>
+__global__ void __launch_bounds__(256, 3) gatv2_fwd_kernel(const GatP p) {
+  using Ctx = LaneCtx<VEC, LPH, CC, HPG>;
+  constexpr int G = Ctx::G;
+  Ctx L;
+  L.init(p);
+  const int HC = p.H * p.C;
+  float* pm = p.partial + (int64_t)p.n_chunks * HC;
+  float* pl = pm + (int64_t)p.n_chunks * p.H;
+  gat_schedule<G>(
+      p,
+      [&](int64_t t, int64_t row, int64_t k0, int64_t k1, bool) {
+        float m, l, acc[CC][VEC];
+        gat_fwd_range<VEC, LPH, CC, HPG>(p, L, row, k0, k1, m, l, acc);
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc)
+          if (L.on[cc]) st_vec<VEC>(p.partial + t * HC + L.off[cc], acc[cc]);
+        if (L.head < p.H && (L.gl % LPH) == 0) {
+          pm[t * p.H + L.head] = m;
+          pl[t * p.H + L.head] = l;
+        }
+      },
+      [&](int64_t row, int64_t rs, int64_t re) {
+        float m, l, acc[CC][VEC];
+        gat_fwd_range<VEC, LPH, CC, HPG>(p, L, row, rs, re, m, l, acc);
+        gat_fwd_store<VEC, LPH, CC, HPG>(p, L, row, m, l, acc);
+      });
+  gat_queue_reset(p);
+}
+
+// merge the chunk states of every hub row in chunk order (log-sum-exp merge), then store like a normal row
+template <int VEC, int LPH, int CC, int HPG>
+__global__ void __launch_bounds__(256) gatv2_fwd_finish_kernel(const GatP p) {
+  using Ctx = LaneCtx<VEC, LPH, CC, HPG>;
+  constexpr int G = Ctx::G, GPW = 32 / G;
+  Ctx L;
+  L.init(p);
+  const int HC = p.H * p.C;
+  const float* pm = p.partial + (int64_t)p.n_chunks * HC;
+  const float* pl = pm + (int64_t)p.n_chunks * p.H;
+  const int lane = threadIdx.x & 31;
+  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
+  for (int64_t h = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + lane / G; h < p.n_hubs;
+       h += (int64_t)gridDim.x * gpb) {
+    const int64_t row = __ldg(p.hub_row + h);
+    const int64_t base = __ldg(p.hub_chunk_base + h);
+    const int nch = __ldg(p.hub_nchunks + h);
+    float m = -INFINITY, l = 0.f, acc[CC][VEC];
+#pragma unroll
+    for (int cc = 0; cc < CC; ++cc)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[cc][e] = 0.f;
+    const int hd = L.head < p.H ? L.head : 0;
+    for (int c = 0; c < nch; ++c) {
+      const float cm = __ldg(pm + (base + c) * p.H + hd), cl = __ldg(pl + (base + c) * p.H + hd);
+      const float mn = fmaxf(m, cm);
+      const float so = (m == -INFINITY) ? 0.f : expf(m - mn);
+      const float sn = (cm == -INFINITY) ? 0.f : expf(cm - mn);
+      l = l * so + cl * sn;
+#pragma unroll
+      for (int cc = 0; cc < CC; ++cc) {
+        float v[VEC];
+        ld_vec<VEC>(p.partial + (base + c) * HC + L.off[cc], v);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[cc][e] = acc[cc][e] * so + v[e] * sn;
       }
-      st_vec<VEC>(p.out + row * HC + off[cc], o);
+      m = mn;
     }
-    if (head < p.H && (gl % LPH) == 0) {
-      p.rowmax[row * p.H + head] = m;
-      p.rowden[row * p.H + head] = l;
-    }
+    gat_fwd_store<VEC, LPH, CC, HPG>(p, L, row, m, l, acc);
   }
 }
 
 // --------------------------------------------------------------------- backward, per target
 template <int VEC, int LPH, int CC, int HPG>
-__global__ void __launch_bounds__(256) gatv2_bwd_dst_kernel(const GatP p) {
-  using L = Lay<VEC, LPH, CC, HPG>;
-  constexpr int G = L::G, GPW = L::GPW;
+__device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<VEC, LPH, CC, HPG>& L, int64_t row,
+                                                   int64_t k0, int64_t k1, float (&ghi)[CC][VEC],
+                                                   float (&ga)[CC][VEC]) {
+  constexpr int G = LPH * HPG;
   constexpr int U = (G < 4) ? G : 4;
-  constexpr int SLOTS = G * CC * VEC;  // floats of the att gradient one group covers
-  __shared__ float red[8][SLOTS];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gl = lane % G, gw = lane / G;
-  const unsigned gmask = group_mask(lane, G);
-  const int head = blockIdx.y * HPG + gl / LPH;
   const int HC = p.H * p.C;
-  bool on[CC];
-  int off[CC];
-  float a[CC][VEC], ga[CC][VEC];
+  float hi[CC][VEC], gi[CC][VEC];
+  float rpart = 0.f;
 #pragma unroll
   for (int cc = 0; cc < CC; ++cc) {
-    const int c0 = ((gl % LPH) + cc * LPH) * VEC;
-    on[cc] = (head < p.H) && (c0 < p.C);
-    off[cc] = head * p.C + c0;
+    float ag[VEC];
+    ld_vec<VEC>(p.hdst + row * HC + L.off[cc], hi[cc]);
+    ld_vec<VEC>(p.g + row * HC + L.off[cc], gi[cc]);
+    ld_vec<VEC>(p.agg + row * HC + L.off[cc], ag);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) { a[cc][e] = 0.f; ga[cc][e] = 0.f; }
-    if (on[cc]) ld_vec<VEC>(p.att + off[cc], a[cc]);
+    for (int e = 0; e < VEC; ++e) {
+      if (!L.on[cc]) gi[cc][e] = 0.f;
+      ghi[cc][e] = 0.f;
+      rpart = fmaf(gi[cc][e], ag[e], rpart);
+    }
   }
-  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
-  for (int64_t row = (int64_t)blockIdx.x * gpb + (int64_t)warp * GPW + gw; row < p.n_dst;
-       row += (int64_t)gridDim.x * gpb) {
-    float hi[CC][VEC], gi[CC][VEC], ghi[CC][VEC];
-    float rpart = 0.f;
+  const float r = head_sum<LPH>(rpart, L.gmask);  // sum_k alpha_k * dalpha_k
+  const int hd = L.head < p.H ? L.head : 0;
+  const float m = __ldg(p.rowmax + row * p.H + hd);
+  const float dinv = 1.f / (__ldg(p.rowden + row * p.H + hd) + 1e-10f);
+  int64_t k = k0;
+  int32_t myc = (k + L.gl < k1) ? __ldg(p.col + k + L.gl) : 0;
+  while (k < k1) {
+    const int64_t rem = k1 - k;
+    const int cnt = rem < G ? (int)rem : G;
+    const int64_t kn = k + G;
+    const int32_t nc = (kn + L.gl < k1) ? __ldg(p.col + kn + L.gl) : 0;
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += U) {
+      float v[U][CC][VEC];
 #pragma unroll
-    for (int cc = 0; cc < CC; ++cc) {
+      for (int u = 0; u < U; ++u) {
+        const int32_t c = __shfl_sync(L.gmask, myc, j + u, G);
+        const float* rp = p.hsrc + (int64_t)c * HC;
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) { hi[cc][e] = 0.f; gi[cc][e] = 0.f; ghi[cc][e] = 0.f; }
-      if (on[cc]) {
-        float ag[VEC];
-        ld_vec<VEC>(p.hdst + row * HC + off[cc], hi[cc]);
-        ld_vec<VEC>(p.g + row * HC + off[cc], gi[cc]);
-        ld_vec<VEC>(p.agg + row * HC + off[cc], ag);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) rpart = fmaf(gi[cc][e], ag[e], rpart);
+        for (int cc = 0; cc < CC; ++cc) ld_vec<VEC>(rp + L.off[cc], v[u][cc]);
       }
-    }
-    const float r = head_sum<LPH>(rpart, gmask);  // sum_k alpha_k * dalpha_k
-    float m = 0.f, dinv = 0.f;
-    if (head < p.H) {
-      m = __ldg(p.rowmax + row * p.H + head);
-      dinv = 1.f / (__ldg(p.rowden + row * p.H + head) + 1e-10f);
-    }
-    const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
-    int64_t k = rs;
-    int32_t myc = (k + gl < re) ? __ldg(p.col + k + gl) : 0;
-    while (k < re) {
-      const int64_t rem = re - k;
-      const int cnt = rem < G ? (int)rem : G;
-      const int64_t kn = k + G;
-      const int32_t nc = (kn + gl < re) ? __ldg(p.col + kn + gl) : 0;
-      for (int j = 0; j < cnt; j += U) {
-        float v[U][CC][VEC];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int32_t c = __shfl_sync(gmask, myc, j + u, G);
-          const bool ok = (j + u) < cnt;
-          const float* rp = p.hsrc + (int64_t)c * HC;
+      for (int u = 0; u < U; ++u) {
+        float sp = 0.f, dp = 0.f;
 #pragma unroll
-          for (int cc = 0; cc < CC; ++cc) {
-            if (ok && on[cc]) ld_vec<VEC>(rp + off[cc], v[u][cc]);
-            else {
+        for (int cc = 0; cc < CC; ++cc)
 #pragma unroll
-              for (int e = 0; e < VEC; ++e) v[u][cc][e] = 0.f;
-            }
+          for (int e = 0; e < VEC; ++e) {
+            const float z = hi[cc][e] + v[u][cc][e];
+            sp = fmaf(L.a[cc][e], z > 0.f ? z : z * p.slope, sp);
+            dp = fmaf(gi[cc][e], v[u][cc][e], dp);
           }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          float sp = 0.f, dp = 0.f;
+        const float s = head_sum<LPH>(sp, L.gmask);
+        const float da = head_sum<LPH>(dp, L.gmask);
+        if ((j + u) < cnt) {
+          const float alpha = expf(s - m) * dinv;
+          const float ds = alpha * (da - r);
 #pragma unroll
           for (int cc = 0; cc < CC; ++cc)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
               const float z = hi[cc][e] + v[u][cc][e];
-              sp = fmaf(a[cc][e], z > 0.f ? z : z * p.slope, sp);
-              dp = fmaf(gi[cc][e], v[u][cc][e], dp);
+              const float lz = z > 0.f ? z : z * p.slope;
+              ghi[cc][e] += ds * L.a[cc][e] * (z > 0.f ? 1.f : p.slope);
+              ga[cc][e] = fmaf(ds, lz, ga[cc][e]);
             }
-          const float s = head_sum<LPH>(sp, gmask);
-          const float da = head_sum<LPH>(dp, gmask);
-          if ((j + u) < cnt && head < p.H) {
-            const float alpha = expf(s - m) * dinv;
-            const float ds = alpha * (da - r);
-#pragma unroll
-            for (int cc = 0; cc < CC; ++cc)
-#pragma unroll
-              for (int e = 0; e < VEC; ++e) {
-                const float z = hi[cc][e] + v[u][cc][e];
-                const float lz = z > 0.f ? z : z * p.slope;
-                const float dz = ds * a[cc][e] * (z > 0.f ? 1.f : p.slope);
-                ghi[cc][e] += dz;
-                ga[cc][e] = fmaf(ds, lz, ga[cc][e]);
-              }
-          }
         }
       }
-      myc = nc;
-      k = kn;
     }
-#pragma unroll
-    for (int cc = 0; cc < CC; ++cc)
-      if (on[cc]) st_vec<VEC>(p.g_hdst + row * HC + off[cc], ghi[cc]);
-    if (head < p.H && (gl % LPH) == 0) p.r_out[row * p.H + head] = r;
+    myc = nc;
+    k = kn;
   }
+  return r;
+}
+
+template <int VEC, int LPH, int CC, int HPG>
+__global__ void __launch_bounds__(256, 2) gatv2_bwd_dst_kernel(const GatP p) {
+  using Ctx = LaneCtx<VEC, LPH, CC, HPG>;
+  constexpr int G = Ctx::G;
+  constexpr int SLOTS = G * CC * VEC;  // floats of the att gradient one group covers
+  __shared__ float red[8][SLOTS];
+  Ctx L;
+  L.init(p);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int HC = p.H * p.C;
+  float ga[CC][VEC];
+#pragma unroll
+  for (int cc = 0; cc < CC; ++cc)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) ga[cc][e] = 0.f;
+  gat_schedule<G>(
+      p,
+      [&](int64_t t, int64_t row, int64_t k0, int64_t k1, bool first) {
+        float ghi[CC][VEC];
+        const float r = gat_bwd_dst_range<VEC, LPH, CC, HPG>(p, L, row, k0, k1, ghi, ga);
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc)
+          if (L.on[cc]) st_vec<VEC>(p.partial + t * HC + L.off[cc], ghi[cc]);
+        if (first && L.head < p.H && (L.gl % LPH) == 0) p.r_out[row * p.H + L.head] = r;
+      },
+      [&](int64_t row, int64_t rs, int64_t re) {
+        float ghi[CC][VEC];
+        const float r = gat_bwd_dst_range<VEC, LPH, CC, HPG>(p, L, row, rs, re, ghi, ga);
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc)
+          if (L.on[cc]) st_vec<VEC>(p.g_hdst + row * HC + L.off[cc], ghi[cc]);
+        if (L.head < p.H && (L.gl % LPH) == 0) p.r_out[row * p.H + L.head] = r;
+      });
   // d att: fold the groups of a warp (fixed order), then the warps of the CTA (fixed order)
+  __syncwarp();
 #pragma unroll
   for (int cc = 0; cc < CC; ++cc)
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      float t = ga[cc][e];
+      float t = L.on[cc] ? ga[cc][e] : 0.f;
 #pragma unroll
       for (int o = G; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
       ga[cc][e] = t;
@@ -286,7 +435,7 @@ __global__ void __launch_bounds__(256) gatv2_bwd_dst_kernel(const GatP p) {
 #pragma unroll
     for (int cc = 0; cc < CC; ++cc)
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) red[warp][(cc * G + gl) * VEC + e] = ga[cc][e];
+      for (int e = 0; e < VEC; ++e) red[warp][(cc * G + L.gl) * VEC + e] = ga[cc][e];
   }
   __syncthreads();
   for (int sidx = threadIdx.x; sidx < SLOTS; sidx += blockDim.x) {
@@ -298,106 +447,116 @@ __global__ void __launch_bounds__(256) gatv2_bwd_dst_kernel(const GatP p) {
     const int c0 = ((lg % LPH) + cc * LPH) * VEC + e;
     if (hd < p.H && c0 < p.C) p.g_att_part[(int64_t)blockIdx.x * HC + hd * p.C + c0] = t;
   }
+  gat_queue_reset(p);
 }
 
 // --------------------------------------------------------------------- backward, per source
 // Walks the transposed structure: row j of (colptr, rowidx) lists the targets i of j's out-edges.
 template <int VEC, int LPH, int CC, int HPG>
-__global__ void __launch_bounds__(256) gatv2_bwd_src_kernel(const GatP p) {
-  using L = Lay<VEC, LPH, CC, HPG>;
-  constexpr int G = L::G, GPW = L::GPW;
+__device__ __forceinline__ void gat_bwd_src_range(const GatP& p, const LaneCtx<VEC, LPH, CC, HPG>& L, int64_t row,
+                                                  int64_t k0, int64_t k1, float (&ghj)[CC][VEC]) {
+  constexpr int G = LPH * HPG;
   constexpr int U = (G < 2) ? G : 2;
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % G, gw = lane / G;
-  const unsigned gmask = group_mask(lane, G);
-  const int head = blockIdx.y * HPG + gl / LPH;
   const int HC = p.H * p.C;
-  bool on[CC];
-  int off[CC];
-  float a[CC][VEC];
+  float hj[CC][VEC];
 #pragma unroll
   for (int cc = 0; cc < CC; ++cc) {
-    const int c0 = ((gl % LPH) + cc * LPH) * VEC;
-    on[cc] = (head < p.H) && (c0 < p.C);
-    off[cc] = head * p.C + c0;
+    ld_vec<VEC>(p.hsrc + row * HC + L.off[cc], hj[cc]);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) a[cc][e] = 0.f;
-    if (on[cc]) ld_vec<VEC>(p.att + off[cc], a[cc]);
+    for (int e = 0; e < VEC; ++e) ghj[cc][e] = 0.f;
   }
-  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
-  for (int64_t row = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; row < p.n_src;
-       row += (int64_t)gridDim.x * gpb) {
-    float hj[CC][VEC], ghj[CC][VEC];
+  const int hd = L.head < p.H ? L.head : 0;
+  int64_t k = k0;
+  int32_t myc = (k + L.gl < k1) ? __ldg(p.col + k + L.gl) : 0;
+  while (k < k1) {
+    const int64_t rem = k1 - k;
+    const int cnt = rem < G ? (int)rem : G;
+    const int64_t kn = k + G;
+    const int32_t nc = (kn + L.gl < k1) ? __ldg(p.col + kn + L.gl) : 0;
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += U) {
+      float hi[U][CC][VEC], gi[U][CC][VEC];
+      float m[U], dinv[U], r[U];
 #pragma unroll
-    for (int cc = 0; cc < CC; ++cc) {
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = __shfl_sync(L.gmask, myc, j + u, G);
+        m[u] = __ldg(p.rowmax + i * p.H + hd);
+        dinv[u] = 1.f / (__ldg(p.rowden + i * p.H + hd) + 1e-10f);
+        r[u] = __ldg(p.r_in + i * p.H + hd);
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) { hj[cc][e] = 0.f; ghj[cc][e] = 0.f; }
-      if (on[cc]) ld_vec<VEC>(p.hsrc + row * HC + off[cc], hj[cc]);
-    }
-    const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
-    int64_t k = rs;
-    int32_t myc = (k + gl < re) ? __ldg(p.col + k + gl) : 0;
-    while (k < re) {
-      const int64_t rem = re - k;
-      const int cnt = rem < G ? (int)rem : G;
-      const int64_t kn = k + G;
-      const int32_t nc = (kn + gl < re) ? __ldg(p.col + kn + gl) : 0;
-      for (int j = 0; j < cnt; j += U) {
-        float hi[U][CC][VEC], gi[U][CC][VEC];
-        float m[U], dinv[U], r[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int64_t i = __shfl_sync(gmask, myc, j + u, G);
-          const bool ok = (j + u) < cnt;
-          m[u] = 0.f; dinv[u] = 0.f; r[u] = 0.f;
-          if (ok && head < p.H) {
-            m[u] = __ldg(p.rowmax + i * p.H + head);
-            dinv[u] = 1.f / (__ldg(p.rowden + i * p.H + head) + 1e-10f);
-            r[u] = __ldg(p.r_in + i * p.H + head);
-          }
-#pragma unroll
-          for (int cc = 0; cc < CC; ++cc) {
-            if (ok && on[cc]) {
-              ld_vec<VEC>(p.hdst + i * HC + off[cc], hi[u][cc]);
-              ld_vec<VEC>(p.g + i * HC + off[cc], gi[u][cc]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < VEC; ++e) { hi[u][cc][e] = 0.f; gi[u][cc][e] = 0.f; }
-            }
-          }
+        for (int cc = 0; cc < CC; ++cc) {
+          ld_vec<VEC>(p.hdst + i * HC + L.off[cc], hi[u][cc]);
+          ld_vec<VEC>(p.g + i * HC + L.off[cc], gi[u][cc]);
         }
+      }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          float sp = 0.f, dp = 0.f;
+      for (int u = 0; u < U; ++u) {
+        float sp = 0.f, dp = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc)
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const float z = hi[u][cc][e] + hj[cc][e];
+            sp = fmaf(L.a[cc][e], z > 0.f ? z : z * p.slope, sp);
+            dp = fmaf(L.on[cc] ? gi[u][cc][e] : 0.f, hj[cc][e], dp);
+          }
+        const float s = head_sum<LPH>(sp, L.gmask);
+        const float da = head_sum<LPH>(dp, L.gmask);
+        if ((j + u) < cnt) {
+          const float alpha = expf(s - m[u]) * dinv[u];
+          const float ds = alpha * (da - r[u]);
 #pragma unroll
           for (int cc = 0; cc < CC; ++cc)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
               const float z = hi[u][cc][e] + hj[cc][e];
-              sp = fmaf(a[cc][e], z > 0.f ? z : z * p.slope, sp);
-              dp = fmaf(gi[u][cc][e], hj[cc][e], dp);
+              ghj[cc][e] += ds * L.a[cc][e] * (z > 0.f ? 1.f : p.slope) + alpha * gi[u][cc][e];
             }
-          const float s = head_sum<LPH>(sp, gmask);
-          const float da = head_sum<LPH>(dp, gmask);
-          if ((j + u) < cnt && head < p.H) {
-            const float alpha = expf(s - m[u]) * dinv[u];
-            const float ds = alpha * (da - r[u]);
-#pragma unroll
-            for (int cc = 0; cc < CC; ++cc)
-#pragma unroll
-              for (int e = 0; e < VEC; ++e) {
-                const float z = hi[u][cc][e] + hj[cc][e];
-                ghj[cc][e] += ds * a[cc][e] * (z > 0.f ? 1.f : p.slope) + alpha * gi[u][cc][e];
-              }
-          }
         }
       }
-      myc = nc;
-      k = kn;
     }
+    myc = nc;
+    k = kn;
+  }
+}
+
+template <int VEC, int LPH, int CC, int HPG>
+__global__ void __launch_bounds__(256, 2) gatv2_bwd_src_kernel(const GatP p) {
+  using Ctx = LaneCtx<VEC, LPH, CC, HPG>;
+  constexpr int G = Ctx::G;
+  Ctx L;
+  L.init(p);
+  const int HC = p.H * p.C;
+  gat_schedule<G>(
+      p,
+      [&](int64_t t, int64_t row, int64_t k0, int64_t k1, bool) {
+        float ghj[CC][VEC];
+        gat_bwd_src_range<VEC, LPH, CC, HPG>(p, L, row, k0, k1, ghj);
 #pragma unroll
-    for (int cc = 0; cc < CC; ++cc)
-      if (on[cc]) st_vec<VEC>(p.g_hsrc + row * HC + off[cc], ghj[cc]);
+        for (int cc = 0; cc < CC; ++cc)
+          if (L.on[cc]) st_vec<VEC>(p.partial + t * HC + L.off[cc], ghj[cc]);
+      },
+      [&](int64_t row, int64_t rs, int64_t re) {
+        float ghj[CC][VEC];
+        gat_bwd_src_range<VEC, LPH, CC, HPG>(p, L, row, rs, re, ghj);
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc)
+          if (L.on[cc]) st_vec<VEC>(p.g_hsrc + row * HC + L.off[cc], ghj[cc]);
+      });
+  gat_queue_reset(p);
+}
+
+// hub rows of either backward pass: out[row,:] = sum over the row's chunks (chunk order) of partial[c,:]
+__global__ void __launch_bounds__(256) gat_sum_finish_kernel(const GatP p, float* __restrict__ out) {
+  const int HC = p.H * p.C;
+  const int64_t total = (int64_t)p.n_hubs * HC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int h = (int)(i / HC), f = (int)(i % HC);
+    const int64_t base = __ldg(p.hub_chunk_base + h);
+    const int nch = __ldg(p.hub_nchunks + h);
+    float s = 0.f;
+    for (int c = 0; c < nch; ++c) s += p.partial[(base + c) * HC + f];
+    out[(int64_t)__ldg(p.hub_row + h) * HC + f] = s;
   }
 }
 
@@ -426,11 +585,12 @@ static bool gat_shape(int H, int C, bool can4, GatShape* s) {
   return true;
 }
 
-enum { GAT_FWD = 0, GAT_BWD_DST = 1, GAT_BWD_SRC = 2 };
+enum { GAT_FWD = 0, GAT_BWD_DST = 1, GAT_BWD_SRC = 2, GAT_FWD_FINISH = 3 };
 
 template <int VEC, int LPH, int CC, int HPG>
 static void gat_launch(int which, dim3 grid, cudaStream_t st, const GatP& p) {
   if (which == GAT_FWD) gatv2_fwd_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
+  else if (which == GAT_FWD_FINISH) gatv2_fwd_finish_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
   else if (which == GAT_BWD_DST) gatv2_bwd_dst_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
   else gatv2_bwd_src_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
 }
@@ -454,30 +614,61 @@ static int gat_dispatch(const GatShape& s, int which, dim3 grid, cudaStream_t st
   return KGB_ERR_UNSUPPORTED;
 }
 
-static int gat_grid_x(int device, int64_t rows, const GatShape& s, int per_sm) {
-  const int64_t gpb = 8 * (32 / (s.lph * s.hpg));
-  int64_t need = ceil_div(rows, gpb);
+static int gat_grid_x(int device, int64_t rows, int64_t chunks, const GatShape& s, int per_sm) {
+  const int gpw = 32 / (s.lph * s.hpg);
+  const int64_t units = ceil_div(chunks, gpw) + ceil_div(rows, (int64_t)GAT_UNIT_ROWS);
+  int64_t need = ceil_div(units, 8);
   const int64_t cap = (int64_t)sm_count(device) * per_sm;
   if (need > cap) need = cap;
   if (need < 1) need = 1;
   return (int)need;
 }
 
-static int gat_run(int device, int which, int64_t rows, GatP& p, cudaStream_t st, int grid_x_override = 0) {
-  const bool can4 = aligned16(p.hsrc) && aligned16(p.hdst) && aligned16(p.att) && (p.C % 4 == 0) &&
-                    (!p.bias || aligned16(p.bias)) && (!p.out || aligned16(p.out)) && (!p.g || aligned16(p.g)) &&
-                    (!p.agg || aligned16(p.agg)) && (!p.g_hdst || aligned16(p.g_hdst)) &&
-                    (!p.g_hsrc || aligned16(p.g_hsrc));
+static bool gat_can4(const GatP& p) {
+  return aligned16(p.hsrc) && aligned16(p.hdst) && aligned16(p.att) && (p.C % 4 == 0) &&
+         (!p.bias || aligned16(p.bias)) && (!p.out || aligned16(p.out)) && (!p.g || aligned16(p.g)) &&
+         (!p.agg || aligned16(p.agg)) && (!p.g_hdst || aligned16(p.g_hdst)) && (!p.g_hsrc || aligned16(p.g_hsrc)) &&
+         (!p.partial || aligned16(p.partial));
+}
+
+static void gat_set_hubs(GatP& p, const kgb_hub_table* hubs) {
+  if (hubs && hubs->n_hubs > 0 && hubs->n_chunks > 0 && hubs->partial) {
+    p.hub_row = hubs->hub_row; p.hub_chunk_base = hubs->hub_chunk_base; p.hub_nchunks = hubs->hub_nchunks;
+    p.chunk_hub = hubs->chunk_hub; p.n_hubs = hubs->n_hubs; p.n_chunks = hubs->n_chunks;
+    p.hub_threshold = hubs->threshold; p.hub_chunk = hubs->chunk; p.partial = hubs->partial;
+  }
+  p.work = hubs ? hubs->work : nullptr;
+}
+
+static int gat_run(int device, int which, GatP& p, cudaStream_t st, int per_sm, int grid_x_cap, float* finish_out) {
   GatShape s;
-  if (!gat_shape(p.H, p.C, can4, &s)) {
+  if (!gat_shape(p.H, p.C, gat_can4(p), &s)) {
     set_error("gatv2: C=%d too wide for the compiled kernels", p.C);
     return KGB_ERR_UNSUPPORTED;
   }
-  const int gx = grid_x_override ? grid_x_override : gat_grid_x(device, rows, s, 8);
+  if (p.work && s.nhb > 32) p.work = nullptr;  // queue scratch holds 32 head blocks
+  int gx = gat_grid_x(device, p.n_rows, p.n_chunks, s, per_sm);
+  if (grid_x_cap > 0 && gx > grid_x_cap) gx = grid_x_cap;
   dim3 grid(gx, s.nhb, 1);
   int rc = (s.vec == 4) ? gat_dispatch<4>(s, which, grid, st, p) : gat_dispatch<1>(s, which, grid, st, p);
   if (rc != KGB_OK) return rc;
   KGB_CHECK_LAUNCH();
+  if (p.n_hubs > 0) {
+    if (which == GAT_FWD) {
+      const int gpw = 32 / (s.lph * s.hpg);
+      int64_t fx = ceil_div((int64_t)p.n_hubs, 8 * gpw);
+      if (fx > (int64_t)sm_count(device) * 8) fx = (int64_t)sm_count(device) * 8;
+      dim3 fgrid((unsigned)fx, s.nhb, 1);
+      rc = (s.vec == 4) ? gat_dispatch<4>(s, GAT_FWD_FINISH, fgrid, st, p) : gat_dispatch<1>(s, GAT_FWD_FINISH, fgrid, st, p);
+      if (rc != KGB_OK) return rc;
+      KGB_CHECK_LAUNCH();
+    } else {
+      int64_t fx = ceil_div((int64_t)p.n_hubs * p.H * p.C, 256);
+      if (fx > (int64_t)sm_count(device) * 8) fx = (int64_t)sm_count(device) * 8;
+      gat_sum_finish_kernel<<<(unsigned)fx, 256, 0, st>>>(p, finish_out);
+      KGB_CHECK_LAUNCH();
+    }
+  }
   return KGB_OK;
 }
 
@@ -487,9 +678,15 @@ using namespace kgb;
 
 extern "C" {
 
+size_t kgb_gatv2_partial_bytes(int32_t n_chunks, int32_t H, int32_t C) {
+  if (n_chunks <= 0) return 0;
+  return align_up((size_t)n_chunks * ((size_t)H * C + 2 * (size_t)H) * sizeof(float), 256);
+}
+
 int kgb_gatv2_fwd(int device, const float* hsrc, const float* hdst, int64_t n_src, int64_t n_dst, int32_t H,
                   int32_t C, const float* att, float slope, const int64_t* rowptr, const int32_t* col,
-                  const float* bias, float* out, float* rowmax, float* rowden, kgb_stream_t stream) {
+                  const float* bias, float* out, float* rowmax, float* rowden, const kgb_hub_table* hubs,
+                  kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(H > 0 && C > 0 && n_dst >= 0 && n_src >= 0, "bad sizes");
   if (n_dst == 0) return KGB_OK;
@@ -497,25 +694,22 @@ int kgb_gatv2_fwd(int device, const float* hsrc, const float* hdst, int64_t n_sr
   GatP p = {};
   p.hsrc = hsrc; p.hdst = hdst; p.n_src = n_src; p.n_dst = n_dst; p.H = H; p.C = C; p.att = att; p.slope = slope;
   p.rowptr = rowptr; p.col = col; p.bias = bias; p.out = out; p.rowmax = rowmax; p.rowden = rowden;
-  return gat_run(device, GAT_FWD, n_dst, p, (cudaStream_t)stream);
+  p.n_rows = n_dst;
+  gat_set_hubs(p, hubs);
+  return gat_run(device, GAT_FWD, p, (cudaStream_t)stream, 6, 0, nullptr);
 }
 
 int kgb_gatv2_bwd_parts(int device, int64_t n_dst, int32_t H, int32_t C) {
   if (kgb::use_device(device) != KGB_OK) return -1;
-  GatShape s;
-  if (H <= 0 || C <= 0 || !gat_shape(H, C, C % 4 == 0, &s)) return -1;
-  // upper bound over both vector widths: the scalar layout never needs more CTAs than this
-  GatShape s1;
-  const int a = gat_grid_x(device, n_dst, s, 4);
-  if (!gat_shape(H, C, false, &s1)) return a;  // scalar layout not compiled for this width
-  const int b = gat_grid_x(device, n_dst, s1, 4);
-  return a > b ? a : b;
+  if (H <= 0 || C <= 0 || n_dst < 0) return -1;
+  return sm_count(device) * 4;  // upper bound of the CTA rows kgb_gatv2_bwd_dst launches
 }
 
 int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float* hsrc, const float* hdst,
                       int64_t n_src, int64_t n_dst, int32_t H, int32_t C, const float* att, float slope,
                       const int64_t* rowptr, const int32_t* col, const float* rowmax, const float* rowden,
-                      float* g_hdst, float* r, float* g_att_part, int32_t n_parts, kgb_stream_t stream) {
+                      float* g_hdst, float* r, float* g_att_part, int32_t n_parts, const kgb_hub_table* hubs,
+                      kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(H > 0 && C > 0 && n_dst >= 0 && n_parts > 0, "bad sizes");
   KGB_REQUIRE(g_att_part, "g_att_part is NULL");
@@ -527,20 +721,15 @@ int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float*
   p.hsrc = hsrc; p.hdst = hdst; p.n_src = n_src; p.n_dst = n_dst; p.H = H; p.C = C; p.att = att; p.slope = slope;
   p.rowptr = rowptr; p.col = col; p.rowmax = const_cast<float*>(rowmax); p.rowden = const_cast<float*>(rowden);
   p.g = g; p.agg = agg; p.g_hdst = g_hdst; p.r_out = r; p.g_att_part = g_att_part;
-  // the CTA count must not exceed the partial rows the caller allocated
-  const bool can4 = aligned16(hsrc) && aligned16(hdst) && aligned16(att) && (C % 4 == 0) && aligned16(g) &&
-                    aligned16(agg) && aligned16(g_hdst);
-  GatShape s;
-  if (!gat_shape(H, C, can4, &s)) { set_error("gatv2: C too wide"); return KGB_ERR_UNSUPPORTED; }
-  int gx = gat_grid_x(device, n_dst, s, 4);
-  if (gx > n_parts) gx = n_parts;
-  return gat_run(device, GAT_BWD_DST, n_dst, p, st, gx);
+  p.n_rows = n_dst;
+  gat_set_hubs(p, hubs);
+  return gat_run(device, GAT_BWD_DST, p, st, 4, n_parts, g_hdst);
 }
 
 int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float* hdst, int64_t n_src,
                       int64_t n_dst, int32_t H, int32_t C, const float* att, float slope, const int64_t* colptr,
                       const int32_t* row, const float* rowmax, const float* rowden, const float* r,
-                      float* g_hsrc, kgb_stream_t stream) {
+                      float* g_hsrc, const kgb_hub_table* hubs, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(H > 0 && C > 0 && n_src >= 0, "bad sizes");
   if (n_src == 0) return KGB_OK;
@@ -549,7 +738,9 @@ int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float
   p.hsrc = hsrc; p.hdst = hdst; p.n_src = n_src; p.n_dst = n_dst; p.H = H; p.C = C; p.att = att; p.slope = slope;
   p.rowptr = colptr; p.col = row; p.rowmax = const_cast<float*>(rowmax); p.rowden = const_cast<float*>(rowden);
   p.g = g; p.r_in = r; p.g_hsrc = g_hsrc;
-  return gat_run(device, GAT_BWD_SRC, n_src, p, (cudaStream_t)stream);
+  p.n_rows = n_src;
+  gat_set_hubs(p, hubs);
+  return gat_run(device, GAT_BWD_SRC, p, (cudaStream_t)stream, 4, 0, g_hsrc);
 }
 
 }  // extern "C"

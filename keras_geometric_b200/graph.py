@@ -49,9 +49,25 @@ class Csr:
         """Task-queue counters of kgb_gather_reduce (zero between launches), one pair per stream."""
         w = self._work.get(stream_id)
         if w is None:
-            w = torch.zeros(2, dtype=torch.int32, device=self.rowptr.device)
+            w = torch.zeros(64, dtype=torch.int32, device=self.rowptr.device)
             self._work[stream_id] = w
         return w
+
+    def hub_table(self, partial_bytes: int, stream_id: int):
+        """ctypes ``kgb_hub_table`` for the GATv2 kernels (keeps the partial buffer alive on self)."""
+        t = _lib.HubTable()
+        if self.n_chunks > 0:
+            key = ("gat", partial_bytes)
+            buf = self._partials.get(key)
+            if buf is None:
+                buf = torch.empty(max(partial_bytes // 4, 1), dtype=torch.float32, device=self.rowptr.device)
+                self._partials[key] = buf
+            t.hub_row, t.hub_chunk_base = self.hub_row.data_ptr(), self.hub_chunk_base.data_ptr()
+            t.hub_nchunks, t.chunk_hub = self.hub_nchunks.data_ptr(), self.chunk_hub.data_ptr()
+            t.n_hubs, t.n_chunks, t.threshold, t.chunk = self.n_hubs, self.n_chunks, HUB_THRESHOLD, HUB_CHUNK
+            t.partial = buf.data_ptr()
+        t.work = self.work(stream_id).data_ptr()
+        return t
 
     @property
     def inv_deg(self) -> torch.Tensor:
@@ -64,11 +80,12 @@ class Csr:
         if self.n_chunks == 0:
             return None
         nbytes = _lib.load().kgb_gather_reduce_partial_bytes(self.n_chunks, F, op)
-        key = nbytes
+        key = ("gr", nbytes)
         buf = self._partials.get(key)
         if buf is None:
             buf = torch.empty(nbytes // 4, dtype=torch.float32, device=self.rowptr.device)
-            self._partials = {key: buf}
+            self._partials = {k: v for k, v in self._partials.items() if k[0] != "gr"}
+            self._partials[key] = buf
         return buf
 
 

@@ -296,10 +296,11 @@ class _GatV2(torch.autograd.Function):
         out = torch.empty((n_dst, H * C), dtype=torch.float32, device=dev)
         rowmax = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
         rowden = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
+        hubs = csr.hub_table(lib.kgb_gatv2_partial_bytes(csr.n_chunks, H, C), _stream(dev))
         _lib.check(lib.kgb_gatv2_fwd(dev.index, h_src.data_ptr(), h_dst.data_ptr(), n_src, n_dst, H, C,
                                      att_c.data_ptr(), float(slope), csr.rowptr.data_ptr(), csr.col.data_ptr(),
                                      _ptr(bias_c), out.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(),
-                                     _stream(dev)), "kgb_gatv2_fwd")
+                                     ctypes.byref(hubs), _stream(dev)), "kgb_gatv2_fwd")
         ctx.graph, ctx.H, ctx.C, ctx.slope, ctx.same = graph, H, C, float(slope), same
         ctx.has_bias = bias is not None
         ctx.save_for_backward(h_src, h_dst, att_c, out, rowmax, rowden, *([bias_c] if bias is not None else []))
@@ -327,8 +328,9 @@ class _GatV2(torch.autograd.Function):
         _lib.check(lib.kgb_gatv2_bwd_dst(dev.index, g.data_ptr(), agg.data_ptr(), h_src.data_ptr(), h_dst.data_ptr(),
                                          n_src, n_dst, H, C, att_c.data_ptr(), ctx.slope, csr.rowptr.data_ptr(),
                                          csr.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(),
-                                         g_hdst.data_ptr(), r.data_ptr(), part.data_ptr(), n_parts, st),
-                   "kgb_gatv2_bwd_dst")
+                                         g_hdst.data_ptr(), r.data_ptr(), part.data_ptr(), n_parts,
+                                         ctypes.byref(csr.hub_table(lib.kgb_gatv2_partial_bytes(csr.n_chunks, H, C), st)),
+                                         st), "kgb_gatv2_bwd_dst")
         g_att = torch.empty(H * C, dtype=torch.float32, device=dev)
         _lib.check(lib.kgb_reduce_parts(dev.index, part.data_ptr(), n_parts, H * C, g_att.data_ptr(), st),
                    "kgb_reduce_parts")
@@ -336,7 +338,9 @@ class _GatV2(torch.autograd.Function):
         _lib.check(lib.kgb_gatv2_bwd_src(dev.index, g.data_ptr(), h_src.data_ptr(), h_dst.data_ptr(), n_src, n_dst,
                                          H, C, att_c.data_ptr(), ctx.slope, csc.rowptr.data_ptr(),
                                          csc.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(), r.data_ptr(),
-                                         g_hsrc.data_ptr(), st), "kgb_gatv2_bwd_src")
+                                         g_hsrc.data_ptr(),
+                                         ctypes.byref(csc.hub_table(lib.kgb_gatv2_partial_bytes(csc.n_chunks, H, C), st)),
+                                         st), "kgb_gatv2_bwd_src")
         g_bias = g.sum(dim=0) if ctx.has_bias else None
         if ctx.same:
             return g_hsrc + g_hdst, None, g_att, g_bias, None, None, None, None
