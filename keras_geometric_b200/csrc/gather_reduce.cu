@@ -51,16 +51,21 @@ __device__ __forceinline__ void init_acc(float (&acc)[NCH][VEC], int32_t (&aidx)
     }
 }
 
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));  // FMNMX.NAN: NaN propagates like torch's amax
+  return d;
+}
+
 template <bool IS_MAX, bool HAS_W = true>
 __device__ __forceinline__ void accum(float& m, int32_t& a, float v, float w, int32_t c, bool negate) {
   if constexpr (IS_MAX) {
     const float val = negate ? -v : v;
-    if (val != val) {
-      m = val;  // NaN propagates like torch's amax
-    } else if (val > m) {
-      m = val;
+    const float mo = m;
+    m = fmax_nan(mo, val);
+    if (val > mo) {
       a = c;
-    } else if (val == m && c != a) {
+    } else if (val == mo && c != a) {
       a = -2;  // tie between different sources: backward re-walks the row.  Parallel edges from the same
                // source are not a tie: their even shares add up to the whole gradient on that one row.
     }
@@ -69,7 +74,6 @@ __device__ __forceinline__ void accum(float& m, int32_t& a, float v, float w, in
     else m = __fadd_rn(m, v);
   }
 }
-
 
 // Load the feature rows of U consecutive slots of the current index batch.  Slots past the end of the
 // batch carry index 0 (a valid row) and are simply never accumulated, so the loads need no predicate.
@@ -357,6 +361,9 @@ __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, i
 #ifndef KGB_GR_MINB_NARROW
 #define KGB_GR_MINB_NARROW 4
 #endif
+#ifndef KGB_GR_MINB_MAX
+#define KGB_GR_MINB_MAX 3  // max/min carry value + argmax per element (twice the accumulator registers)
+#endif
 
 // Tasks: first the hub chunks (the long ones), then units of UNIT_ROWS consecutive rows.  They are
 // handed out by a global queue (one atomicAdd per warp and unit) because static striding correlates
@@ -364,7 +371,8 @@ __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, i
 // 27 % of the SM-cycles idle in the first version.  Which warp computes a row never changes the
 // result, so the output stays deterministic.
 template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
-__global__ void __launch_bounds__(256, ((VEC == 4 && G >= 16) ? KGB_GR_MINB_WIDE : KGB_GR_MINB_NARROW))
+__global__ void __launch_bounds__(256, ((VEC == 4 && G >= 16) ? (IS_MAX ? KGB_GR_MINB_MAX : KGB_GR_MINB_WIDE)
+                                                              : KGB_GR_MINB_NARROW))
 gather_reduce_kernel(const GRP p) {
   constexpr int GPW = 32 / G;
   constexpr int BPU = UNIT_ROWS / G;  // row blocks per unit
