@@ -35,7 +35,8 @@ enum {
   KGB_ERR_UNSUPPORTED = -4  /* shape outside the compiled kernel set */
 };
 
-enum { KGB_OP_SUM = 0, KGB_OP_MEAN = 1, KGB_OP_MAX = 2, KGB_OP_MIN = 3 };
+enum { KGB_OP_SUM = 0, KGB_OP_MEAN = 1, KGB_OP_MAX = 2, KGB_OP_MIN = 3,
+       KGB_OP_MAX_RAW = 4 /* keras segment_max itself: empty segment = -inf, no inf -> 0 rewrite */ };
 enum { KGB_ACT_NONE = 0, KGB_ACT_RELU = 1 };
 
 /* status bits written by kgb_csr_build into *status (device int32) */

@@ -12,8 +12,9 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 from . import _build
 
-OP_SUM, OP_MEAN, OP_MAX, OP_MIN = 0, 1, 2, 3
-OPS = {"sum": OP_SUM, "mean": OP_MEAN, "max": OP_MAX, "min": OP_MIN}
+OP_SUM, OP_MEAN, OP_MAX, OP_MIN, OP_MAX_RAW = 0, 1, 2, 3, 4
+OPS = {"sum": OP_SUM, "mean": OP_MEAN, "max": OP_MAX, "min": OP_MIN, "max_raw": OP_MAX_RAW}
+MAX_OPS = (OP_MAX, OP_MIN, OP_MAX_RAW)
 ACT_NONE, ACT_RELU = 0, 1
 STATUS_OOB_INDEX = 1
 

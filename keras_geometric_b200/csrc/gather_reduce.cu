@@ -31,7 +31,7 @@ struct GRP {
   const int32_t* row_ids;
   const float* edge_w; const float* src_scale; const float* out_scale;
   const float* addend; int64_t ld_addend; float addend_scale;
-  const float* bias; int act; int mean; int negate;
+  const float* bias; int act; int mean; int negate; int raw_max;
   float* out; int64_t ldo; int32_t* arg;
   const int32_t* hub_row; const int32_t* hub_chunk_base; const int32_t* hub_nchunks;
   const int32_t* chunk_hub;
@@ -187,7 +187,7 @@ __device__ __forceinline__ void epilogue(const GRP& p, int64_t slot, int64_t deg
       a[e] = aidx[ch][e];
       if constexpr (IS_MAX) {
         if (p.negate) r[e] = -r[e];
-        if (isinf(r[e])) { r[e] = 0.f; a[e] = -1; }  // empty segment, or a genuine +-inf (reference quirk)
+        if (!p.raw_max && isinf(r[e])) { r[e] = 0.f; a[e] = -1; }  // empty segment, or a genuine +-inf (reference quirk)
         if (r[e] != r[e]) a[e] = -1;
       }
       if (p.mean) r[e] = __fdiv_rn(r[e], den);
@@ -684,7 +684,7 @@ extern "C" {
 size_t kgb_gather_reduce_partial_bytes(int32_t n_chunks, int32_t F, int32_t op) {
   if (n_chunks <= 0) return 0;
   size_t b = align_up((size_t)n_chunks * (size_t)F * sizeof(float), 256);
-  if (op == KGB_OP_MAX || op == KGB_OP_MIN) b *= 2;  // values + arg
+  if (op == KGB_OP_MAX || op == KGB_OP_MIN || op == KGB_OP_MAX_RAW) b *= 2;  // values + arg
   return b;
 }
 
@@ -693,7 +693,7 @@ int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t 
   KGB_REQUIRE(a != nullptr, "args is NULL");
   KGB_REQUIRE(a->F > 0, "F must be positive (got %d)", a->F);
   KGB_REQUIRE(a->n_rows >= 0, "n_rows < 0");
-  KGB_REQUIRE(a->op >= KGB_OP_SUM && a->op <= KGB_OP_MIN, "bad op %d", a->op);
+  KGB_REQUIRE(a->op >= KGB_OP_SUM && a->op <= KGB_OP_MAX_RAW, "bad op %d", a->op);
   if (a->n_rows == 0) return KGB_OK;
   KGB_REQUIRE(a->x && a->rowptr && a->out, "x/rowptr/out must be non-NULL");
   KGB_REQUIRE(a->ldx >= a->F && a->ldo >= a->F, "leading dimension smaller than F");
@@ -703,7 +703,7 @@ int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t 
                 "hub table given but a pointer is NULL");
     KGB_REQUIRE(a->hub_chunk > 0 && a->hub_threshold >= a->hub_chunk, "bad hub threshold/chunk");
   }
-  const bool is_max = (a->op == KGB_OP_MAX || a->op == KGB_OP_MIN);
+  const bool is_max = (a->op == KGB_OP_MAX || a->op == KGB_OP_MIN || a->op == KGB_OP_MAX_RAW);
   cudaStream_t st = (cudaStream_t)stream;
 
   const bool can4 = aligned16(a->x) && aligned16(a->out) && (a->ldx % 4 == 0) && (a->ldo % 4 == 0) &&
@@ -721,7 +721,7 @@ int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t 
     p.addend = a->addend ? a->addend + f0 : nullptr; p.ld_addend = a->ld_addend;
     p.addend_scale = a->addend_scale;
     p.bias = a->bias ? a->bias + f0 : nullptr; p.act = a->act;
-    p.mean = (a->op == KGB_OP_MEAN); p.negate = (a->op == KGB_OP_MIN);
+    p.mean = (a->op == KGB_OP_MEAN); p.negate = (a->op == KGB_OP_MIN); p.raw_max = (a->op == KGB_OP_MAX_RAW);
     p.out = a->out + f0; p.ldo = a->ldo; p.arg = a->arg ? a->arg + f0 : nullptr;
     p.hub_row = a->hub_row; p.hub_chunk_base = a->hub_chunk_base; p.hub_nchunks = a->hub_nchunks;
     p.chunk_hub = a->chunk_hub;
@@ -747,7 +747,7 @@ int kgb_gather_max_bwd(int device, const float* g, int64_t ldg, const int32_t* a
                        const int32_t* col, const int32_t* row_ids, int64_t n_rows, int32_t F,
                        int32_t op, float* gx, int64_t ldgx, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
-  KGB_REQUIRE(op == KGB_OP_MAX || op == KGB_OP_MIN, "op must be MAX or MIN");
+  KGB_REQUIRE(op == KGB_OP_MAX || op == KGB_OP_MIN || op == KGB_OP_MAX_RAW, "op must be MAX or MIN");
   KGB_REQUIRE(F > 0 && n_rows >= 0, "bad sizes");
   if (n_rows == 0) return KGB_OK;
   KGB_REQUIRE(g && arg && out && x && rowptr && col && gx, "NULL pointer");

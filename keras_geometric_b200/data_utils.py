@@ -1,0 +1,99 @@
+"""``GraphData`` / ``batch_graphs`` with the reference's interface
+(/root/reference/src/keras_geometric/utils/data_utils.py).  SURVEY 8(f) "next-2": the step right before the
+path for batched graph classification.  The reference builds the disjoint union with O(#graphs)
+``slice_update`` calls; here it is three concatenations plus two ``repeat_interleave`` on the device."""
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+import torch
+
+from ._compat import to_device_tensor
+
+
+class GraphData:
+    """data_utils.py:8-136."""
+
+    def __init__(self, x, edge_index, edge_attr=None, y=None, num_nodes=None, **kwargs: Any) -> None:
+        object.__setattr__(self, "_additional_data", {})
+        self.x = self._ensure_tensor(x)
+        self.edge_index = self._ensure_tensor(edge_index, torch.int32)
+        self.edge_attr = self._ensure_tensor(edge_attr) if edge_attr is not None else None
+        self.y = self._ensure_tensor(y) if y is not None else None
+        self._num_nodes = int(self.x.shape[0]) if num_nodes is None else num_nodes
+        for key, value in kwargs.items():
+            self._additional_data[key] = self._ensure_tensor(value)
+
+    @staticmethod
+    def _ensure_tensor(data, dtype=None):
+        if data is None:
+            return None
+        if isinstance(data, np.ndarray):
+            return to_device_tensor(data, dtype)
+        return data
+
+    @property
+    def num_nodes(self) -> int:
+        return self._num_nodes
+
+    @property
+    def num_edges(self) -> int:
+        return 0 if self.edge_index is None else int(self.edge_index.shape[1])
+
+    @property
+    def num_node_features(self) -> int:
+        return 0 if self.x is None else int(self.x.shape[1])
+
+    @property
+    def num_edge_features(self) -> int:
+        return 0 if self.edge_attr is None else int(self.edge_attr.shape[1])
+
+    def to_dict(self) -> dict:
+        d = {"x": self.x, "edge_index": self.edge_index}
+        if self.edge_attr is not None:
+            d["edge_attr"] = self.edge_attr
+        if self.y is not None:
+            d["y"] = self.y
+        d.update(self._additional_data)
+        return d
+
+    def to_inputs(self) -> list:
+        inputs = [self.x, self.edge_index]
+        if self.edge_attr is not None:
+            inputs.append(self.edge_attr)
+        return inputs
+
+    def __getattr__(self, name: str) -> Any:
+        extra = object.__getattribute__(self, "_additional_data")
+        if name in extra:
+            return extra[name]
+        raise AttributeError(f"'{self.__class__.__name__}' object has no attribute '{name}'")
+
+
+def batch_graphs(graphs: list) -> GraphData:
+    """Disjoint union of graphs (data_utils.py:139-272): node ids shifted by the running node count, a ``batch``
+    vector mapping every node to its graph, node- or graph-level targets stacked."""
+    if not graphs:
+        raise ValueError("Cannot batch empty list of graphs")
+    xs = [to_device_tensor(g.x, what="x") for g in graphs]
+    dev = xs[0].device
+    n_nodes = torch.tensor([g.num_nodes for g in graphs], dtype=torch.int64, device=dev)
+    n_edges = torch.tensor([g.num_edges for g in graphs], dtype=torch.int64, device=dev)
+    total_nodes = int(sum(g.num_nodes for g in graphs))
+    offsets = torch.cumsum(n_nodes, 0) - n_nodes
+    batch_x = torch.cat(xs, dim=0)
+    eis = [to_device_tensor(g.edge_index, what="edge_index") for g in graphs]
+    ei_dtype = eis[0].dtype
+    shift = torch.repeat_interleave(offsets, n_edges).to(ei_dtype)
+    batch_ei = torch.cat([e.reshape(2, -1).to(ei_dtype) for e in eis], dim=1) + shift.unsqueeze(0)
+    batch = torch.repeat_interleave(torch.arange(len(graphs), dtype=torch.int32, device=dev), n_nodes)
+    batch_ea = None
+    if all(g.edge_attr is not None for g in graphs):
+        batch_ea = torch.cat([to_device_tensor(g.edge_attr, what="edge_attr") for g in graphs], dim=0)
+    batch_y = None
+    if all(g.y is not None for g in graphs):
+        ys = [to_device_tensor(g.y, what="y") for g in graphs]
+        batch_y = torch.stack(ys, dim=0) if ys[0].dim() == 1 else torch.cat(ys, dim=0)
+    return GraphData(x=batch_x, edge_index=batch_ei, edge_attr=batch_ea, y=batch_y, num_nodes=total_nodes,
+                     batch=batch)

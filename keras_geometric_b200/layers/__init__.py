@@ -5,8 +5,9 @@ from .gatv2_conv import GATv2Conv
 from .gcn_conv import GCNConv
 from .gin_conv import GINConv
 from .message_passing import MessagePassing
+from .pooling import BatchGlobalPooling, GlobalPooling
 from .sage_conv import SAGEConv
 
 __all__ = ["MessagePassing", "GCNConv", "GINConv", "GATv2Conv", "SAGEConv", "Aggregator", "AggregatorFactory",
            "MeanAggregator", "MaxAggregator", "SumAggregator", "MinAggregator", "StdAggregator",
-           "PoolingAggregator"]
+           "PoolingAggregator", "GlobalPooling", "BatchGlobalPooling"]

@@ -18,7 +18,7 @@ _ACT = {None: _lib.ACT_NONE, "linear": _lib.ACT_NONE, "relu": _lib.ACT_RELU}
 # When set to a list, every gather-reduce launch appends {label, start, end, bytes} with CUDA events
 # recorded on the launching stream (bench.py reads it for the per-kernel roofline).
 PROFILE = None
-_OP_NAMES = {0: "sum", 1: "mean", 2: "max", 3: "min"}
+_OP_NAMES = {0: "sum", 1: "mean", 2: "max", 3: "min", 4: "max"}
 
 
 def _algorithmic_bytes(nnz, n_rows, F, per_edge_extra, per_row_extra):
@@ -137,7 +137,7 @@ class _GatherReduce(torch.autograd.Function):
         kw = {}
         ctx.weight_kind = None
         if weight is not None:
-            if op in (_lib.OP_MAX, _lib.OP_MIN):
+            if op in _lib.MAX_OPS:
                 raise ValueError("max/min aggregation does not take edge weights")
             if isinstance(weight, str) and weight == "gcn":
                 dis, _ = graph.gcn_norm()
@@ -157,7 +157,7 @@ class _GatherReduce(torch.autograd.Function):
                 ctx.w_coo = w
         addend_c = _f32c(addend, "addend") if addend is not None else None
         bias_c = _f32c(bias, "bias") if bias is not None else None
-        is_max = op in (_lib.OP_MAX, _lib.OP_MIN)
+        is_max = op in _lib.MAX_OPS
         if is_max and (addend is not None or bias is not None or act not in (None, "linear")):
             raise ValueError("max/min aggregation cannot be fused with an epilogue (ties are detected on the raw result)")
         out, arg = gather_reduce_raw(x, csr, op, addend=addend_c, addend_scale=addend_scale, bias=bias_c,
@@ -179,7 +179,7 @@ class _GatherReduce(torch.autograd.Function):
         graph, op = ctx.graph, ctx.op
         g = _f32c(g, "grad")
         saved = list(ctx.saved_tensors)
-        is_max = op in (_lib.OP_MAX, _lib.OP_MIN)
+        is_max = op in _lib.MAX_OPS
         out = saved[-1] if (is_max or ctx.act == "relu") else None
         if ctx.act == "relu":
             g = g * (out > 0)
@@ -225,7 +225,7 @@ class _SegmentReduce(torch.autograd.Function):
         op = _lib.OPS[op_name]
         m = _f32c(messages, "messages")
         csr = graph.csr
-        is_max = op in (_lib.OP_MAX, _lib.OP_MIN)
+        is_max = op in _lib.MAX_OPS
         out, arg = gather_reduce_raw(m, csr, op, col=csr.perm, want_arg=is_max)
         ctx.graph, ctx.op, ctx.n_msg = graph, op, int(m.shape[0])
         ctx.save_for_backward(*([m, arg, out] if is_max else []))
@@ -236,7 +236,7 @@ class _SegmentReduce(torch.autograd.Function):
     def backward(ctx, g):
         graph, op = ctx.graph, ctx.op
         g = _f32c(g, "grad")
-        if op in (_lib.OP_MAX, _lib.OP_MIN):
+        if op in _lib.MAX_OPS:
             m, arg, out = ctx.saved_tensors
             return _max_bwd(g, arg, out, m, graph.csr, graph.csr.perm, op, ctx.n_msg), None, None
         if op == _lib.OP_MEAN:

@@ -253,3 +253,39 @@ def stable_csr(edge_index, num_segments: int, by_source: bool = False):
     rowptr = np.zeros(num_segments + 1, dtype=np.int64)
     np.cumsum(deg, out=rowptr[1:])
     return rowptr, val[perm].astype(np.int32), perm.astype(np.int32), deg.astype(np.int32)
+
+
+# ------------------------------------------------------- layers/pooling/global_pooling.py, utils/data_utils.py
+
+
+def global_pooling(x, pooling: str = "mean"):
+    """layers/pooling/global_pooling.py:57-80 - whole-tensor mean/max/sum with keepdims -> [1, F]."""
+    fn = {"mean": ops.mean, "max": ops.max, "sum": ops.sum}[pooling]
+    return fn(ops.convert_to_tensor(x), axis=0, keepdims=True)
+
+
+def batch_global_pooling(x, batch, pooling: str = "mean"):
+    """layers/pooling/global_pooling.py:200-251 - segment mean/max/sum over the batch vector;
+    num_graphs = max(batch) + 1, mean divides by max(count, 1), max is the raw segment_max."""
+    x, batch = ops.convert_to_tensor(x), ops.convert_to_tensor(batch)
+    g = int(ops.max(batch)) + 1
+    if pooling == "sum":
+        return ops.segment_sum(x, batch, num_segments=g)
+    if pooling == "max":
+        return ops.segment_max(x, batch, num_segments=g)
+    total = ops.segment_sum(x, batch, num_segments=g)
+    cnt = ops.maximum(ops.segment_sum(ops.ones_like(batch, dtype=x.dtype), batch, num_segments=g), 1.0)
+    return total / ops.expand_dims(cnt, axis=1)
+
+
+def batch_graphs(xs, edge_indices):
+    """utils/data_utils.py:139-272 (node features, shifted edge_index, batch vector of the disjoint union)."""
+    import numpy as np
+
+    off, bx, bei, bb = 0, [], [], []
+    for i, (x, ei) in enumerate(zip(xs, edge_indices)):
+        bx.append(np.asarray(x))
+        bei.append(np.asarray(ei) + off)
+        bb.append(np.full(len(x), i, np.int32))
+        off += len(x)
+    return np.concatenate(bx), np.concatenate(bei, axis=1), np.concatenate(bb)

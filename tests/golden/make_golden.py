@@ -212,6 +212,39 @@ def main():
         save("gatv2_" + tag, kw, arrays)
 
 
+def extra():
+    """next-1 / next-2 rows of SURVEY 8(f): pooling read-outs and batch_graphs."""
+    from keras_geometric.layers.pooling import BatchGlobalPooling, GlobalPooling
+    rng = np.random.default_rng(77)
+    sizes = [5, 1, 9, 4, 12]
+    n, f = sum(sizes), 6
+    x = rng.standard_normal((n, f)).astype(np.float32)
+    batch = np.repeat(np.arange(len(sizes)), sizes).astype(np.int32)
+    arrays = {"x": x, "batch": batch}
+    for pool in ["mean", "max", "sum"]:
+        arrays["global_" + pool] = GlobalPooling(pooling=pool)(torch.from_numpy(x)).numpy()
+        xt = torch.from_numpy(x).clone().requires_grad_(True)
+        out = BatchGlobalPooling(pooling=pool)([xt, torch.from_numpy(batch)])
+        r = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+        (g,) = torch.autograd.grad((out * torch.from_numpy(r)).sum(), [xt])
+        arrays.update({"batch_" + pool: out.detach().numpy(), "R_" + pool: r, "grad_" + pool: g.numpy()})
+    save("pooling", {"sizes": sizes}, arrays)
+
+    graphs, arrays = [], {}
+    for i, (nn, ee) in enumerate([(4, 6), (3, 0), (6, 10)]):
+        gx = rng.standard_normal((nn, 3)).astype(np.float32)
+        gei = np.stack([rng.integers(0, nn, ee), rng.integers(0, nn, ee)]).astype(np.int32)
+        gy = rng.standard_normal((nn, 2)).astype(np.float32)
+        ga = rng.standard_normal((ee, 2)).astype(np.float32)
+        arrays.update({f"x{i}": gx, f"ei{i}": gei, f"y{i}": gy, f"ea{i}": ga})
+        graphs.append(kg.GraphData(x=gx, edge_index=gei, edge_attr=ga, y=gy))
+    b = kg.batch_graphs(graphs)
+    arrays.update({"bx": b.x.numpy(), "bei": b.edge_index.numpy(), "by": b.y.numpy(), "bea": b.edge_attr.numpy(),
+                   "bbatch": b.batch.numpy(), "bnum_nodes": b.num_nodes})
+    save("batch_graphs", {"n_graphs": 3}, arrays)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     main()
+    extra()

@@ -504,3 +504,33 @@ def test_linear_tensor_core_gemm(M, K, N):
     close(gx, (R.double() @ w64.t()).float(), rtol=1e-5, atol_scale=2e-6, msg="gemm dX")
     close(gw, (x64.t() @ R.double()).float(), rtol=1e-5, atol_scale=2e-6, msg="gemm dW")
     close(gad, R, msg="gemm d addend")
+
+
+# ------------------------------------------------------------------ SURVEY 8(f) next-1 / next-2
+def test_golden_pooling():
+    from keras_geometric_b200.layers import BatchGlobalPooling, GlobalPooling
+    g = load_golden("pooling")
+    for pool in ["mean", "max", "sum"]:
+        close(GlobalPooling(pooling=pool)(g["x"]), g["global_" + pool], msg="global " + pool)
+        x = cuda(g["x"]).requires_grad_(True)
+        out = BatchGlobalPooling(pooling=pool)([x, g["batch"]])
+        close(out, g["batch_" + pool], msg="batch " + pool)
+        (gx,) = torch.autograd.grad((out * cuda(g["R_" + pool])).sum(), [x])
+        close(gx, g["grad_" + pool], msg="batch grad " + pool)
+    with pytest.raises(ValueError, match="pooling must be one of"):
+        GlobalPooling(pooling="median")
+    assert BatchGlobalPooling().compute_output_shape([(10, 4), (10,)]) == (None, 4)
+
+
+def test_golden_batch_graphs():
+    import keras_geometric_b200 as kg
+    g = load_golden("batch_graphs")
+    graphs = [kg.GraphData(x=g[f"x{i}"], edge_index=g[f"ei{i}"], edge_attr=g[f"ea{i}"], y=g[f"y{i}"]) for i in range(3)]
+    b = kg.batch_graphs(graphs)
+    np.testing.assert_array_equal(b.x.cpu().numpy(), g["bx"])
+    np.testing.assert_array_equal(b.edge_index.cpu().numpy(), g["bei"])
+    np.testing.assert_array_equal(b.batch.cpu().numpy(), g["bbatch"])
+    np.testing.assert_array_equal(b.y.cpu().numpy(), g["by"])
+    np.testing.assert_array_equal(b.edge_attr.cpu().numpy(), g["bea"])
+    assert b.num_nodes == int(g["bnum_nodes"]) and b.num_edges == g["bei"].shape[1]
+    assert b.to_inputs()[1].dtype == torch.int32

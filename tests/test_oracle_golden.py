@@ -215,3 +215,19 @@ def test_keras_segment_semantics():
     ids = t(np.array([0, 5, -1], np.int32))
     np.testing.assert_array_equal(kops.segment_sum(d, ids, 2).numpy(), [[1.0], [0.0]])
     np.testing.assert_array_equal(kops.segment_max(d, ids, 2).numpy(), [[1.0], [-np.inf]])
+
+
+def test_golden_pooling_and_batch_graphs():
+    g = load_golden("pooling")
+    for pool in ["mean", "max", "sum"]:
+        np.testing.assert_allclose(ref.global_pooling(t(g["x"]), pool).numpy(), g["global_" + pool], rtol=RTOL, atol=ATOL)
+        x = t(g["x"]).clone().requires_grad_(True)
+        out = ref.batch_global_pooling(x, t(g["batch"]), pool)
+        np.testing.assert_allclose(out.detach().numpy(), g["batch_" + pool], rtol=RTOL, atol=ATOL)
+        (gr,) = torch.autograd.grad((out * t(g["R_" + pool])).sum(), [x])
+        np.testing.assert_allclose(gr.numpy(), g["grad_" + pool], rtol=RTOL, atol=ATOL)
+    g = load_golden("batch_graphs")
+    bx, bei, bb = ref.batch_graphs([g[f"x{i}"] for i in range(3)], [g[f"ei{i}"] for i in range(3)])
+    np.testing.assert_array_equal(bx, g["bx"])
+    np.testing.assert_array_equal(bei, g["bei"])
+    np.testing.assert_array_equal(bb, g["bbatch"])
