@@ -269,7 +269,7 @@ def cpu_reference_step_factory(sample_div: int):
         loss = torch.nn.functional.cross_entropy(h, y)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     return step, n, e
 
