@@ -153,6 +153,7 @@ typedef struct kgb_gather_reduce_args {
 size_t kgb_gather_reduce_partial_bytes(int32_t n_chunks, int32_t F, int32_t op);
 int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t stream);
 
+struct kgb_hub_table;
 /* Backward of MAX/MIN (torch.scatter_reduce(amax) semantics: the gradient is split evenly
  * between tied maxima).  gx must be zero-initialised by the caller; accumulates
  *   gx[arg[r,f], f] += g[r,f]                       (unique extremum)
@@ -162,7 +163,10 @@ int kgb_gather_max_bwd(int device, const float* g, int64_t ldg, const int32_t* a
                        const float* out, int64_t ldo, const float* x, int64_t ldx,
                        const int64_t* rowptr, const int32_t* col, const int32_t* row_ids,
                        int64_t n_rows, int32_t F, int32_t op, float* gx, int64_t ldgx,
-                       kgb_stream_t stream);
+                       const struct kgb_hub_table* hubs, kgb_stream_t stream);
+/* `hubs` (optional) lets tied entries of hub rows be resolved chunk-parallel; its `partial` workspace must
+ * hold kgb_gather_max_bwd_workspace_bytes(n_hubs, n_chunks, F) bytes. */
+size_t kgb_gather_max_bwd_workspace_bytes(int32_t n_hubs, int32_t n_chunks, int32_t F);
 
 /* out[r,:] = scale * src[idx[r],:]   (row gather: backward of the generic segment-sum w.r.t.
  * materialised messages, and the halo "pack" step of the partitioned path). idx may be NULL

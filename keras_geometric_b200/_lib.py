@@ -64,7 +64,8 @@ SIGNATURES = {
     "kgb_gather_reduce": (c_int, [c_int, POINTER(GatherReduceArgs), c_void_p]),
     "kgb_gather_max_bwd": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                    c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64,
-                                   c_void_p]),
+                                   POINTER(HubTable), c_void_p]),
+    "kgb_gather_max_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "kgb_gather_rows": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_float, c_void_p, c_int64,
                                 c_void_p]),
     "kgb_gatv2_partial_bytes": (c_size_t, [c_int32, c_int32, c_int32]),

@@ -60,15 +60,16 @@ __device__ __forceinline__ float fmax_nan(float a, float b) {
 template <bool IS_MAX, bool HAS_W = true>
 __device__ __forceinline__ void accum(float& m, int32_t& a, float v, float w, int32_t c, bool negate) {
   if constexpr (IS_MAX) {
+    // branch-free on purpose: an if/else chain compiles to divergent BSSY/BRA/BSYNC per element
     const float val = negate ? -v : v;
     const float mo = m;
     m = fmax_nan(mo, val);
-    if (val > mo) {
-      a = c;
-    } else if (val == mo && c != a) {
-      a = -2;  // tie between different sources: backward re-walks the row.  Parallel edges from the same
-               // source are not a tie: their even shares add up to the whole gradient on that one row.
-    }
+    const bool gt = val > mo;
+    const bool eq = val == mo;
+    // tie between different sources: backward re-walks the row.  Parallel edges from the same source are
+    // not a tie: their even shares add up to the whole gradient on that one row.
+    const int32_t a_eq = (c != a) ? -2 : a;
+    a = gt ? c : (eq ? a_eq : a);
   } else {
     if constexpr (HAS_W) m = __fadd_rn(m, __fmul_rn(w, v));  // mul then add, like message*w then segment_sum
     else m = __fadd_rn(m, v);
@@ -473,74 +474,185 @@ __global__ void __launch_bounds__(256) hub_finish_kernel(const GRP p) {
 }
 
 // ---- backward of max/min -------------------------------------------------------------------
-template <int VEC, int G, int NCH>
-__global__ void __launch_bounds__(256)
-gather_max_bwd_kernel(const float* __restrict__ g, int64_t ldg, const int32_t* __restrict__ arg,
-                      const float* __restrict__ out, int64_t ldo, const float* __restrict__ x,
-                      int64_t ldx, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                      const int32_t* __restrict__ row_ids, int64_t n_rows, int F,
-                      float* __restrict__ gx, int64_t ldgx) {
-  constexpr int GPW = 32 / G;
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % G;
-  const int gw = lane / G;
-  const unsigned gmask = group_mask(lane, G);
-  const int nv = F / VEC;
-  bool on[NCH];
+// torch.scatter_reduce(amax) backward: g[r,f] goes to the source attaining the extremum; when several
+// DIFFERENT sources tie (arg == -2) it is split evenly over every tied edge.  Unique entries are an
+// N*F scatter (no edge traffic).  Tied entries re-walk the row with batched index loads; tied entries
+// of hub rows are handled chunk-parallel by three small follow-up kernels (count, total, scatter).
+struct MaxBwdP {
+  const float* g; int64_t ldg; const int32_t* arg; const float* out; int64_t ldo;
+  const float* x; int64_t ldx; const int64_t* rowptr; const int32_t* col; const int32_t* row_ids;
+  int64_t n_rows; int F; float* gx; int64_t ldgx;
+  const int32_t* hub_row; const int32_t* hub_chunk_base; const int32_t* hub_nchunks; const int32_t* chunk_hub;
+  int n_hubs; int n_chunks; int hub_threshold; int hub_chunk;
+  float* cnt_partial;  // [n_chunks, F]
+  float* cnt_total;    // [n_hubs, F]
+  int32_t* hub_tie;    // [n_hubs]
+};
+
+// Walk CSR slots [k0, k1): phase 0 counts, per element, the edges whose source value equals o; phase 1
+// adds gv / cnt to those sources.  Only elements with a == -2 take part.
+template <int VEC, int G, int NCH, int PHASE>
+__device__ __forceinline__ void tie_walk(const MaxBwdP& p, int64_t k0, int64_t k1, int gl, unsigned gmask,
+                                         const bool (&on)[NCH], const int32_t (&a)[NCH][VEC],
+                                         const float (&o)[NCH][VEC], const float (&gv)[NCH][VEC],
+                                         float (&cnt)[NCH][VEC]) {
+  constexpr int U = (G < 4) ? G : 4;
+  int loff[NCH];
 #pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) on[ch] = (gl + ch * G) < nv;
-  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
-  for (int64_t s = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; s < n_rows;
-       s += (int64_t)gridDim.x * gpb) {
-    const int64_t r = row_ids ? (int64_t)__ldg(row_ids + s) : s;
-    float gv[NCH][VEC];
-    int32_t a[NCH][VEC];
-    bool tie = false;
+  for (int ch = 0; ch < NCH; ++ch) loff[ch] = on[ch] ? (gl + ch * G) * VEC : 0;
+  for (int64_t k = k0; k < k1; k += G) {
+    const int64_t rem = k1 - k;
+    const int cnt_e = rem < G ? (int)rem : G;
+    const int32_t myc = (k + gl < k1) ? __ldg(p.col + k + gl) : 0;
+#pragma unroll 1
+    for (int j = 0; j < cnt_e; j += U) {
+      float v[U][NCH][VEC];
+      int32_t c[U];
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
+      for (int u = 0; u < U; ++u) {
+        c[u] = __shfl_sync(gmask, myc, j + u, G);
+        const float* rp = p.x + (int64_t)c[u] * p.ldx;
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) { gv[ch][e] = 0.f; a[ch][e] = -1; }
-      if (!on[ch]) continue;
-      const int f0 = (gl + ch * G) * VEC;
-      ld_vec<VEC>(g + r * ldg + f0, gv[ch]);
-      ld_vec_i<VEC>(arg + r * ldo + f0, a[ch]);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        if (a[ch][e] >= 0) atomicAdd(gx + (int64_t)a[ch][e] * ldgx + f0 + e, gv[ch][e]);
-        tie |= (a[ch][e] == -2);
+        for (int ch = 0; ch < NCH; ++ch) ld_vec<VEC>(rp + loff[ch], v[u][ch]);
       }
-    }
-    if (__ballot_sync(gmask, tie) & gmask) {
-      // torch.scatter_reduce(amax) backward: split g evenly over every edge attaining the extremum
-      float o[NCH][VEC];
-      float cnt[NCH][VEC];
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
+      for (int u = 0; u < U; ++u) {
+        if ((j + u) >= cnt_e) continue;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) { o[ch][e] = 0.f; cnt[ch][e] = 0.f; }
-        if (on[ch]) ld_vec<VEC>(out + r * ldo + (gl + ch * G) * VEC, o[ch]);
-      }
-      const int64_t rs = __ldg(rowptr + s), re = __ldg(rowptr + s + 1);
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int64_t k = rs; k < re; ++k) {
-          const int64_t c = __ldg(col + k);
+        for (int ch = 0; ch < NCH; ++ch) {
+          if (!on[ch]) continue;
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) {
-            if (!on[ch]) continue;
-            const int f0 = (gl + ch * G) * VEC;
-            float v[VEC];
-            ld_vec<VEC>(x + c * ldx + f0, v);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-              if (a[ch][e] == -2 && v[e] == o[ch][e]) {
-                if (pass == 0) cnt[ch][e] += 1.f;
-                else atomicAdd(gx + c * ldgx + f0 + e, __fdiv_rn(gv[ch][e], cnt[ch][e]));
-              }
+          for (int e = 0; e < VEC; ++e) {
+            if (a[ch][e] == -2 && v[u][ch][e] == o[ch][e]) {
+              if (PHASE == 0) cnt[ch][e] += 1.f;
+              else atomicAdd(p.gx + (int64_t)c[u] * p.ldgx + (gl + ch * G) * VEC + e, __fdiv_rn(gv[ch][e], cnt[ch][e]));
             }
           }
         }
       }
     }
+  }
+}
+
+template <int VEC, int G, int NCH>
+__device__ __forceinline__ bool max_bwd_load_row(const MaxBwdP& p, int64_t r, int gl, unsigned gmask,
+                                                 const bool (&on)[NCH], float (&gv)[NCH][VEC], int32_t (&a)[NCH][VEC]) {
+  bool tie = false;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { gv[ch][e] = 0.f; a[ch][e] = -1; }
+    if (!on[ch]) continue;
+    const int f0 = (gl + ch * G) * VEC;
+    ld_vec<VEC>(p.g + r * p.ldg + f0, gv[ch]);
+    ld_vec_i<VEC>(p.arg + r * p.ldo + f0, a[ch]);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      if (a[ch][e] >= 0) atomicAdd(p.gx + (int64_t)a[ch][e] * p.ldgx + f0 + e, gv[ch][e]);
+      tie |= (a[ch][e] == -2);
+    }
+  }
+  return (__ballot_sync(gmask, tie) & gmask) != 0;
+}
+
+// pass 1: every row scatters its unique entries; non-hub rows with ties re-walk themselves; hub rows
+// (mode 1, one group per hub) only raise hub_tie[h]
+template <int VEC, int G, int NCH, int MODE>
+__global__ void __launch_bounds__(256) gather_max_bwd_kernel(const MaxBwdP p) {
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int gw = lane / G;
+  const unsigned gmask = group_mask(lane, G);
+  const int nv = p.F / VEC;
+  bool on[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) on[ch] = (gl + ch * G) < nv;
+  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
+  const int64_t n_items = MODE == 0 ? p.n_rows : (int64_t)p.n_hubs;
+  for (int64_t it = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; it < n_items;
+       it += (int64_t)gridDim.x * gpb) {
+    const int64_t s = MODE == 0 ? it : (int64_t)__ldg(p.hub_row + it);
+    const int64_t rs = __ldg(p.rowptr + s), re = __ldg(p.rowptr + s + 1);
+    if (MODE == 0 && p.n_hubs > 0 && (re - rs) > p.hub_threshold) continue;  // hub rows: mode-1 launch
+    const int64_t r = p.row_ids ? (int64_t)__ldg(p.row_ids + s) : s;
+    float gv[NCH][VEC];
+    int32_t a[NCH][VEC];
+    const bool any_tie = max_bwd_load_row<VEC, G, NCH>(p, r, gl, gmask, on, gv, a);
+    if (!any_tie) continue;
+    if (MODE == 1) {
+      if (gl == 0) p.hub_tie[it] = 1;
+      continue;
+    }
+    float o[NCH][VEC], cnt[NCH][VEC];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { o[ch][e] = 0.f; cnt[ch][e] = 0.f; }
+      if (on[ch]) ld_vec<VEC>(p.out + r * p.ldo + (gl + ch * G) * VEC, o[ch]);
+    }
+    tie_walk<VEC, G, NCH, 0>(p, rs, re, gl, gmask, on, a, o, gv, cnt);
+    tie_walk<VEC, G, NCH, 1>(p, rs, re, gl, gmask, on, a, o, gv, cnt);
+  }
+}
+
+// pass 2 (PHASE 0): per chunk of a hub row that has ties, count the tied edges -> cnt_partial[t,:]
+// pass 4 (PHASE 1): per chunk, scatter g / cnt_total to the tied edges
+template <int VEC, int G, int NCH, int PHASE>
+__global__ void __launch_bounds__(256) max_bwd_hub_chunk_kernel(const MaxBwdP p) {
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int gw = lane / G;
+  const unsigned gmask = group_mask(lane, G);
+  const int nv = p.F / VEC;
+  bool on[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) on[ch] = (gl + ch * G) < nv;
+  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
+  for (int64_t t = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; t < p.n_chunks;
+       t += (int64_t)gridDim.x * gpb) {
+    const int h = __ldg(p.chunk_hub + t);
+    if (p.hub_tie[h] == 0) continue;
+    const int64_t s = __ldg(p.hub_row + h);
+    const int64_t r = p.row_ids ? (int64_t)__ldg(p.row_ids + s) : s;
+    const int64_t ci = t - __ldg(p.hub_chunk_base + h);
+    const int64_t rs = __ldg(p.rowptr + s), re = __ldg(p.rowptr + s + 1);
+    const int64_t k0 = rs + ci * p.hub_chunk;
+    const int64_t k1 = (k0 + p.hub_chunk < re) ? k0 + p.hub_chunk : re;
+    float gv[NCH][VEC], o[NCH][VEC], cnt[NCH][VEC];
+    int32_t a[NCH][VEC];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { gv[ch][e] = 0.f; o[ch][e] = 0.f; cnt[ch][e] = 0.f; a[ch][e] = -1; }
+      if (!on[ch]) continue;
+      const int f0 = (gl + ch * G) * VEC;
+      ld_vec<VEC>(p.g + r * p.ldg + f0, gv[ch]);
+      ld_vec_i<VEC>(p.arg + r * p.ldo + f0, a[ch]);
+      ld_vec<VEC>(p.out + r * p.ldo + f0, o[ch]);
+      if (PHASE == 1) ld_vec<VEC>(p.cnt_total + (int64_t)h * p.F + f0, cnt[ch]);
+    }
+    tie_walk<VEC, G, NCH, PHASE>(p, k0, k1, gl, gmask, on, a, o, gv, cnt);
+    if (PHASE == 0) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+        if (on[ch]) st_vec<VEC>(p.cnt_partial + t * (int64_t)p.F + (gl + ch * G) * VEC, cnt[ch]);
+    }
+  }
+}
+
+// pass 3: cnt_total[h,:] = sum over the hub's chunks of cnt_partial (only hubs with ties)
+__global__ void __launch_bounds__(256) max_bwd_hub_total_kernel(const MaxBwdP p) {
+  const int64_t total = (int64_t)p.n_hubs * p.F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int h = (int)(i / p.F), f = (int)(i % p.F);
+    if (p.hub_tie[h] == 0) continue;
+    const int64_t base = __ldg(p.hub_chunk_base + h);
+    const int nch = __ldg(p.hub_nchunks + h);
+    float s = 0.f;
+    for (int c = 0; c < nch; ++c) s += p.cnt_partial[(base + c) * p.F + f];
+    p.cnt_total[i] = s;
   }
 }
 
@@ -742,28 +854,62 @@ int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t 
   return KGB_OK;
 }
 
+size_t kgb_gather_max_bwd_workspace_bytes(int32_t n_hubs, int32_t n_chunks, int32_t F) {
+  if (n_hubs <= 0 || n_chunks <= 0) return 0;
+  return align_up((size_t)n_chunks * F * sizeof(float), 256) + align_up((size_t)n_hubs * F * sizeof(float), 256) +
+         align_up((size_t)n_hubs * sizeof(int32_t), 256);
+}
+
 int kgb_gather_max_bwd(int device, const float* g, int64_t ldg, const int32_t* arg, const float* out,
                        int64_t ldo, const float* x, int64_t ldx, const int64_t* rowptr,
                        const int32_t* col, const int32_t* row_ids, int64_t n_rows, int32_t F,
-                       int32_t op, float* gx, int64_t ldgx, kgb_stream_t stream) {
+                       int32_t op, float* gx, int64_t ldgx, const kgb_hub_table* hubs, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(op == KGB_OP_MAX || op == KGB_OP_MIN || op == KGB_OP_MAX_RAW, "op must be MAX or MIN");
   KGB_REQUIRE(F > 0 && n_rows >= 0, "bad sizes");
   if (n_rows == 0) return KGB_OK;
   KGB_REQUIRE(g && arg && out && x && rowptr && col && gx, "NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  const bool use_hubs = hubs && hubs->n_hubs > 0 && hubs->n_chunks > 0 && hubs->partial;
   const bool can4 = aligned16(g) && aligned16(arg) && aligned16(out) && aligned16(x) && ldg % 4 == 0 &&
-                    ldo % 4 == 0 && ldx % 4 == 0;
+                    ldo % 4 == 0 && ldx % 4 == 0 && (!use_hubs || aligned16(hubs->partial));
   const int vec = (can4 && F % 4 == 0) ? 4 : 1;
   const int slab = 32 * 4 * vec;
   for (int f0 = 0; f0 < F; f0 += slab) {
     const int Fs = (F - f0 < slab) ? (F - f0) : slab;
+    MaxBwdP p = {};
+    p.g = g + f0; p.ldg = ldg; p.arg = arg + f0; p.out = out + f0; p.ldo = ldo; p.x = x + f0; p.ldx = ldx;
+    p.rowptr = rowptr; p.col = col; p.row_ids = row_ids; p.n_rows = n_rows; p.F = Fs; p.gx = gx + f0; p.ldgx = ldgx;
+    if (use_hubs) {
+      p.hub_row = hubs->hub_row; p.hub_chunk_base = hubs->hub_chunk_base; p.hub_nchunks = hubs->hub_nchunks;
+      p.chunk_hub = hubs->chunk_hub; p.n_hubs = hubs->n_hubs; p.n_chunks = hubs->n_chunks;
+      p.hub_threshold = hubs->threshold; p.hub_chunk = hubs->chunk;
+      char* w = reinterpret_cast<char*>(hubs->partial);
+      p.cnt_partial = reinterpret_cast<float*>(w);
+      w += align_up((size_t)p.n_chunks * F * sizeof(float), 256);
+      p.cnt_total = reinterpret_cast<float*>(w);
+      w += align_up((size_t)p.n_hubs * F * sizeof(float), 256);
+      p.hub_tie = reinterpret_cast<int32_t*>(w);
+      KGB_CHECK_CUDA(cudaMemsetAsync(p.hub_tie, 0, (size_t)p.n_hubs * sizeof(int32_t), st));
+    }
     Shape s = pick_shape(Fs, vec == 4);
     const int grid = grid_for(device, n_rows, s.g);
-    KGB_DISPATCH_SHAPE(s, (gather_max_bwd_kernel<V, G_, N_><<<grid, 256, 0, st>>>(
-                              g + f0, ldg, arg + f0, out + f0, ldo, x + f0, ldx, rowptr, col, row_ids,
-                              n_rows, Fs, gx + f0, ldgx)));
+    KGB_DISPATCH_SHAPE(s, (gather_max_bwd_kernel<V, G_, N_, 0><<<grid, 256, 0, st>>>(p)));
     KGB_CHECK_LAUNCH();
+    if (use_hubs) {
+      const int hgrid = grid_for(device, p.n_hubs, s.g);
+      const int cgrid = grid_for(device, p.n_chunks, s.g);
+      KGB_DISPATCH_SHAPE(s, (gather_max_bwd_kernel<V, G_, N_, 1><<<hgrid, 256, 0, st>>>(p)));
+      KGB_CHECK_LAUNCH();
+      KGB_DISPATCH_SHAPE(s, (max_bwd_hub_chunk_kernel<V, G_, N_, 0><<<cgrid, 256, 0, st>>>(p)));
+      KGB_CHECK_LAUNCH();
+      int64_t tg = ceil_div((int64_t)p.n_hubs * Fs, 256);
+      if (tg > (int64_t)sm_count(device) * 8) tg = (int64_t)sm_count(device) * 8;
+      max_bwd_hub_total_kernel<<<(int)tg, 256, 0, st>>>(p);
+      KGB_CHECK_LAUNCH();
+      KGB_DISPATCH_SHAPE(s, (max_bwd_hub_chunk_kernel<V, G_, N_, 1><<<cgrid, 256, 0, st>>>(p)));
+      KGB_CHECK_LAUNCH();
+    }
   }
   return KGB_OK;
 }

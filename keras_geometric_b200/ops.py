@@ -95,10 +95,12 @@ def _max_bwd(g, arg, out, x, csr: Csr, col, op: int, n_src_rows: int):
     F = int(g.shape[1])
     gx = torch.zeros((n_src_rows, F), dtype=torch.float32, device=g.device)
     if csr.n_rows and F:
+        st = _stream(g.device)
+        hubs = csr.hub_table(lib.kgb_gather_max_bwd_workspace_bytes(csr.n_hubs, csr.n_chunks, F), st)
         _lib.check(lib.kgb_gather_max_bwd(g.device.index, g.data_ptr(), g.stride(0), arg.data_ptr(), out.data_ptr(),
                                           out.stride(0), x.data_ptr(), x.stride(0), csr.rowptr.data_ptr(),
                                           col.data_ptr(), None, csr.n_rows, F, op, gx.data_ptr(), gx.stride(0),
-                                          _stream(g.device)), "kgb_gather_max_bwd")
+                                          ctypes.byref(hubs), st), "kgb_gather_max_bwd")
     return gx
 
 

@@ -1,5 +1,5 @@
 import ctypes, sys, os, torch
-lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_scratch", "cut_t.so"))
+lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_scratch", sys.argv[1] if len(sys.argv) > 1 else "cut_t.so"))
 lib.run_nn.restype = ctypes.c_int
 lib.run_nn.argtypes = [ctypes.c_void_p]*4 + [ctypes.c_int]*3 + [ctypes.c_float]*2 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
 dev = torch.device("cuda")
