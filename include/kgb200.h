@@ -245,6 +245,19 @@ int kgb_dense_gemm(int device, int mode, const float* A, int64_t lda, int64_t ba
                    int M, int N, int K, int L, float alpha, float beta, void* ws, size_t ws_bytes,
                    kgb_stream_t stream);
 
+/* K8, hand-written variant (csrc/tc_gemm.cu): D[M,N] = A[M,K] * Wt[N,K]^T (+ C) (+ bias) (ReLU) with
+ * tcgen05.mma.kind::tf32 and a 3xTF32 split (fp32-accurate), TMA operand staging, TMEM accumulators, one persistent
+ * warp-specialised CTA per SM.  Wt must be pre-split by kgb_split_tf32 into wt_hi / wt_lo, each a dense
+ * [kgb_linear_tc_rows(N), K] fp32 matrix whose rows >= N are zero.  Needs M >= 128, N <= 256, N % 4 == K % 4 == 0,
+ * 16-byte aligned pointers and leading dimensions that are multiples of 4. */
+int32_t kgb_linear_tc_rows(int32_t N);
+/* hi = tf32-truncated W, lo = W - hi; written transposed ([cols, rows]) when transpose != 0 */
+int kgb_split_tf32(int device, const float* w, int32_t rows, int32_t cols, int64_t ld, int32_t transpose,
+                   float* hi, float* lo, kgb_stream_t stream);
+int kgb_linear_tc(int device, const float* A, int64_t lda, int32_t M, int32_t K, const float* wt_hi,
+                  const float* wt_lo, int32_t N, const float* C, int64_t ldc, const float* bias, int32_t act,
+                  float* D, int64_t ldd, kgb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

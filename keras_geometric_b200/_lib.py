@@ -84,6 +84,10 @@ SIGNATURES = {
     "kgb_dense_gemm": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                                c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
                                c_size_t, c_void_p]),
+    "kgb_linear_tc_rows": (c_int32, [c_int32]),
+    "kgb_split_tf32": (c_int, [c_int, c_void_p, c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "kgb_linear_tc": (c_int, [c_int, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
+                              c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
 }
 GEMM_NN, GEMM_NT, GEMM_TN = 0, 1, 2
 

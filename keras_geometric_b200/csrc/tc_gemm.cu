@@ -1,0 +1,407 @@
+// K8 (hand-written): fp32-accurate dense transform  D[M,N] = A[M,K] * Wt[N,K]^T (+ C) (+ bias) (ReLU)
+// on the 5th-generation tensor cores, written directly against PTX (no CUTLASS):
+//
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a multi-stage shared-memory ring,
+//   * tcgen05.mma.kind::tf32 issued by ONE thread, fp32 accumulators in TMEM (2 x BN columns, double buffered),
+//   * "3xTF32" split for fp32 accuracy without an extra HBM pass: transform warps rewrite the fp32 A tile in
+//     shared memory as A_hi = round_tf32(A) (in place) and A_lo = round_tf32(A - A_hi) (second tile); the
+//     (tiny) weight matrix is split once per call into Wt_hi / Wt_lo in global memory;
+//     each k-step issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is ~2^-22),
+//   * warp-specialised persistent CTAs (one per SM): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
+//     warps 2-5 transform, warps 6-9 epilogue (tcgen05.ld -> registers -> +C/+bias/ReLU -> global),
+//     connected by mbarriers (full / lo-ready / empty per stage, tmem-full / tmem-empty per accumulator).
+//
+// M is the node dimension (millions), N <= 256 and K are feature widths: the A stream is read once from HBM,
+// W stays in L2.  SASS: UTCHMMA-class UTCMMA (tf32), UTMALDG, LDTM.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace kgb {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;  // 32 fp32 = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 320;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// fp32 -> (hi, lo) with hi = a rounded to tf32 (10 explicit mantissa bits) and lo = tf32-rounded remainder; rounding
+// (instead of the truncation the tensor core applies to raw fp32) keeps the split error unbiased.  inf/nan: lo = 0.
+__device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u);
+  float r = a - hi;
+  r = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+  lo = (fabsf(r) <= 3.0e38f) ? r : 0.f;
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address >> 4 [0,14), LBO [16,30) (unused for swizzled K-major, 1), SBO [32,46) = 1024 B between 8-row groups,
+// version [46,48) = 1 (Blackwell), layout type [61,64) = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct TcParams {
+  int M, N, K;
+  const float* C; int64_t ldc;   // optional addend
+  const float* bias;             // optional [N]
+  int relu;
+  float* D; int64_t ldd;
+  int n_tiles;
+};
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
+  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+               const __grid_constant__ CUtensorMap map_blo, const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int S = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;            // [S]  TMA bytes landed
+  uint64_t* lo_rdy = bars + S;      // [S]  A_lo written
+  uint64_t* empty = bars + 2 * S;   // [S]  MMAs that read the stage retired
+  uint64_t* tfull = bars + 3 * S;   // [2]  accumulator complete
+  uint64_t* tempty = tfull + 2;     // [2]  accumulator drained
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(lo_rdy + s, 4);   // one arrival per transform warp
+      mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b, 1);
+      mbar_init(tempty + b, 4);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 2 accumulators of BN fp32 columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                 "r"(2 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  auto sA = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
+  auto sAlo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+  auto sBhi = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES; };
+  auto sBlo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES + Cfg::B_BYTES; };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_expect_tx(full + s, Cfg::A_BYTES + 2 * Cfg::B_BYTES);
+          tma_load_2d(sA(s), &map_a, full + s, kb * TC_BK, tile * TC_BM);
+          tma_load_2d(sBhi(s), &map_bhi, full + s, kb * TC_BK, 0);
+          tma_load_2d(sBlo(s), &map_blo, full + s, kb * TC_BK, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D fp32 (1<<4), A/B tf32 (2<<7, 2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      uint32_t it = 0;
+      int j = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
+        const int b = j & 1;
+        mbar_wait(tempty + b, ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + b * BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(full + s, ph);
+          mbar_wait(lo_rdy + s, ph);
+          tc_fence_after();
+          const uint64_t da_hi = make_desc(smem_u32(sA(s))), da_lo = make_desc(smem_u32(sAlo(s)));
+          const uint64_t db_hi = make_desc(smem_u32(sBhi(s))), db_lo = make_desc(smem_u32(sBlo(s)));
+#pragma unroll
+          for (int k4 = 0; k4 < TC_BK / 8; ++k4) {  // UMMA_K = 8 tf32 = 32 bytes: advance the start address
+            const uint64_t adv = (uint64_t)(k4 * 2);
+            umma_tf32(tmem_c, da_lo + adv, db_hi + adv, idesc, (kb | k4) != 0);
+            umma_tf32(tmem_c, da_hi + adv, db_lo + adv, idesc, 1);
+            umma_tf32(tmem_c, da_hi + adv, db_hi + adv, idesc, 1);
+          }
+          umma_commit(empty + s);  // frees the stage when these MMAs retire
+        }
+        umma_commit(tfull + b);    // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp < 6) {
+    // ===== transform warps: A -> (A_hi, A_lo) tf32 split (element-wise, so the swizzled layout is preserved) =====
+    const int t = threadIdx.x - 64;  // 0..127
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(full + s, ph);
+        float4* src = reinterpret_cast<float4*>(sA(s));
+        float4* dst = reinterpret_cast<float4*>(sAlo(s));
+#pragma unroll
+        for (int i = 0; i < Cfg::A_BYTES / 16 / 128; ++i) {
+          const float4 v = src[t + i * 128];
+          float4 h, r;
+          split_tf32(v.x, h.x, r.x);
+          split_tf32(v.y, h.y, r.y);
+          split_tf32(v.z, h.z, r.z);
+          split_tf32(v.w, h.w, r.w);
+          src[t + i * 128] = h;   // the TMA tile becomes the (rounded) high operand in place
+          dst[t + i * 128] = r;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(lo_rdy + s);
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> (+C, +bias, ReLU) -> global =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int j = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
+      const int b = j & 1;
+      mbar_wait(tfull + b, (j >> 1) & 1);
+      tc_fence_after();
+      const int64_t row = (int64_t)tile * TC_BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (c0 >= p.N) break;
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr + c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < p.M) {
+          float* drow = p.D + row * p.ldd + c0;
+          const float* crow = p.C ? p.C + row * p.ldc + c0 : nullptr;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            if (c0 + v * 4 >= p.N) break;  // N is a multiple of 4
+            float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                   __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+            if (crow) {
+              const float4 c = *reinterpret_cast<const float4*>(crow + v * 4);
+              o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+            }
+            if (p.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + v * 4));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (p.relu) {
+              o.x = o.x <= 0.f ? 0.f : o.x; o.y = o.y <= 0.f ? 0.f : o.y;
+              o.z = o.z <= 0.f ? 0.f : o.z; o.w = o.w <= 0.f ? 0.f : o.w;
+            }
+            *reinterpret_cast<float4*>(drow + v * 4) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + b);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+  }
+}
+
+// W [rows, cols] (row-major, ld) -> hi/lo tf32 parts, optionally transposed: out is [cols, rows] when transpose
+__global__ void split_tf32_kernel(const float* __restrict__ w, int rows, int cols, int64_t ld, int transpose,
+                                  float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float v = w[(int64_t)r * ld + c];
+    float h, l;
+    split_tf32(v, h, l);
+    const int64_t o = transpose ? (int64_t)c * rows + r : i;
+    hi[o] = h;
+    lo[o] = l;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] row-major with leading dimension ld, box = {TC_BK cols, box_rows rows}, 128B swizzle
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return KGB_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
+              (long long)cols, (long long)ld);
+    return KGB_ERR_CUDA;
+  }
+  return KGB_OK;
+}
+
+template <int BN>
+static int tc_launch(int device, const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p,
+                     cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_done[64] = {};
+  if (device < 64 && !attr_done[device]) {
+    KGB_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done[device] = true;
+  }
+  int grid = sm_count(device);
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  tc_gemm_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mh, ml, p);
+  KGB_CHECK_LAUNCH();
+  return KGB_OK;
+}
+
+}  // namespace kgb
+
+using namespace kgb;
+
+extern "C" {
+
+int32_t kgb_linear_tc_rows(int32_t N) { return N <= 64 ? 64 : (N <= 128 ? 128 : 256); }
+
+int kgb_split_tf32(int device, const float* w, int32_t rows, int32_t cols, int64_t ld, int32_t transpose, float* hi,
+                   float* lo, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(w && hi && lo && rows > 0 && cols > 0 && ld >= cols, "bad arguments");
+  const int64_t n = (int64_t)rows * cols;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 1184) grid = 1184;
+  split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, rows, cols, ld, transpose, hi, lo);
+  KGB_CHECK_LAUNCH();
+  return KGB_OK;
+}
+
+int kgb_linear_tc(int device, const float* A, int64_t lda, int32_t M, int32_t K, const float* wt_hi, const float* wt_lo,
+                  int32_t N, const float* C, int64_t ldc, const float* bias, int32_t act, float* D, int64_t ldd,
+                  kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(M >= 0 && N > 0 && K > 0, "bad sizes");
+  if (M == 0) return KGB_OK;
+  KGB_REQUIRE(M >= TC_BM, "kgb_linear_tc needs at least %d rows", TC_BM);
+  KGB_REQUIRE(A && wt_hi && wt_lo && D, "NULL operand");
+  KGB_REQUIRE(N <= 256 && N % 4 == 0 && K % 4 == 0, "kgb_linear_tc needs N <= 256 and N, K multiples of 4");
+  KGB_REQUIRE(aligned16(A) && aligned16(wt_hi) && aligned16(wt_lo) && aligned16(D) && (!C || aligned16(C)) &&
+                  (!bias || aligned16(bias)) && lda % 4 == 0 && ldd % 4 == 0 && (!C || ldc % 4 == 0),
+              "operands must be 16-byte aligned with leading dimensions multiple of 4");
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  CUtensorMap ma, mh, ml;
+  int rc = make_map(&ma, A, M, K, lda, TC_BM);
+  if (rc != KGB_OK) return rc;
+  rc = make_map(&mh, wt_hi, BN, K, K, BN);  // the split buffers are zero-padded to BN rows (kgb_linear_tc_rows)
+  if (rc != KGB_OK) return rc;
+  rc = make_map(&ml, wt_lo, BN, K, K, BN);
+  if (rc != KGB_OK) return rc;
+  TcParams p;
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.relu = (act == KGB_ACT_RELU);
+  p.D = D; p.ldd = ldd; p.n_tiles = (M + TC_BM - 1) / TC_BM;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 64) return tc_launch<64>(device, ma, mh, ml, p, st);
+  if (BN == 128) return tc_launch<128>(device, ma, mh, ml, p, st);
+  return tc_launch<256>(device, ma, mh, ml, p, st);
+}
+
+}  // extern "C"

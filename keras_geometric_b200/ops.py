@@ -398,17 +398,51 @@ def dense_gemm(mode: int, a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: i
 _SPLIT_ROWS = 8192  # rows of the long (node) dimension reduced by one CTA column in dW = X^T G
 
 
+def _tc_ok(M: int, n_out: int) -> bool:
+    return M >= 128 and n_out <= 256
+
+
+def _split_weight(w: torch.Tensor, transpose: bool):
+    """tf32 hi/lo parts of a weight matrix laid out [n_out, k] (zero-padded rows) for kgb_linear_tc."""
+    lib = _lib.load()
+    rows, cols = int(w.shape[0]), int(w.shape[1])
+    n_out, k = (cols, rows) if transpose else (rows, cols)
+    bn = lib.kgb_linear_tc_rows(n_out)
+    buf = torch.zeros((2, bn, k), dtype=torch.float32, device=w.device)
+    _lib.check(lib.kgb_split_tf32(w.device.index, w.data_ptr(), rows, cols, w.stride(0), int(transpose),
+                                  buf[0].data_ptr(), buf[1].data_ptr(), _stream(w.device)), "kgb_split_tf32")
+    return buf[0], buf[1]
+
+
+def linear_tc(a: torch.Tensor, w_hi: torch.Tensor, w_lo: torch.Tensor, n_out: int, *, c=None, bias=None,
+              relu: bool = False) -> torch.Tensor:
+    """One kgb_linear_tc launch: a [M,K] @ Wt[n_out,K]^T (+ c) (+ bias) (ReLU) on tcgen05 (3xTF32)."""
+    lib = _lib.load()
+    M, K = int(a.shape[0]), int(a.shape[1])
+    out = torch.empty((M, n_out), dtype=torch.float32, device=a.device)
+    _lib.check(lib.kgb_linear_tc(a.device.index, a.data_ptr(), a.stride(0), M, K, w_hi.data_ptr(), w_lo.data_ptr(),
+                                 n_out, _ptr(c), c.stride(0) if c is not None else 0, _ptr(bias),
+                                 _lib.ACT_RELU if relu else _lib.ACT_NONE, out.data_ptr(), out.stride(0),
+                                 _stream(a.device)), "kgb_linear_tc")
+    return out
+
+
 class _Linear(torch.autograd.Function):
-    """out = x @ w (+ addend) on the tensor cores (K8); falls back to torch.matmul (cuBLAS, on the GPU) only for
-    shapes the TMA alignment rules exclude (a dimension not divisible by 4)."""
+    """out = x @ w (+ addend) on the tensor cores (K8).  Forward and dX run the hand-written tcgen05 3xTF32 kernel
+    (csrc/tc_gemm.cu); dW = X^T G (reduction over the node dimension) runs the batched bf16x9 kernel
+    (csrc/dense_gemm_tn.cu).  torch.matmul (cuBLAS, on the GPU) is used only for shapes the TMA alignment rules
+    exclude (a dimension not divisible by 4)."""
 
     @staticmethod
     def forward(ctx, x, w, addend):
         x = _f32c(x, "x")
         w = _f32c(w, "w")
         ctx.fast = _gemm_ok(x, w, addend) and x.shape[0] > 0
-        if ctx.fast:
-            M, K, N = int(x.shape[0]), int(x.shape[1]), int(w.shape[1])
+        M, K, N = int(x.shape[0]), int(x.shape[1]), int(w.shape[1])
+        if ctx.fast and _tc_ok(M, N):
+            hi, lo = _split_weight(w, transpose=True)
+            out = linear_tc(x, hi, lo, N, c=addend)
+        elif ctx.fast:
             out = dense_gemm(_lib.GEMM_NN, x, w, M, N, K, c=addend, beta=1.0 if addend is not None else 0.0)
         else:
             out = torch.matmul(x, w)
@@ -429,7 +463,13 @@ class _Linear(torch.autograd.Function):
         M, K, N = int(x.shape[0]), int(x.shape[1]), int(w.shape[1])
         fast = ctx.fast and _gemm_ok(g)
         if ctx.needs_input_grad[0]:
-            gx = dense_gemm(_lib.GEMM_NT, g, w, M, K, N) if fast else torch.matmul(g, w.t())
+            if fast and _tc_ok(M, K):
+                hi, lo = _split_weight(w, transpose=False)  # dX = G @ W^T: W [K,N] already is "Wt" for output width K
+                gx = linear_tc(g, hi, lo, K)
+            elif fast:
+                gx = dense_gemm(_lib.GEMM_NT, g, w, M, K, N)
+            else:
+                gx = torch.matmul(g, w.t())
         if ctx.needs_input_grad[1]:
             if fast:
                 # dW[K,N] = X^T G: the reduction runs over the M nodes; cut it into slices that become the batch
