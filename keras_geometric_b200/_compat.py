@@ -360,10 +360,13 @@ else:
 
         def call(self, x, training=None):
             if x.is_cuda and x.dim() == 2:
-                from . import ops  # tensor-core transform (K8)
-                y = ops.linear(x, self.kernel)
-            else:
-                y = torch.matmul(x, self.kernel)
+                from . import ops  # tensor-core transform (K8) with bias / ReLU in the epilogue
+                name = getattr(self.activation, "__name__", None)
+                if name in ("relu", "linear"):
+                    return ops.linear(x, self.kernel, bias=self.bias, act=None if name == "linear" else "relu")
+                y = ops.linear(x, self.kernel, bias=self.bias)
+                return self.activation(y)
+            y = torch.matmul(x, self.kernel)
             if self.bias is not None:
                 y = y + self.bias
             return self.activation(y)

@@ -189,14 +189,16 @@ class SAGEConv(MessagePassing):
         return out[:, :fout] if pad else out
 
     def _dense_update(self, aggregated, x, w_neigh, w_self, bias, dropping=False):
-        """act(lin_self(x) + lin_neigh(agg) + b) (sage_conv.py:411-433) as two accumulating GEMMs."""
-        out = ops.linear(aggregated, w_neigh)
-        if w_self is not None:
+        """act(lin_self(x) + lin_neigh(agg) + b) (sage_conv.py:411-433) as two accumulating GEMMs; the second one
+        carries addend, bias and ReLU in its epilogue."""
+        fuse_relu = self._activation_id == "relu"
+        if w_self is None:
+            out = ops.linear(aggregated, w_neigh, bias=bias, act="relu" if fuse_relu else None)
+        else:
+            out = ops.linear(aggregated, w_neigh)
             x_self = Dropout(self.dropout_rate)(x, training=True) if dropping else x
-            out = ops.linear(x_self, w_self, addend=out)  # accumulates in the GEMM epilogue (beta = 1)
-        if bias is not None:
-            out = out + bias
-        if self.activation is not None:
+            out = ops.linear(x_self, w_self, addend=out, bias=bias, act="relu" if fuse_relu else None)
+        if self.activation is not None and not fuse_relu:
             out = self.activation(out)
         return out
 
@@ -222,10 +224,8 @@ class SAGEConv(MessagePassing):
             root = ops.linear(x, w_self) if w_self is not None else None   # ... behind the root transform
             pg.exchange_finish()
             aggregated = ops.gather_reduce(x_ext, pg.graph, self.actual_aggregator)
-            out = ops.linear(aggregated, w_neigh, addend=root)
-            if bias is not None:
-                out = out + bias
-            if self.activation is not None:
+            out = ops.linear(aggregated, w_neigh, addend=root, bias=bias, act="relu" if act_is_relu else None)
+            if self.activation is not None and not act_is_relu:
                 out = self.activation(out)
         if self.normalize:
             out = out / torch.clamp(torch.linalg.vector_norm(out, ord=2, dim=-1, keepdim=True), min=1e-12)

@@ -434,29 +434,40 @@ class _Linear(torch.autograd.Function):
     exclude (a dimension not divisible by 4)."""
 
     @staticmethod
-    def forward(ctx, x, w, addend):
+    def forward(ctx, x, w, addend, bias, act):
         x = _f32c(x, "x")
         w = _f32c(w, "w")
+        relu = act == "relu"
+        if act not in (None, "linear", "relu"):
+            raise ValueError(f"linear: unsupported fused activation {act!r}")
+        bias_c = _f32c(bias, "bias").contiguous() if bias is not None else None
         ctx.fast = _gemm_ok(x, w, addend) and x.shape[0] > 0
         M, K, N = int(x.shape[0]), int(x.shape[1]), int(w.shape[1])
         if ctx.fast and _tc_ok(M, N):
             hi, lo = _split_weight(w, transpose=True)
-            out = linear_tc(x, hi, lo, N, c=addend)
-        elif ctx.fast:
-            out = dense_gemm(_lib.GEMM_NN, x, w, M, N, K, c=addend, beta=1.0 if addend is not None else 0.0)
+            out = linear_tc(x, hi, lo, N, c=addend, bias=bias_c, relu=relu)  # epilogue fused in the GEMM
         else:
-            out = torch.matmul(x, w)
-            if addend is not None:
-                out = out + addend
-        ctx.save_for_backward(x, w)
-        ctx.has_addend = addend is not None
+            if ctx.fast:
+                out = dense_gemm(_lib.GEMM_NN, x, w, M, N, K, c=addend, beta=1.0 if addend is not None else 0.0)
+            else:
+                out = torch.matmul(x, w)
+                if addend is not None:
+                    out = out + addend
+            if bias_c is not None:
+                out = out + bias_c
+            if relu:
+                out = torch.relu(out)
+        ctx.save_for_backward(x, w, *([out] if relu else []))
+        ctx.has_addend, ctx.has_bias, ctx.relu = addend is not None, bias is not None, relu
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        x, w = ctx.saved_tensors
+        x, w = ctx.saved_tensors[:2]
         g = _f32c(g, "grad")
+        if ctx.relu:
+            g = g * (ctx.saved_tensors[2] > 0)
         if g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
             g = g.contiguous()
         gx = gw = None
@@ -490,9 +501,10 @@ class _Linear(torch.autograd.Function):
                                                             gw.data_ptr(), _stream(x.device)), "kgb_reduce_parts")
             else:
                 gw = torch.matmul(x.t(), g)
-        return gx, gw, (g if ctx.has_addend else None)
+        return gx, gw, (g if ctx.has_addend else None), (g.sum(dim=0) if ctx.has_bias else None), None
 
 
-def linear(x, w, addend=None) -> torch.Tensor:
-    """x @ w (+ addend) - the dense node-feature transform of every conv layer (K8)."""
-    return _Linear.apply(x, w, addend)
+def linear(x, w, addend=None, bias=None, act=None) -> torch.Tensor:
+    """act(x @ w + addend + bias) - the dense node-feature transform of every conv layer (K8); ``act`` in
+    (None, "relu").  Addend, bias and ReLU run in the GEMM epilogue."""
+    return _Linear.apply(x, w, addend, bias, act)
