@@ -258,6 +258,14 @@ int kgb_linear_tc(int device, const float* A, int64_t lda, int32_t M, int32_t K,
                   const float* wt_lo, int32_t N, const float* C, int64_t ldc, const float* bias, int32_t act,
                   float* D, int64_t ldd, kgb_stream_t stream);
 
+/* dW[Kx,N] = X[M,Kx]^T * G[M,N] with the same tcgen05 3xTF32 machinery (both operands MN-major, both split in
+ * shared memory).  The node dimension is cut into kgb_linear_tc_dw_parts() contiguous slices, one per CTA; slice p
+ * writes partials[p, :, :] and the caller adds the partials in order with kgb_reduce_parts (deterministic).
+ * Needs M >= 16, Kx, N <= 256 and multiples of 4, 16-byte aligned operands. */
+int32_t kgb_linear_tc_dw_parts(int device, int64_t M);
+int kgb_linear_tc_dw(int device, const float* X, int64_t ldx, const float* G, int64_t ldg, int32_t M, int32_t Kx,
+                     int32_t N, float* partials, int32_t n_parts, kgb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

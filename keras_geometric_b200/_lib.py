@@ -88,6 +88,9 @@ SIGNATURES = {
     "kgb_split_tf32": (c_int, [c_int, c_void_p, c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "kgb_linear_tc": (c_int, [c_int, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
                               c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
+    "kgb_linear_tc_dw_parts": (c_int32, [c_int, c_int64]),
+    "kgb_linear_tc_dw": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p,
+                                 c_int32, c_void_p]),
 }
 GEMM_NN, GEMM_NT, GEMM_TN = 0, 1, 2
 

@@ -286,6 +286,226 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+// --------------------------------------------------------------------------------------------------
+// dW[Kx,N] = X[M,Kx]^T * G[M,N]: the reduction runs over the M nodes, so BOTH operands are MN-major in memory
+// (their feature index is contiguous).  TMA boxes of {32 features x 16 nodes} with the 128B/32B-atom swizzle land as
+// canonical MN-major SWIZZLE_128B_BASE32B atoms (4 node-rows x 128 B); feature groups are LBO = 2 KB apart, 4-node
+// groups SBO = 512 B apart, one k-step (8 nodes) advances the start address by 1 KB.  Both tiles are split into tf32 hi/lo in shared memory (both operands are large here).
+// Every CTA reduces a contiguous slice of nodes into its own [Kx,N] partial (TMEM: up to 2 x 256 columns);
+// the partials are added in CTA order by kgb_reduce_parts (deterministic split-K, no atomics).
+// The tensor core adds into its fp32 accumulator with truncation, which biases long chains (1e-4 relative after
+// 16 k nodes), so the TMEM chain is cut every `chain_blocks` k-blocks (256 nodes): the epilogue warps add the chain's
+// result to the CTA's partial with IEEE fp32 adds (the partial is L2-resident) and the next chain starts from zero.
+constexpr int DW_R = 16;  // nodes per pipeline stage (2 k-steps of 8)
+
+struct DwParams {
+  int M, Kx, N;
+  int nodes_per_cta;
+  int chain_blocks;  // k-blocks (of DW_R nodes) accumulated in TMEM before the sum is promoted to fp32 in memory
+  float* partial;    // [gridDim.x, Kx, N]
+};
+
+template <int BN, int MT>
+struct DwCfg {
+  static constexpr int X_BYTES = MT * 128 * DW_R * 4;   // MT * 8 KB
+  static constexpr int G_BYTES = BN * DW_R * 4;         // BN * 64 B
+  static constexpr int HALF = X_BYTES + G_BYTES;        // raw (hi) tiles; the lo tiles follow
+  static constexpr int STAGE_BYTES = 2 * HALF;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+// MN-major descriptor for 32-bit operands: the only legal swizzle is SWIZZLE_128B_BASE32B (layout type 1): atoms of
+// 4 K-rows x 128 B with 32-byte chunks XOR-ed by the row index (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+// LBO = bytes between 32-element MN atoms, SBO = bytes between 4-row K groups.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (1ull << 61);
+}
+
+template <int BN, int MT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const DwParams p) {
+  using Cfg = DwCfg<BN, MT>;
+  constexpr int S = Cfg::STAGES;
+  constexpr int BOX = 32 * DW_R * 4;  // 2 KB per TMA box
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* lo_rdy = bars + S;
+  uint64_t* empty = bars + 2 * S;
+  uint64_t* tfull = bars + 3 * S;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t node0 = (int64_t)blockIdx.x * p.nodes_per_cta;
+  int64_t node1 = node0 + p.nodes_per_cta;
+  if (node1 > p.M) node1 = p.M;
+  const int kblocks = node1 > node0 ? (int)((node1 - node0 + DW_R - 1) / DW_R) : 0;
+  constexpr int TMEM_COLS = MT * BN < 32 ? 32 : MT * BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(lo_rdy + s, 4);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const int n_chains = (kblocks + p.chain_blocks - 1) / p.chain_blocks;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_expect_tx(full + s, Cfg::HALF);
+        uint8_t* base = smem + s * Cfg::STAGE_BYTES;
+        const int row = (int)(node0 + (int64_t)kb * DW_R);
+#pragma unroll
+        for (int b = 0; b < MT * 4; ++b) tma_load_2d(base + b * BOX, &map_x, full + s, b * 32, row);
+#pragma unroll
+        for (int b = 0; b < BN / 32; ++b) tma_load_2d(base + Cfg::X_BYTES + b * BOX, &map_g, full + s, b * 32, row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D fp32, A/B tf32, both MN-major (bits 15, 16)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        const int chain = kb / p.chain_blocks, kc = kb % p.chain_blocks;
+        if (kc == 0) {  // new accumulation chain: the epilogue must have drained the previous one
+          mbar_wait(tempty, (chain & 1) ^ 1);
+          tc_fence_after();
+        }
+        mbar_wait(full + s, ph);
+        mbar_wait(lo_rdy + s, ph);
+        tc_fence_after();
+        const uint32_t hi = smem_u32(smem + s * Cfg::STAGE_BYTES), lo = hi + Cfg::HALF;
+#pragma unroll
+        for (int ks = 0; ks < DW_R / 8; ++ks) {
+          const uint64_t gb_hi = make_desc_mn(hi + Cfg::X_BYTES + ks * 1024, BOX, 512);
+          const uint64_t gb_lo = make_desc_mn(lo + Cfg::X_BYTES + ks * 1024, BOX, 512);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t xa_hi = make_desc_mn(hi + mt * 4 * BOX + ks * 1024, BOX, 512);
+            const uint64_t xa_lo = make_desc_mn(lo + mt * 4 * BOX + ks * 1024, BOX, 512);
+            const uint32_t tc = tmem_base + mt * BN;
+            umma_tf32(tc, xa_lo, gb_hi, idesc, (kc | ks) != 0);
+            umma_tf32(tc, xa_hi, gb_lo, idesc, 1);
+            umma_tf32(tc, xa_hi, gb_hi, idesc, 1);
+          }
+        }
+        umma_commit(empty + s);
+        if (kc == p.chain_blocks - 1 || kb == kblocks - 1) umma_commit(tfull);  // chain complete
+      }
+    }
+  } else if (warp < 6) {
+    const int t = threadIdx.x - 64;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      const int s = kb % S;
+      const uint32_t ph = (kb / S) & 1;
+      mbar_wait(full + s, ph);
+      float4* src = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES);
+      float4* dst = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES + Cfg::HALF);
+#pragma unroll 4
+      for (int i = t; i < Cfg::HALF / 16; i += 128) {
+        const float4 v = src[i];
+        float4 h, r;
+        split_tf32(v.x, h.x, r.x);
+        split_tf32(v.y, h.y, r.y);
+        split_tf32(v.z, h.z, r.z);
+        split_tf32(v.w, h.w, r.w);
+        src[i] = h;
+        dst[i] = r;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(lo_rdy + s);
+    }
+  } else {
+    // epilogue: after every chain, partial (+)= accumulator with IEEE fp32 adds; a CTA without nodes writes zeros
+    const int q = warp & 3;
+    float* out = p.partial + (int64_t)blockIdx.x * p.Kx * p.N;
+    const int passes = n_chains > 0 ? n_chains : 1;
+#pragma unroll 1
+    for (int chain = 0; chain < passes; ++chain) {
+      if (n_chains > 0) {
+        mbar_wait(tfull, chain & 1);
+        tc_fence_after();
+      }
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int row = mt * 128 + q * 32 + lane;  // feature index kx
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (c0 >= p.N) break;
+          uint32_t r[32];
+          if (n_chains > 0) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + mt * BN + c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = 0u;
+          }
+          if (row < p.Kx) {
+            float* drow = out + (int64_t)row * p.N + c0;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              if (c0 + v * 4 >= p.N) break;
+              const float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                           __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+              if (chain > 0) {
+                // fire-and-forget fp32 add performed at the L2 (IEEE add, single writer per address => deterministic);
+                // no load sits on the drain's critical path
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + v * 4), "f"(o.x), "f"(o.y),
+                             "f"(o.z), "f"(o.w)
+                             : "memory");
+              } else {
+                *reinterpret_cast<float4*>(drow + v * 4) = o;
+              }
+            }
+          }
+        }
+      }
+      if (n_chains > 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
 // W [rows, cols] (row-major, ld) -> hi/lo tf32 parts, optionally transposed: out is [cols, rows] when transpose
 __global__ void split_tf32_kernel(const float* __restrict__ w, int rows, int cols, int64_t ld, int transpose,
                                   float* __restrict__ hi, float* __restrict__ lo) {
@@ -317,8 +537,9 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows, cols] row-major with leading dimension ld, box = {TC_BK cols, box_rows rows}, 128B swizzle
-static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D fp32 tensor [rows, cols] row-major with leading dimension ld, box = {32 cols, box_rows rows}, 128B swizzle
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -329,7 +550,7 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t col
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
@@ -355,11 +576,61 @@ static int tc_launch(int device, const CUtensorMap& ma, const CUtensorMap& mh, c
   return KGB_OK;
 }
 
+
+template <int BN, int MT>
+static int dw_launch(int device, const CUtensorMap& mx, const CUtensorMap& mg, const DwParams& p, int grid,
+                     cudaStream_t st) {
+  using Cfg = DwCfg<BN, MT>;
+  static bool attr_done[64] = {};
+  if (device < 64 && !attr_done[device]) {
+    KGB_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done[device] = true;
+  }
+  tc_dw_kernel<BN, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mg, p);
+  KGB_CHECK_LAUNCH();
+  return KGB_OK;
+}
+
 }  // namespace kgb
 
 using namespace kgb;
 
 extern "C" {
+
+int32_t kgb_linear_tc_dw_parts(int device, int64_t M) {
+  if (kgb::use_device(device) != KGB_OK) return -1;
+  int64_t g = sm_count(device);
+  const int64_t blocks = (M + DW_R - 1) / DW_R;
+  if (g > blocks) g = blocks;
+  return (int32_t)(g < 1 ? 1 : g);
+}
+
+int kgb_linear_tc_dw(int device, const float* X, int64_t ldx, const float* G, int64_t ldg, int32_t M, int32_t Kx,
+                     int32_t N, float* partials, int32_t n_parts, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(M >= DW_R && Kx > 0 && N > 0, "kgb_linear_tc_dw needs M >= %d", DW_R);
+  KGB_REQUIRE(X && G && partials, "NULL operand");
+  KGB_REQUIRE(Kx <= 256 && N <= 256 && Kx % 4 == 0 && N % 4 == 0, "needs Kx, N <= 256 and multiples of 4");
+  KGB_REQUIRE(aligned16(X) && aligned16(G) && aligned16(partials) && ldx % 4 == 0 && ldg % 4 == 0, "alignment");
+  KGB_REQUIRE(n_parts == kgb_linear_tc_dw_parts(device, M), "n_parts must come from kgb_linear_tc_dw_parts");
+  CUtensorMap mx, mg;
+  int rc = make_map(&mx, X, M, Kx, ldx, DW_R, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != KGB_OK) return rc;
+  rc = make_map(&mg, G, M, N, ldg, DW_R, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != KGB_OK) return rc;
+  DwParams p;
+  p.M = M; p.Kx = Kx; p.N = N; p.partial = partials;
+  const int64_t blocks = (M + DW_R - 1) / DW_R;
+  p.nodes_per_cta = (int)(((blocks + n_parts - 1) / n_parts) * DW_R);
+  p.chain_blocks = 256 / DW_R;  // promote the TMEM sum to fp32 memory every 256 nodes
+  cudaStream_t st = (cudaStream_t)stream;
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int MT = Kx <= 128 ? 1 : 2;
+#define KGB_DW_CASE(BN_, MT_) if (BN == BN_ && MT == MT_) return dw_launch<BN_, MT_>(device, mx, mg, p, n_parts, st);
+  KGB_DW_CASE(64, 1) KGB_DW_CASE(64, 2) KGB_DW_CASE(128, 1) KGB_DW_CASE(128, 2) KGB_DW_CASE(256, 1) KGB_DW_CASE(256, 2)
+#undef KGB_DW_CASE
+  return KGB_ERR_UNSUPPORTED;
+}
 
 int32_t kgb_linear_tc_rows(int32_t N) { return N <= 64 ? 64 : (N <= 128 ? 128 : 256); }
 

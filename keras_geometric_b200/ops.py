@@ -429,8 +429,8 @@ def linear_tc(a: torch.Tensor, w_hi: torch.Tensor, w_lo: torch.Tensor, n_out: in
 
 class _Linear(torch.autograd.Function):
     """out = x @ w (+ addend) on the tensor cores (K8).  Forward and dX run the hand-written tcgen05 3xTF32 kernel
-    (csrc/tc_gemm.cu); dW = X^T G (reduction over the node dimension) runs the batched bf16x9 kernel
-    (csrc/dense_gemm_tn.cu).  torch.matmul (cuBLAS, on the GPU) is used only for shapes the TMA alignment rules
+    (csrc/tc_gemm.cu), and so does dW = X^T G (MN-major operands, reduction over the node dimension) for widths up
+    to 256; wider shapes use the bf16x9 kernels instantiated from CuTe/CUTLASS templates (csrc/dense_gemm_*.cu).  torch.matmul (cuBLAS, on the GPU) is used only for shapes the TMA alignment rules
     exclude (a dimension not divisible by 4)."""
 
     @staticmethod
@@ -482,9 +482,22 @@ class _Linear(torch.autograd.Function):
             else:
                 gx = torch.matmul(g, w.t())
         if ctx.needs_input_grad[1]:
-            if fast:
-                # dW[K,N] = X^T G: the reduction runs over the M nodes; cut it into slices that become the batch
-                # mode of one launch, then add the partials in slice order (deterministic, no atomics)
+            if fast and M >= 16 and K <= 256 and N <= 256:
+                # dW[K,N] = X^T G on the hand-written tcgen05 kernel: one node slice per CTA -> per-CTA partials
+                # (promoted to fp32 every 256 nodes), added in CTA order (deterministic, no float atomics across CTAs)
+                lib = _lib.load()
+                n_parts = lib.kgb_linear_tc_dw_parts(x.device.index, M)
+                parts = torch.empty((n_parts, K, N), dtype=torch.float32, device=x.device)
+                _lib.check(lib.kgb_linear_tc_dw(x.device.index, x.data_ptr(), x.stride(0), g.data_ptr(), g.stride(0), M,
+                                                K, N, parts.data_ptr(), n_parts, _stream(x.device)), "kgb_linear_tc_dw")
+                if n_parts == 1:
+                    gw = parts[0]
+                else:
+                    gw = torch.empty((K, N), dtype=torch.float32, device=x.device)
+                    _lib.check(lib.kgb_reduce_parts(x.device.index, parts.data_ptr(), n_parts, K * N, gw.data_ptr(),
+                                                    _stream(x.device)), "kgb_reduce_parts")
+            elif fast:
+                # wider than the hand-written kernel: batched bf16x9 kernel over node slices, partials added in order
                 S = _SPLIT_ROWS
                 L, rem = divmod(M, S)
                 parts = torch.empty((L + (1 if rem else 0), K, N), dtype=torch.float32, device=x.device)
