@@ -25,7 +25,7 @@ def edge_balanced_bounds(dst: torch.Tensor, n_global: int, world: int) -> list:
 
 
 def run(args, world, rank, local_rank):
-    from bench import C4, RMAT, ClockSampler, build_model, rmat_edge_index
+    from bench import C4, RMAT, ClockSampler, build_model, cross_entropy, rmat_edge_index
     from keras_geometric_b200 import _lib, ops
     from keras_geometric_b200.dist import PartitionedGraph
 
@@ -62,7 +62,7 @@ def run(args, world, rank, local_rank):
         h = x
         for lyr in layers:
             h = lyr([h, pg])
-        loss = torch.nn.functional.cross_entropy(h, y, reduction="sum") / n_global
+        loss = cross_entropy(h, y) * (pg.n_local / n_global)
         loss.backward()
         flat = torch.cat([p.grad.reshape(-1) for p in params])
         dist.all_reduce(flat)                      # data-parallel weight gradients

@@ -91,6 +91,9 @@ int kgb_csr_hubs(int device, const int64_t* rowptr, int64_t n_seg, int32_t thres
  * ------------------------------------------------------------------------------------- */
 int kgb_gcn_norm(int device, const int32_t* deg, int64_t n_nodes, const int32_t* edge_index,
                  int64_t E, int64_t n_loops, float* dis, float* w, kgb_stream_t stream);
+/* out[r,f] = y[r,f] > 0 ? g[r,f] : 0 - backward of the ReLU fused into the gather / GEMM epilogues; out is dense [rows,F] */
+int kgb_relu_bwd(int device, const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t F,
+                 float* out, kgb_stream_t stream);
 /* out[k] = in[perm[k]]  (bring COO-ordered edge weights into CSR / CSC slot order) */
 int kgb_permute_f32(int device, const float* in, const int32_t* perm, int64_t n, float* out,
                     kgb_stream_t stream);

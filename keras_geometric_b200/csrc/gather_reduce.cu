@@ -684,6 +684,25 @@ gather_rows_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __
   }
 }
 
+// gm = g where y > 0 else 0 (backward of a fused ReLU epilogue), one pass, 128-bit accesses when aligned
+__global__ void relu_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
+                                int64_t rows, int F, float* __restrict__ out) {
+  const int64_t total = rows * (int64_t)F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F;
+    const int f = (int)(i - r * F);
+    out[i] = y[r * ldy + f] > 0.f ? g[r * ldg + f] : 0.f;
+  }
+}
+
+__global__ void relu_bwd_vec4_kernel(const float4* __restrict__ g, const float4* __restrict__ y, int64_t n4,
+                                     float4* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = g[i], b = y[i];
+    out[i] = make_float4(b.x > 0.f ? a.x : 0.f, b.y > 0.f ? a.y : 0.f, b.z > 0.f ? a.z : 0.f, b.w > 0.f ? a.w : 0.f);
+  }
+}
+
 __global__ void permute_f32_kernel(const float* __restrict__ in, const int32_t* __restrict__ perm,
                                    int64_t n, float* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -932,6 +951,30 @@ int kgb_gather_rows(int device, const float* src, int64_t lds, const int32_t* id
                                                                                scale, out + f0, ldo)));
     KGB_CHECK_LAUNCH();
   }
+  return KGB_OK;
+}
+
+int kgb_relu_bwd(int device, const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t F,
+                 float* out, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(rows >= 0 && F > 0, "bad sizes");
+  if (rows == 0) return KGB_OK;
+  KGB_REQUIRE(g && y && out, "NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = rows * (int64_t)F;
+  const int64_t cap = (int64_t)sm_count(device) * 16;
+  if (ldg == F && ldy == F && total % 4 == 0 && aligned16(g) && aligned16(y) && aligned16(out)) {
+    int64_t grid = ceil_div(total / 4, 256);
+    if (grid > cap) grid = cap;
+    relu_bwd_vec4_kernel<<<(int)grid, 256, 0, st>>>(reinterpret_cast<const float4*>(g),
+                                                     reinterpret_cast<const float4*>(y), total / 4,
+                                                     reinterpret_cast<float4*>(out));
+  } else {
+    int64_t grid = ceil_div(total, 256);
+    if (grid > cap) grid = cap;
+    relu_bwd_kernel<<<(int)grid, 256, 0, st>>>(g, ldg, y, ldy, rows, F, out);
+  }
+  KGB_CHECK_LAUNCH();
   return KGB_OK;
 }
 

@@ -119,6 +119,17 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor | None, scale: float = 1.0,
     return out
 
 
+def relu_bwd(g: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """g * (y > 0) in one pass (kgb_relu_bwd); g and y are [rows, F] with unit column stride."""
+    lib = _lib.load()
+    rows, F = int(g.shape[0]), int(g.shape[1])
+    out = torch.empty((rows, F), dtype=torch.float32, device=g.device)
+    if rows and F:
+        _lib.check(lib.kgb_relu_bwd(g.device.index, g.data_ptr(), g.stride(0), y.data_ptr(), y.stride(0), rows, F,
+                                    out.data_ptr(), _stream(g.device)), "kgb_relu_bwd")
+    return out
+
+
 def permute_f32(w: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(perm.shape[0], dtype=torch.float32, device=w.device)
@@ -184,7 +195,7 @@ class _GatherReduce(torch.autograd.Function):
         is_max = op in _lib.MAX_OPS
         out = saved[-1] if (is_max or ctx.act == "relu") else None
         if ctx.act == "relu":
-            g = g * (out > 0)
+            g = relu_bwd(g, out)
         g_addend = (g * ctx.addend_scale if ctx.addend_scale != 1.0 else g) if ctx.has_addend else None
         g_bias = g.sum(dim=0) if ctx.has_bias else None
         gx = None
@@ -467,7 +478,7 @@ class _Linear(torch.autograd.Function):
         x, w = ctx.saved_tensors[:2]
         g = _f32c(g, "grad")
         if ctx.relu:
-            g = g * (ctx.saved_tensors[2] > 0)
+            g = relu_bwd(g, ctx.saved_tensors[2])
         if g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
             g = g.contiguous()
         gx = gw = None

@@ -1,0 +1,34 @@
+"""Kernel-time breakdown of the C4 bench step via torch.profiler (CUPTI), top kernels by device time."""
+import sys, os, collections, re
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import profile, ProfilerActivity
+import bench
+dev = torch.device("cuda", 0)
+cfg = bench.C4
+ei = bench.rmat_edge_index(cfg["nodes"], cfg["edges"], cfg["rmat_scale"], 0, dev)
+gen = torch.Generator(device=dev).manual_seed(1)
+x = torch.randn((cfg["nodes"], cfg["feats"]), device=dev, generator=gen)
+y = torch.randint(0, cfg["classes"], (cfg["nodes"],), device=dev, generator=gen)
+layers = bench.build_model(cfg["feats"], cfg["hidden"], cfg["classes"])
+params = [p for l in layers for p in l.trainable_weights]
+opt = torch.optim.SGD(params, lr=1e-3)
+def step():
+    opt.zero_grad(set_to_none=True)
+    h = x
+    for l in layers: h = l([h, ei])
+    loss = torch.nn.functional.cross_entropy(h, y); loss.backward(); opt.step()
+for _ in range(3): step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(2): step()
+    torch.cuda.synchronize()
+tot = collections.defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        name = re.sub(r"<.*", "", e.name)[:60]
+        tot[name][0] += 1; tot[name][1] += e.device_time
+s = sum(v[1] for v in tot.values())
+print(f"total device time per step {s/2/1e3:.2f} ms")
+for k, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:22]:
+    print(f"{t/2/1e3:8.2f} ms/step  n={n//2:3d}  {k}")
