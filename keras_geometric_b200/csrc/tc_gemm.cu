@@ -101,7 +101,9 @@ struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
   static constexpr int B_BYTES = BN * TC_BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_LD = 36;                                   // padded row (floats) of the store staging tile
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;               // one 32x32 tile per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
@@ -112,7 +114,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
+  float* epi_stage = reinterpret_cast<float*>(smem + S * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full = bars;            // [S]  TMA bytes landed
   uint64_t* lo_rdy = bars + S;      // [S]  A_lo written
   uint64_t* empty = bars + 2 * S;   // [S]  MMAs that read the stage retired
@@ -233,7 +236,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int b = j & 1;
       mbar_wait(tfull + b, (j >> 1) & 1);
       tc_fence_after();
-      const int64_t row = (int64_t)tile * TC_BM + q * 32 + lane;
+      const int64_t tile_row0 = (int64_t)tile * TC_BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -249,29 +252,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr + c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < p.M) {
-          float* drow = p.D + row * p.ldd + c0;
-          const float* crow = p.C ? p.C + row * p.ldc + c0 : nullptr;
+        // Each thread holds 32 consecutive columns of ITS row; storing that directly would touch 32 different rows
+        // per instruction.  Transpose through a padded shared tile so every global access covers whole 128-byte
+        // row segments (4 rows x 128 B per warp instruction).
+        float* stg = epi_stage + q * 32 * Cfg::EPI_LD;
 #pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            if (c0 + v * 4 >= p.N) break;  // N is a multiple of 4
-            float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                   __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
-            if (crow) {
-              const float4 c = *reinterpret_cast<const float4*>(crow + v * 4);
+        for (int v = 0; v < 8; ++v)
+          *reinterpret_cast<float4*>(stg + lane * Cfg::EPI_LD + v * 4) =
+              make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                          __uint_as_float(r[4 * v + 3]));
+        __syncwarp();
+        const int cv = (lane & 7) * 4;        // column (within the chunk) of this lane's float4
+        const bool col_ok = (c0 + cv) < p.N;  // N is a multiple of 4
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok) bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + cv));
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          const int64_t grow = (int64_t)tile_row0 + rr;
+          float4 o = *reinterpret_cast<const float4*>(stg + rr * Cfg::EPI_LD + cv);
+          if (grow < p.M && col_ok) {
+            if (p.C) {
+              const float4 c = *reinterpret_cast<const float4*>(p.C + grow * p.ldc + c0 + cv);
               o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
             }
-            if (p.bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + v * 4));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
             if (p.relu) {
               o.x = o.x <= 0.f ? 0.f : o.x; o.y = o.y <= 0.f ? 0.f : o.y;
               o.z = o.z <= 0.f ? 0.f : o.z; o.w = o.w <= 0.f ? 0.f : o.w;
             }
-            *reinterpret_cast<float4*>(drow + v * 4) = o;
+            *reinterpret_cast<float4*>(p.D + grow * p.ldd + c0 + cv) = o;
           }
         }
+        __syncwarp();  // the tile is reused by the next column chunk
       }
       tc_fence_before();
       __syncwarp();
