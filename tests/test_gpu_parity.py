@@ -535,3 +535,81 @@ def test_golden_batch_graphs():
     np.testing.assert_array_equal(b.edge_attr.cpu().numpy(), g["bea"])
     assert b.num_nodes == int(g["bnum_nodes"]) and b.num_edges == g["bei"].shape[1]
     assert b.to_inputs()[1].dtype == torch.int32
+
+
+# ------------------------------------------------------------------------- edge cases through the layers
+def test_layer_edge_cases_match_reference_conventions():
+    """N == 0, E == 0, [E,2] layout, float64 / int64 inputs, isolated nodes."""
+    import keras_geometric_b200 as kg
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((6, 4)).astype(np.float32)
+    e0 = np.zeros((2, 0), np.int32)
+    # N == 0
+    for layer in (kg.GCNConv(3), kg.GINConv(3), kg.GATv2Conv(3, heads=2)):
+        out = layer([np.zeros((0, 4), np.float32), e0])
+        assert tuple(out.shape) == (0, 3 if not isinstance(layer, kg.GATv2Conv) else 6)
+    # E == 0: GCN without self-loops = xW + b; with self-loops every node sees itself
+    g = kg.GCNConv(3, add_self_loops=False)
+    out = g([x, e0])
+    close(out, x @ g.kernel.detach().cpu().numpy() + g.bias.detach().cpu().numpy(), msg="gcn no edges")
+    g2 = kg.GCNConv(3)
+    close(g2([x, e0]), x @ g2.kernel.detach().cpu().numpy() + g2.bias.detach().cpu().numpy(), msg="gcn loops only")
+    # SAGE with no edges: aggregated = 0 -> act(lin_self(x) + b)
+    s = kg.SAGEConv(3, activation=None)
+    close(s([x, e0]), x @ s.lin_self.kernel.detach().cpu().numpy() + s.bias.detach().cpu().numpy(), msg="sage no edges")
+    # GIN with no edges: mlp((1 + eps) x)
+    gin = kg.GINConv(3, mlp_hidden=[5], eps_init=0.5)
+    out_gin = gin([x, e0])  # builds the MLP
+    want = ref.gin_conv(torch.from_numpy(x), torch.from_numpy(e0.astype(np.int64)), lambda h: torch.relu(
+        h @ gin.mlp.layers[0].kernel.detach().cpu() + gin.mlp.layers[0].bias.detach().cpu()) @ gin.mlp.layers[1].kernel.detach().cpu()
+        + gin.mlp.layers[1].bias.detach().cpu(), 0.5)
+    close(out_gin, want, msg="gin no edges")
+    # GATv2 without self-loops and without edges: zeros, no bias (gatv2_conv.py:204-210)
+    gat = kg.GATv2Conv(3, heads=2, add_self_loops=False)
+    assert float(gat([x, e0]).abs().max()) == 0.0
+    # dtype / layout tolerance: float64 features, int64 edges, [E,2] layout (GCN, SAGE)
+    ei = np.array([[0, 1], [1, 2], [2, 0], [5, 0]], np.int64)  # [E,2]
+    a = g2([x.astype(np.float64), ei])
+    b = g2([x, np.ascontiguousarray(ei.T).astype(np.int32)])
+    assert a.dtype == torch.float32 and torch.equal(a, b)
+    with pytest.raises(ValueError, match="edge_index must have shape"):
+        g2([x, np.zeros((3, 5), np.int32)])
+    # NaN / inf propagate (tests/unit/test_error_handling.py:233-258)
+    xn = x.copy(); xn[2, 1] = np.nan
+    assert torch.isnan(g2([xn, np.ascontiguousarray(ei.T).astype(np.int32)])).any()
+
+
+def test_property_random_graphs_vs_oracle():
+    """Randomised structural cases (duplicates, self-loops, isolated nodes, hubs) - CSR bit-exact, aggregations in tolerance."""
+    from keras_geometric_b200 import ops
+    from keras_geometric_b200.graph import GraphStructure
+    rng = np.random.default_rng(123)
+    for trial in range(12):
+        n = int(rng.integers(1, 400))
+        e = int(rng.integers(0, 3000))
+        F = int(rng.choice([1, 2, 5, 8, 20, 33, 64, 130]))
+        skew = rng.random() < 0.5
+        dst = (rng.pareto(1.0, e) * 2).astype(np.int64) % n if skew else rng.integers(0, n, e)
+        src = rng.integers(0, n, e)
+        if e > 10:
+            src[:5] = dst[:5]            # self-loops
+            src[5:10], dst[5:10] = src[0], dst[0]  # duplicates
+        ei = np.stack([src, dst]).astype(np.int32)
+        loops = n if rng.random() < 0.3 else 0
+        g = GraphStructure(cuda(ei), n, n, loops)
+        full = ei if not loops else np.concatenate([ei, np.stack([np.arange(n), np.arange(n)]).astype(np.int32)], 1)
+        rowptr, col, perm, deg = ref.stable_csr(full, n)
+        np.testing.assert_array_equal(g.csr.perm.cpu().numpy(), perm)
+        np.testing.assert_array_equal(g.csr.rowptr.cpu().numpy(), rowptr)
+        x = np.round(rng.standard_normal((n, F)), 1).astype(np.float32)
+        if full.shape[1] == 0:
+            continue
+        for op in ("sum", "mean", "max", "min"):
+            xg = cuda(x).requires_grad_(True)
+            out = ops.gather_reduce(xg, g, op)
+            xo = torch.from_numpy(x).requires_grad_(True)
+            want = ref.propagate(xo, torch.from_numpy(full), op)
+            close(out, want, msg=f"trial {trial} {op} n={n} e={e} F={F}")
+            (gx,) = torch.autograd.grad(out.sum(), [xg])
+            (gw,) = torch.autograd.grad(want.sum(), [xo])
+            close(gx, gw, msg=f"trial {trial} grad {op}")
