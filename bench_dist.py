@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 
 
-NODE_WEIGHT = 44  # cost of one node (dense transforms) in units of one edge (gather), measured on C4
+NODE_WEIGHT = 28  # cost of one node (dense transforms) in units of one edge (gather), measured on C4
 
 
 def edge_balanced_bounds(dst: torch.Tensor, n_global: int, world: int) -> list:

@@ -97,3 +97,55 @@ def batch_graphs(graphs: list) -> GraphData:
         batch_y = torch.stack(ys, dim=0) if ys[0].dim() == 1 else torch.cat(ys, dim=0)
     return GraphData(x=batch_x, edge_index=batch_ei, edge_attr=batch_ea, y=batch_y, num_nodes=total_nodes,
                      batch=batch)
+
+
+# ---- processed-dataset files (SURVEY 8(f) "next-4") -------------------------------------------------------------
+def save_processed_npz(path: str, graphs: list, num_classes: int | None = None) -> None:
+    """Write graphs in the reference's processed format (datasets/base.py:124-156): arrays ``x_i``,
+    ``edge_index_i``, optional ``edge_attr_i`` / ``y_i`` per graph plus ``num_graphs`` / ``num_classes``."""
+    def host(t):
+        return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+    data = {}
+    for i, g in enumerate(graphs):
+        data[f"x_{i}"] = host(g.x)
+        data[f"edge_index_{i}"] = host(g.edge_index)
+        if g.edge_attr is not None:
+            data[f"edge_attr_{i}"] = host(g.edge_attr)
+        if g.y is not None:
+            data[f"y_{i}"] = host(g.y)
+    data["num_graphs"] = len(graphs)
+    if num_classes is not None:
+        data["num_classes"] = num_classes
+    np.savez(path, **data)
+
+
+def read_processed_npz(path: str):
+    """Host-side parse of a processed ``<name>.npz`` (datasets/base.py:158-182) into plain numpy dicts; no device
+    is touched, so the format logic is testable without a GPU.  Returns ``(graphs, num_classes)``."""
+    data = np.load(path, allow_pickle=False)
+    num_graphs = int(data["num_graphs"])
+    num_classes = int(data["num_classes"]) if "num_classes" in data else None
+    graphs = []
+    for i in range(num_graphs):
+        graphs.append({"x": data[f"x_{i}"], "edge_index": data[f"edge_index_{i}"],
+                       "edge_attr": data[f"edge_attr_{i}"] if f"edge_attr_{i}" in data else None,
+                       "y": data[f"y_{i}"] if f"y_{i}" in data else None})
+    return graphs, num_classes
+
+
+def load_processed_npz(path: str, build_structure: bool = True):
+    """``processed/<name>.npz`` -> device ``GraphData`` list (+ num_classes).  With ``build_structure`` the CSR/CSC
+    of every graph is built right away (kgb_csr_build) and cached on its ``edge_index`` tensor, so the first layer
+    call does not pay for it and the COO never has to be re-sorted on the host."""
+    from .graph import get_graph
+
+    host_graphs, num_classes = read_processed_npz(path)
+    out = []
+    for g in host_graphs:
+        gd = GraphData(x=g["x"].astype(np.float32, copy=False), edge_index=g["edge_index"], edge_attr=g["edge_attr"],
+                       y=g["y"])
+        if build_structure and gd.num_edges > 0:
+            get_graph(gd.edge_index, gd.num_nodes, gd.num_nodes, 0)
+        out.append(gd)
+    return out, num_classes

@@ -613,3 +613,20 @@ def test_property_random_graphs_vs_oracle():
             (gx,) = torch.autograd.grad(out.sum(), [xg])
             (gw,) = torch.autograd.grad(want.sum(), [xo])
             close(gx, gw, msg=f"trial {trial} grad {op}")
+
+
+def test_processed_npz_to_device(tmp_path):
+    import keras_geometric_b200 as kg
+    from keras_geometric_b200.data_utils import load_processed_npz, save_processed_npz
+    rng = np.random.default_rng(1)
+    gs = [kg.GraphData(x=rng.standard_normal((n, 3)).astype(np.float32),
+                       edge_index=rng.integers(0, n, (2, e)).astype(np.int32), y=rng.integers(0, 2, n))
+          for n, e in [(7, 12), (4, 5)]]
+    path = str(tmp_path / "ds.npz")
+    save_processed_npz(path, gs, num_classes=2)
+    back, nc = load_processed_npz(path)
+    assert nc == 2 and len(back) == 2
+    for a, b in zip(gs, back):
+        assert torch.equal(a.x, b.x) and torch.equal(a.edge_index, b.edge_index) and b.x.is_cuda
+    out = kg.GCNConv(2)([back[0].x, back[0].edge_index])
+    assert tuple(out.shape) == (7, 2)

@@ -195,3 +195,27 @@ def test_message_passing_base_output_shape():
     lyr = kg.MessagePassing()
     assert lyr.compute_output_shape([(None, 5, 32), (None, 2, None)]) == (None, 5, 32)
     assert lyr.compute_output_shape(((None, 5, 32), (None, 2, None))) == (None, 5, 32)
+
+
+def test_processed_npz_format_round_trip(tmp_path):
+    """The reference's processed-dataset layout (datasets/base.py:124-182): x_i / edge_index_i / y_i / num_graphs /
+    num_classes.  Host-side parse only (no device)."""
+    from keras_geometric_b200.data_utils import read_processed_npz
+
+    rng = np.random.default_rng(0)
+    ref_file = {}
+    for i, (n, e) in enumerate([(5, 8), (3, 0)]):
+        ref_file[f"x_{i}"] = rng.standard_normal((n, 4)).astype(np.float32)
+        ref_file[f"edge_index_{i}"] = rng.integers(0, n, (2, e)).astype(np.int32)
+        ref_file[f"y_{i}"] = rng.integers(0, 3, n).astype(np.int64)
+    ref_file["edge_attr_0"] = rng.standard_normal((8, 2)).astype(np.float32)
+    ref_file["num_graphs"] = 2
+    ref_file["num_classes"] = 3
+    path = str(tmp_path / "toy.npz")
+    np.savez(path, **ref_file)  # written exactly like Dataset._save_processed does
+    graphs, num_classes = read_processed_npz(path)
+    assert num_classes == 3 and len(graphs) == 2
+    np.testing.assert_array_equal(graphs[0]["x"], ref_file["x_0"])
+    np.testing.assert_array_equal(graphs[1]["edge_index"], ref_file["edge_index_1"])
+    assert graphs[1]["edge_attr"] is None and graphs[0]["edge_attr"].shape == (8, 2)
+    np.testing.assert_array_equal(graphs[0]["y"], ref_file["y_0"])
