@@ -151,7 +151,14 @@ typedef struct kgb_gather_reduce_args {
   int32_t* work;           /* optional int32[2], ZERO on entry and left zero on exit: dynamic task
                               queue (load balance on skewed graphs).  One buffer must not be shared
                               by launches that can overlap in time.  NULL = static striding.     */
+  const int32_t* unit_order; /* optional (used with `work`): a PERMUTATION of the
+                              ceil(n_rows / kgb_gather_unit_rows()) row units, in the order the queue
+                              hands them out.  Heaviest-first (by edge count, hub rows excluded) removes
+                              the tail on power-law graphs; the result does not depend on it.   */
 } kgb_gather_reduce_args;
+
+/* rows per task-queue unit of kgb_gather_reduce (unit u covers rows [u*R, (u+1)*R)) */
+int32_t kgb_gather_unit_rows(void);
 
 size_t kgb_gather_reduce_partial_bytes(int32_t n_chunks, int32_t F, int32_t op);
 int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t stream);
@@ -200,7 +207,10 @@ typedef struct kgb_hub_table {
   int32_t chunk;
   float* partial;   /* kgb_gatv2_partial_bytes(n_chunks, H, C) bytes                              */
   int32_t* work;    /* optional int32[64], zero on entry / left zero: dynamic task queue scratch */
+  const int32_t* unit_order; /* optional (GATv2 kernels, with `work`): permutation of the
+                       ceil(n_rows / kgb_gatv2_unit_rows()) row units, heaviest first               */
 } kgb_hub_table;
+int32_t kgb_gatv2_unit_rows(void);
 size_t kgb_gatv2_partial_bytes(int32_t n_chunks, int32_t H, int32_t C);
 
 int kgb_gatv2_fwd(int device, const float* hsrc, const float* hdst, int64_t n_src, int64_t n_dst,

@@ -35,7 +35,7 @@ class GatherReduceArgs(Structure):
         ("hub_row", c_void_p), ("hub_chunk_base", c_void_p), ("hub_nchunks", c_void_p),
         ("chunk_hub", c_void_p), ("n_hubs", c_int32), ("n_chunks", c_int32),
         ("hub_threshold", c_int32), ("hub_chunk", c_int32), ("partial", c_void_p),
-        ("work", c_void_p),
+        ("work", c_void_p), ("unit_order", c_void_p),
     ]
 
 
@@ -44,7 +44,7 @@ class HubTable(Structure):
 
     _fields_ = [("hub_row", c_void_p), ("hub_chunk_base", c_void_p), ("hub_nchunks", c_void_p),
                 ("chunk_hub", c_void_p), ("n_hubs", c_int32), ("n_chunks", c_int32), ("threshold", c_int32),
-                ("chunk", c_int32), ("partial", c_void_p), ("work", c_void_p)]
+                ("chunk", c_int32), ("partial", c_void_p), ("work", c_void_p), ("unit_order", c_void_p)]
 
 
 # name -> (restype, argtypes); every name declared in include/kgb200.h must appear here
@@ -66,6 +66,8 @@ SIGNATURES = {
     "kgb_gather_max_bwd": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                    c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64,
                                    POINTER(HubTable), c_void_p]),
+    "kgb_gather_unit_rows": (c_int32, []),
+    "kgb_gatv2_unit_rows": (c_int32, []),
     "kgb_gather_max_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "kgb_gather_rows": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_float, c_void_p, c_int64,
                                 c_void_p]),

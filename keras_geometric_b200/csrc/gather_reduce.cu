@@ -38,6 +38,7 @@ struct GRP {
   int n_hubs; int n_chunks; int hub_threshold; int hub_chunk;
   float* partial; int32_t* partial_arg;
   int32_t* work;  // [2] zero on entry: dynamic task queue head + finished-CTA count (self-resetting)
+  const int32_t* unit_order;  // optional permutation of the row units (heaviest first)
 };
 
 template <int VEC, int G, int NCH, bool IS_MAX>
@@ -305,7 +306,10 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
 
 
 // Rows handed out per queue fetch (one atomic per warp per UNIT_ROWS rows).
-constexpr int UNIT_ROWS = 128;
+#ifndef KGB_GR_UNIT_ROWS
+#define KGB_GR_UNIT_ROWS 32
+#endif
+constexpr int UNIT_ROWS = KGB_GR_UNIT_ROWS;
 
 template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
 __device__ __forceinline__ void do_chunk(const GRP& p, int64_t t, int gl, unsigned gmask, const bool (&on)[NCH]) {
@@ -403,7 +407,9 @@ gather_reduce_kernel(const GRP p) {
       const int64_t t = u * GPW + gw;
       if (t < p.n_chunks) do_chunk<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, t, gl, gmask, on);
     } else {
-      const int64_t base = (u - chunk_units) * UNIT_ROWS;
+      int64_t ui = u - chunk_units;
+      if (p.unit_order) ui = __ldg(p.unit_order + ui);
+      const int64_t base = ui * UNIT_ROWS;
       for (int b = gw; b < BPU; b += GPW) {
         const int64_t r0 = base + (int64_t)b * G;
         if (r0 < p.n_rows) do_row_block<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, r0, gl, gw, gmask, on);
@@ -812,6 +818,8 @@ using namespace kgb;
 
 extern "C" {
 
+int32_t kgb_gather_unit_rows(void) { return kgb::UNIT_ROWS; }
+
 size_t kgb_gather_reduce_partial_bytes(int32_t n_chunks, int32_t F, int32_t op) {
   if (n_chunks <= 0) return 0;
   size_t b = align_up((size_t)n_chunks * (size_t)F * sizeof(float), 256);
@@ -860,6 +868,7 @@ int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t 
     p.hub_threshold = a->hub_threshold; p.hub_chunk = a->hub_chunk;
     p.partial = a->partial;
     p.work = a->work;
+    p.unit_order = a->work ? a->unit_order : nullptr;
     p.partial_arg = nullptr;
     if (hubs && is_max)
       p.partial_arg = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(a->partial) +

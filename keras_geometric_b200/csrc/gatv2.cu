@@ -40,6 +40,7 @@ struct GatP {
   int n_hubs; int n_chunks; int hub_threshold; int hub_chunk;
   float* partial;  // fwd: acc [n_chunks,HC] | m [n_chunks,H] | l [n_chunks,H];  bwd: sums [n_chunks,HC]
   int32_t* work;   // [2 * gridDim.y] zero on entry (queue head, finished CTAs) or NULL
+  const int32_t* unit_order;  // optional permutation of the row units (heaviest first)
   int64_t n_rows;  // rows of the walked structure
 };
 
@@ -50,7 +51,10 @@ __device__ __forceinline__ float head_sum(float v, unsigned gmask) {
   return v;
 }
 
-constexpr int GAT_UNIT_ROWS = 64;
+#ifndef KGB_GAT_UNIT_ROWS
+#define KGB_GAT_UNIT_ROWS 16
+#endif
+constexpr int GAT_UNIT_ROWS = KGB_GAT_UNIT_ROWS;  // rows per queue fetch (one atomic per warp)
 
 // Hands (chunk | row) tasks to the lane groups of the CTA; see the header comment.
 template <int G, class FC, class FR>
@@ -84,7 +88,9 @@ __device__ __forceinline__ void gat_schedule(const GatP& p, FC&& on_chunk, FR&& 
         on_chunk(t, row, k0, k1, ci == 0);
       }
     } else {
-      const int64_t base = (u - chunk_units) * GAT_UNIT_ROWS;
+      int64_t ui = u - chunk_units;
+      if (p.unit_order) ui = __ldg(p.unit_order + ui);
+      const int64_t base = ui * GAT_UNIT_ROWS;
       const int64_t lim = (base + GAT_UNIT_ROWS < p.n_rows) ? base + GAT_UNIT_ROWS : p.n_rows;
       for (int64_t row = base + gw; row < lim; row += GPW) {
         const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
@@ -145,7 +151,11 @@ template <int VEC, int LPH, int CC, int HPG>
 __device__ __forceinline__ void gat_fwd_range(const GatP& p, const LaneCtx<VEC, LPH, CC, HPG>& L, int64_t row,
                                               int64_t k0, int64_t k1, float& m, float& l, float (&acc)[CC][VEC]) {
   constexpr int G = LPH * HPG;
-  constexpr int U = (G < 4) ? G : 4;
+#ifndef KGB_GAT_U
+#define KGB_GAT_U 8
+#endif
+  constexpr int UMAX = (KGB_GAT_U / CC) < 1 ? 1 : (KGB_GAT_U / CC);
+  constexpr int U = (G < UMAX) ? G : UMAX;
   const int HC = p.H * p.C;
   float hi[CC][VEC];
 #pragma unroll
@@ -638,6 +648,7 @@ static void gat_set_hubs(GatP& p, const kgb_hub_table* hubs) {
     p.hub_threshold = hubs->threshold; p.hub_chunk = hubs->chunk; p.partial = hubs->partial;
   }
   p.work = hubs ? hubs->work : nullptr;
+  p.unit_order = (hubs && hubs->work) ? hubs->unit_order : nullptr;
 }
 
 static int gat_run(int device, int which, GatP& p, cudaStream_t st, int per_sm, int grid_x_cap, float* finish_out) {
@@ -646,7 +657,7 @@ static int gat_run(int device, int which, GatP& p, cudaStream_t st, int per_sm, 
     set_error("gatv2: C=%d too wide for the compiled kernels", p.C);
     return KGB_ERR_UNSUPPORTED;
   }
-  if (p.work && s.nhb > 32) p.work = nullptr;  // queue scratch holds 32 head blocks
+  if (p.work && s.nhb > 32) { p.work = nullptr; p.unit_order = nullptr; }  // queue scratch holds 32 head blocks
   int gx = gat_grid_x(device, p.n_rows, p.n_chunks, s, per_sm);
   if (grid_x_cap > 0 && gx > grid_x_cap) gx = grid_x_cap;
   dim3 grid(gx, s.nhb, 1);
@@ -677,6 +688,8 @@ static int gat_run(int device, int which, GatP& p, cudaStream_t st, int per_sm, 
 using namespace kgb;
 
 extern "C" {
+
+int32_t kgb_gatv2_unit_rows(void) { return kgb::GAT_UNIT_ROWS; }
 
 size_t kgb_gatv2_partial_bytes(int32_t n_chunks, int32_t H, int32_t C) {
   if (n_chunks <= 0) return 0;

@@ -86,6 +86,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+__device__ __forceinline__ float4 ld_stream4(const float* p) {  // read-once data: do not allocate in L1
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 struct TcParams {
   int M, N, K;
   const float* C; int64_t ldc;   // optional addend
@@ -241,6 +248,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (c0 >= p.N) break;
+        // addend rows of this chunk: issued before the TMEM read so their DRAM latency hides behind it (loading them
+        // next to the store would serialise 8 dependent round trips per chunk: D may alias C as far as the compiler knows)
+        const int cv = (lane & 7) * 4;        // column (within the chunk) of this lane's float4
+        const bool col_ok = (c0 + cv) < p.N;  // N is a multiple of 4
+        float4 cc[8];
+        if (p.C) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int64_t grow = (int64_t)tile_row0 + it * 4 + (lane >> 3);
+            cc[it] = (grow < p.M && col_ok) ? ld_stream4(p.C + grow * p.ldc + c0 + cv) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t r[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -262,8 +281,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
                           __uint_as_float(r[4 * v + 3]));
         __syncwarp();
-        const int cv = (lane & 7) * 4;        // column (within the chunk) of this lane's float4
-        const bool col_ok = (c0 + cv) < p.N;  // N is a multiple of 4
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias && col_ok) bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + cv));
 #pragma unroll
@@ -272,10 +289,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int64_t grow = (int64_t)tile_row0 + rr;
           float4 o = *reinterpret_cast<const float4*>(stg + rr * Cfg::EPI_LD + cv);
           if (grow < p.M && col_ok) {
-            if (p.C) {
-              const float4 c = *reinterpret_cast<const float4*>(p.C + grow * p.ldc + c0 + cv);
-              o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
-            }
+            if (p.C) { o.x += cc[it].x; o.y += cc[it].y; o.z += cc[it].z; o.w += cc[it].w; }
             o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
             if (p.relu) {
               o.x = o.x <= 0.f ? 0.f : o.x; o.y = o.y <= 0.f ? 0.f : o.y;

@@ -120,20 +120,40 @@ class PartitionedGraph:
         self._dis_ext = None
 
     # ---- forward/backward exchange ------------------------------------------------------------
-    def exchange(self, x_local: torch.Tensor) -> torch.Tensor:
-        """[n_local, F] -> [n_local + n_halo, F] (autograd-aware)."""
-        return _HaloExchange.apply(x_local, self, False)
+    # The exchange (pack kernel, all-to-all, and in the backward the reverse all-to-all + segmented sum) runs on a
+    # dedicated CUDA stream.  autograd replays each node's backward on the stream its forward ran on and inserts the
+    # cross-stream dependencies itself, so the halo traffic of both directions overlaps the work that does not need
+    # it (root-weight GEMM forward; weight-gradient and root GEMMs backward).
+    def _comm_stream(self) -> torch.cuda.Stream:
+        cs = getattr(self, "_cs", None)
+        if cs is None:
+            cs = self._cs = torch.cuda.Stream(device=self.graph.device)
+        return cs
 
     def exchange_start(self, x_local: torch.Tensor) -> torch.Tensor:
-        """Like ``exchange`` but the all-to-all is left in flight on NCCL's stream so that work which does not
-        need the halo rows (the root-weight GEMM) overlaps it.  Call ``exchange_finish`` before the first use of
-        the returned tensor's halo rows."""
-        return _HaloExchange.apply(x_local, self, True)
+        """[n_local, F] -> [n_local + n_halo, F] (autograd-aware), left in flight on the communication stream.
+        Call ``exchange_finish`` before the first use of the result on the current stream."""
+        self.exchange_finish()
+        cur = torch.cuda.current_stream(self.graph.device)
+        cs = self._comm_stream()
+        cs.wait_stream(cur)
+        with torch.cuda.stream(cs):
+            x_ext = _HaloExchange.apply(x_local, self)
+        x_local.record_stream(cs)
+        self._pending = x_ext
+        return x_ext
 
     def exchange_finish(self) -> None:
-        w, self._pending = getattr(self, "_pending", None), None
-        if w is not None:
-            w.wait()  # orders the current stream after the collective
+        x_ext, self._pending = getattr(self, "_pending", None), None
+        if x_ext is not None:
+            cur = torch.cuda.current_stream(self.graph.device)
+            cur.wait_stream(self._comm_stream())
+            x_ext.record_stream(cur)
+
+    def exchange(self, x_local: torch.Tensor) -> torch.Tensor:
+        x_ext = self.exchange_start(x_local)
+        self.exchange_finish()
+        return x_ext
 
     def exchange_vector(self, v_local: torch.Tensor) -> torch.Tensor:
         """Per-node scalar (e.g. GCN dis) -> [n_ext]; no autograd."""
@@ -152,28 +172,24 @@ class PartitionedGraph:
         return self._dis_ext
 
 
-def _exchange_fwd(x_local: torch.Tensor, pg: PartitionedGraph, in_flight: bool = False) -> torch.Tensor:
+def _exchange_fwd(x_local: torch.Tensor, pg: PartitionedGraph) -> torch.Tensor:
     from . import ops
     p = pg.plan
     F = int(x_local.shape[1])
     x_ext = torch.empty((pg.n_ext, F), dtype=x_local.dtype, device=x_local.device)
     if pg.world > 1:
         send = ops.gather_rows(x_local, p.send_idx) if p.n_send else x_local.new_empty((0, F))
-        work = dist.all_to_all_single(x_ext[pg.n_local:], send, output_split_sizes=p.recv_counts,
-                                      input_split_sizes=p.send_counts, group=pg.group, async_op=in_flight)
-        if in_flight:
-            pg.exchange_finish()
-            pg._pending = work
-            pg._pending_send = send  # keep the packed buffer alive until the collective has consumed it
+        dist.all_to_all_single(x_ext[pg.n_local:], send, output_split_sizes=p.recv_counts,
+                               input_split_sizes=p.send_counts, group=pg.group)
     x_ext[:pg.n_local].copy_(x_local)
     return x_ext
 
 
 class _HaloExchange(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_local, pg: PartitionedGraph, in_flight: bool = False):
+    def forward(ctx, x_local, pg: PartitionedGraph):
         ctx.pg = pg
-        return _exchange_fwd(x_local.contiguous(), pg, in_flight)
+        return _exchange_fwd(x_local.contiguous(), pg)
 
     @staticmethod
     @once_differentiable
@@ -182,6 +198,7 @@ class _HaloExchange(torch.autograd.Function):
         pg = ctx.pg
         p = pg.plan
         g_ext = g_ext.contiguous()
+        g_ext.record_stream(torch.cuda.current_stream(g_ext.device))  # produced on the compute stream
         g_local = g_ext[:pg.n_local].clone()
         if pg.world > 1:
             F = int(g_ext.shape[1])
@@ -191,4 +208,4 @@ class _HaloExchange(torch.autograd.Function):
             if p.n_send:
                 add, _ = ops.gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm)
                 g_local += add
-        return g_local, None, None
+        return g_local, None

@@ -34,7 +34,7 @@ class Csr:
     ``perm`` int32 [nnz] (original edge id of each slot, stable), ``deg`` int32 [n]."""
 
     __slots__ = ("n_rows", "n_cols", "nnz", "rowptr", "col", "perm", "deg", "hub_row", "hub_chunk_base",
-                 "hub_nchunks", "chunk_hub", "n_hubs", "n_chunks", "_inv_deg", "_partials", "_deg_f", "_work")
+                 "hub_nchunks", "chunk_hub", "n_hubs", "n_chunks", "_inv_deg", "_partials", "_deg_f", "_work", "_unit_order")
 
     def __init__(self):
         self._inv_deg = None
@@ -44,6 +44,7 @@ class Csr:
         self.n_chunks = 0
         self.hub_row = self.hub_chunk_base = self.hub_nchunks = self.chunk_hub = None
         self._work = {}
+        self._unit_order = {}
 
     def work(self, stream_id: int) -> torch.Tensor:
         """Task-queue counters of kgb_gather_reduce (zero between launches), one pair per stream."""
@@ -53,7 +54,22 @@ class Csr:
             self._work[stream_id] = w
         return w
 
-    def hub_table(self, partial_bytes: int, stream_id: int):
+    def unit_order(self, unit_rows: int | None = None):
+        """Row units of a kernel's task queue, heaviest first (longest-processing-time order): on a power-law
+        graph the natural order leaves a tail of ~25 % of the kernel in which most warps have run dry."""
+        ur = int(_lib.load().kgb_gather_unit_rows()) if unit_rows is None else int(unit_rows)
+        if self.n_rows <= 4 * ur:
+            return None
+        order = self._unit_order.get(ur)
+        if order is None:
+            d = self.rowptr[1:] - self.rowptr[:-1]
+            if self.n_hubs > 0:
+                d = torch.where(d > HUB_THRESHOLD, torch.zeros_like(d), d)   # hub rows go through the chunk tasks
+            d = torch.nn.functional.pad(d, (0, (-self.n_rows) % ur)).view(-1, ur).sum(1)
+            order = self._unit_order[ur] = torch.sort(d, descending=True, stable=True)[1].to(torch.int32)
+        return order
+
+    def hub_table(self, partial_bytes: int, stream_id: int, gat: bool = False):
         """ctypes ``kgb_hub_table`` for the GATv2 kernels (keeps the partial buffer alive on self)."""
         t = _lib.HubTable()
         if self.n_chunks > 0:
@@ -67,6 +83,9 @@ class Csr:
             t.n_hubs, t.n_chunks, t.threshold, t.chunk = self.n_hubs, self.n_chunks, HUB_THRESHOLD, HUB_CHUNK
             t.partial = buf.data_ptr()
         t.work = self.work(stream_id).data_ptr()
+        if gat:
+            order = self.unit_order(int(_lib.load().kgb_gatv2_unit_rows()))
+            t.unit_order = order.data_ptr() if order is not None else None
         return t
 
     @property

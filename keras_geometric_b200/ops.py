@@ -74,6 +74,7 @@ def gather_reduce_raw(x: torch.Tensor, csr: Csr, op: int, *, col: torch.Tensor |
         a.hub_threshold, a.hub_chunk = HUB_THRESHOLD, HUB_CHUNK
         a.partial = partial.data_ptr()
     a.work = csr.work(_stream(dev)).data_ptr()
+    a.unit_order = _ptr(csr.unit_order())
     rec = None
     if PROFILE is not None:
         rec = {"start": torch.cuda.Event(enable_timing=True), "end": torch.cuda.Event(enable_timing=True)}
@@ -309,7 +310,7 @@ class _GatV2(torch.autograd.Function):
         out = torch.empty((n_dst, H * C), dtype=torch.float32, device=dev)
         rowmax = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
         rowden = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
-        hubs = csr.hub_table(lib.kgb_gatv2_partial_bytes(csr.n_chunks, H, C), _stream(dev))
+        hubs = csr.hub_table(lib.kgb_gatv2_partial_bytes(csr.n_chunks, H, C), _stream(dev), gat=True)
         _lib.check(lib.kgb_gatv2_fwd(dev.index, h_src.data_ptr(), h_dst.data_ptr(), n_src, n_dst, H, C,
                                      att_c.data_ptr(), float(slope), csr.rowptr.data_ptr(), csr.col.data_ptr(),
                                      _ptr(bias_c), out.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(),
@@ -342,7 +343,7 @@ class _GatV2(torch.autograd.Function):
                                          n_src, n_dst, H, C, att_c.data_ptr(), ctx.slope, csr.rowptr.data_ptr(),
                                          csr.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(),
                                          g_hdst.data_ptr(), r.data_ptr(), part.data_ptr(), n_parts,
-                                         ctypes.byref(csr.hub_table(lib.kgb_gatv2_partial_bytes(csr.n_chunks, H, C), st)),
+                                         ctypes.byref(csr.hub_table(lib.kgb_gatv2_partial_bytes(csr.n_chunks, H, C), st, gat=True)),
                                          st), "kgb_gatv2_bwd_dst")
         g_att = torch.empty(H * C, dtype=torch.float32, device=dev)
         _lib.check(lib.kgb_reduce_parts(dev.index, part.data_ptr(), n_parts, H * C, g_att.data_ptr(), st),
@@ -352,7 +353,7 @@ class _GatV2(torch.autograd.Function):
                                          H, C, att_c.data_ptr(), ctx.slope, csc.rowptr.data_ptr(),
                                          csc.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(), r.data_ptr(),
                                          g_hsrc.data_ptr(),
-                                         ctypes.byref(csc.hub_table(lib.kgb_gatv2_partial_bytes(csc.n_chunks, H, C), st)),
+                                         ctypes.byref(csc.hub_table(lib.kgb_gatv2_partial_bytes(csc.n_chunks, H, C), st, gat=True)),
                                          st), "kgb_gatv2_bwd_src")
         g_bias = g.sum(dim=0) if ctx.has_bias else None
         if ctx.same:
