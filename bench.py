@@ -102,9 +102,10 @@ class ClockSampler:
 
 
 def cross_entropy(logits: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """mean cross-entropy as logsumexp - picked logit (same value as F.cross_entropy; torch's nll_loss kernels are
-    single-block reductions that take 4 ms on 2.4 M rows)."""
-    return (torch.logsumexp(logits, dim=1) - logits.gather(1, y.unsqueeze(1)).squeeze(1)).mean()
+    """mean cross-entropy over all nodes (same value as F.cross_entropy) through the library's one-pass kernel
+    (torch's nll_loss kernels are single-block reductions that take 4 ms on 2.4 M rows)."""
+    from keras_geometric_b200 import ops
+    return ops.softmax_cross_entropy(logits, y)
 
 
 # ------------------------------------------------------------------------------------- our arm
@@ -212,10 +213,21 @@ def run_ours(args):
     ei_host = ei.cpu().pin_memory()
     e2e_steps = max(2, min(args.steps, 5))
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    ei_landed = torch.cuda.Event()
+
     def e2e_step():
         clear_cache()  # a fresh edge list arrives every step: the CSR/CSC build is inside the timed region
-        xd = x_host.to(dev, non_blocking=True)
+        cur = torch.cuda.current_stream(dev)
         eid = ei_host.to(dev, non_blocking=True)
+        ei_landed.record(cur)
+        copy_stream.wait_event(ei_landed)
+        with torch.cuda.stream(copy_stream):  # x follows edge_index over PCIe while the structure is built
+            xd = x_host.to(dev, non_blocking=True)
+        graph = get_graph(eid, n, n, 0)
+        graph.csc  # noqa: B018  (the source-major orientation the backward walks)
+        cur.wait_stream(copy_stream)
+        xd.record_stream(cur)
         return float(step(xd, eid).item())  # device -> host read of the loss
 
     e2e_step()
@@ -227,7 +239,7 @@ def run_ours(args):
     e2e_ms = (time.perf_counter() - w0) * 1e3 / e2e_steps
     e2e = {"value": n_layers * e / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": x_host.numel() * 4 + ei_host.numel() * 4, "d2h_bytes_per_step": 4,
-           "includes": "H2D of x and edge_index from pinned memory, CSR+CSC build, fwd+bwd+SGD, loss readback"}
+           "includes": "H2D of edge_index then x from pinned memory (x overlaps the CSR+CSC build), fwd+bwd+SGD, loss readback"}
 
     out = {
         "metric": "aggregated edges/sec per layer fwd+bwd", "value": value, "unit": "GTEPS", "n_gpus": 1,

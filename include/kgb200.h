@@ -94,6 +94,20 @@ int kgb_gcn_norm(int device, const int32_t* deg, int64_t n_nodes, const int32_t*
 /* out[r,f] = y[r,f] > 0 ? g[r,f] : 0 - backward of the ReLU fused into the gather / GEMM epilogues; out is dense [rows,F] */
 int kgb_relu_bwd(int device, const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t F,
                  float* out, kgb_stream_t stream);
+/* Same with the bias gradient in the same pass: out[r,f] = (y ? y[r,f] > 0 : true) ? g[r,f] : 0 and
+ * partial[p, f] = sum over the rows of CTA p of out[r,f] (p < n_parts = kgb_colsum_parts(device, rows));
+ * kgb_reduce_parts(partial, n_parts, F, bias_grad) adds them in order (deterministic).  y == NULL: no mask
+ * (plain column sums; out may then be NULL too).  F % 4 == 0, F <= 1024, 16-byte aligned rows. */
+int32_t kgb_colsum_parts(int device, int64_t rows);
+int kgb_relu_bwd_colsum(int device, const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t F,
+                        float* out, int64_t ldo, float* partial, int32_t n_parts, kgb_stream_t stream);
+/* Softmax cross-entropy over integer labels (the training step's loss; one warp per row, C <= 1024):
+ *   fwd: row_loss[r] = logsumexp(logits[r,:]) - logits[r, labels[r]]
+ *   bwd: dlogits[r,c] = (softmax(logits[r,:])[c] - (c == labels[r])) * scale * grad_loss[0]   (grad_loss: device scalar) */
+int kgb_softmax_xent_fwd(int device, const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C,
+                         float* row_loss, kgb_stream_t stream);
+int kgb_softmax_xent_bwd(int device, const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C,
+                         const float* grad_loss, float scale, float* dlogits, int64_t ldd, kgb_stream_t stream);
 /* out[k] = in[perm[k]]  (bring COO-ordered edge weights into CSR / CSC slot order) */
 int kgb_permute_f32(int device, const float* in, const int32_t* perm, int64_t n, float* out,
                     kgb_stream_t stream);

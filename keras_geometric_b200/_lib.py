@@ -60,6 +60,12 @@ SIGNATURES = {
                              c_int64, c_int64, c_void_p, c_void_p]),
     "kgb_gcn_norm": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "kgb_relu_bwd": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p]),
+    "kgb_colsum_parts": (c_int32, [c_int, c_int64]),
+    "kgb_relu_bwd_colsum": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int64,
+                                    c_void_p, c_int32, c_void_p]),
+    "kgb_softmax_xent_fwd": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "kgb_softmax_xent_bwd": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_float, c_void_p,
+                                     c_int64, c_void_p]),
     "kgb_permute_f32": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "kgb_gather_reduce_partial_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "kgb_gather_reduce": (c_int, [c_int, POINTER(GatherReduceArgs), c_void_p]),

@@ -1,0 +1,184 @@
+// Row-streaming helpers of the training step (HBM-bound, one pass each):
+//   * kgb_relu_bwd_colsum: g_pre = g * (y > 0) and the bias gradient sum_r g_pre[r,:] in the same pass
+//     (per-CTA column partials in a fixed order -> kgb_reduce_parts; deterministic, no float atomics),
+//   * kgb_softmax_xent_fwd / _bwd: mean softmax cross-entropy over integer labels, one warp per row.
+#include "common.cuh"
+
+namespace kgb {
+
+constexpr int CS_THREADS = 256;
+
+// Thread t owns column group cg = t % CG (4 floats) and row lane rl = t / CG; a CTA streams a contiguous block of rows.
+template <bool HAS_Y, bool WRITE>
+__global__ void __launch_bounds__(CS_THREADS)
+relu_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
+                       int64_t rows, int F, float* __restrict__ out, int64_t ldo, float* __restrict__ partial,
+                       int64_t rows_per_cta) {
+  extern __shared__ float4 cs_smem[];  // [RL][CG]
+  const int CG = F >> 2;
+  const int RL = CS_THREADS / CG;      // >= 1 (F <= 1024)
+  const int cg = threadIdx.x % CG;
+  const int rl = threadIdx.x / CG;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = (r0 + rows_per_cta < rows) ? r0 + rows_per_cta : rows;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < RL) {
+#pragma unroll 4
+    for (int64_t r = r0 + rl; r < r1; r += RL) {
+      float4 v = __ldcs(reinterpret_cast<const float4*>(g + r * ldg) + cg);
+      if (HAS_Y) {
+        const float4 yy = __ldcs(reinterpret_cast<const float4*>(y + r * ldy) + cg);
+        v.x = yy.x > 0.f ? v.x : 0.f;
+        v.y = yy.y > 0.f ? v.y : 0.f;
+        v.z = yy.z > 0.f ? v.z : 0.f;
+        v.w = yy.w > 0.f ? v.w : 0.f;
+      }
+      if (WRITE) *(reinterpret_cast<float4*>(out + r * ldo) + cg) = v;
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    cs_smem[rl * CG + cg] = acc;
+  }
+  __syncthreads();
+  if (rl == 0) {
+    for (int j = 1; j < RL; ++j) {
+      const float4 o = cs_smem[j * CG + cg];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    *(reinterpret_cast<float4*>(partial + (int64_t)blockIdx.x * F) + cg) = acc;
+  }
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// PER = ceil(C / 32) logits per lane kept in registers (C <= 32 * PER)
+template <int PER, bool BWD>
+__global__ void __launch_bounds__(256)
+softmax_xent_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels, int64_t rows, int C,
+                    float* __restrict__ row_loss, const float* __restrict__ gup, float scale,
+                    float* __restrict__ dlogits, int64_t ldd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wpb = blockDim.x >> 5;
+  float gs = 0.f;
+  if (BWD) gs = __ldg(gup) * scale;
+  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
+    float v[PER];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int c = lane + i * 32;
+      v[i] = (c < C) ? __ldg(logits + r * ld + c) : -INFINITY;
+      m = fmaxf(m, v[i]);
+    }
+    m = warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      v[i] = (lane + i * 32 < C) ? expf(v[i] - m) : 0.f;
+      s += v[i];
+    }
+    s = warp_sum(s);
+    const int64_t lab = __ldg(labels + r);
+    if (!BWD) {
+      // loss = logsumexp - logit[label]
+      float picked = 0.f;
+      if (lab >= 0 && lab < C && (lab & 31) == lane) picked = __ldg(logits + r * ld + lab);
+      picked = warp_sum(picked);
+      if (lane == 0) row_loss[r] = (logf(s) + m) - picked;
+    } else {
+      const float inv = 1.f / s;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = lane + i * 32;
+        if (c < C) dlogits[r * ldd + c] = (v[i] * inv - ((int64_t)c == lab ? 1.f : 0.f)) * gs;
+      }
+    }
+  }
+}
+
+template <bool BWD>
+static int launch_xent(int device, const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int C,
+                       float* row_loss, const float* gup, float scale, float* dlogits, int64_t ldd, cudaStream_t st) {
+  int64_t grid = ceil_div(rows, 8);
+  const int64_t cap = (int64_t)sm_count(device) * 8;
+  if (grid > cap) grid = cap;
+#define KGB_XENT(P)                                                                                             \
+  softmax_xent_kernel<P, BWD><<<(int)grid, 256, 0, st>>>(logits, ld, labels, rows, C, row_loss, gup, scale, dlogits, ldd)
+  if (C <= 32) KGB_XENT(1);
+  else if (C <= 64) KGB_XENT(2);
+  else if (C <= 128) KGB_XENT(4);
+  else if (C <= 256) KGB_XENT(8);
+  else if (C <= 512) KGB_XENT(16);
+  else KGB_XENT(32);
+#undef KGB_XENT
+  KGB_CHECK_LAUNCH();
+  return KGB_OK;
+}
+
+}  // namespace kgb
+
+using namespace kgb;
+
+extern "C" {
+
+int32_t kgb_colsum_parts(int device, int64_t rows) {
+  if (kgb::use_device(device) != KGB_OK) return -1;
+  int64_t parts = (int64_t)sm_count(device) * 4;
+  const int64_t by_rows = ceil_div(rows, 64);  // at least 64 rows per CTA
+  if (parts > by_rows) parts = by_rows;
+  return (int32_t)(parts < 1 ? 1 : parts);
+}
+
+int kgb_relu_bwd_colsum(int device, const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t F,
+                        float* out, int64_t ldo, float* partial, int32_t n_parts, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(rows > 0 && F > 0 && F % 4 == 0 && F <= 1024, "relu_bwd_colsum: rows > 0, F a multiple of 4 and <= 1024");
+  KGB_REQUIRE(g && partial, "NULL pointer");
+  KGB_REQUIRE(n_parts == kgb_colsum_parts(device, rows), "n_parts must come from kgb_colsum_parts");
+  KGB_REQUIRE(ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0,
+              "g / partial must be 16-byte aligned with ld % 4 == 0");
+  KGB_REQUIRE(!y || (ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0), "y must be 16-byte aligned");
+  KGB_REQUIRE(!out || (ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0), "out must be 16-byte aligned");
+  KGB_REQUIRE(!y || out, "the masked gradient needs an output buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int CG = F / 4;
+  const int RL = CS_THREADS / CG;
+  const size_t smem = (size_t)RL * CG * sizeof(float4);
+  const int64_t rpc = ceil_div(rows, (int64_t)n_parts);
+  if (y)
+    relu_bwd_colsum_kernel<true, true><<<n_parts, CS_THREADS, smem, st>>>(g, ldg, y, ldy, rows, F, out, ldo, partial, rpc);
+  else if (out)
+    relu_bwd_colsum_kernel<false, true><<<n_parts, CS_THREADS, smem, st>>>(g, ldg, y, ldy, rows, F, out, ldo, partial, rpc);
+  else
+    relu_bwd_colsum_kernel<false, false><<<n_parts, CS_THREADS, smem, st>>>(g, ldg, y, ldy, rows, F, out, ldo, partial, rpc);
+  KGB_CHECK_LAUNCH();
+  return KGB_OK;
+}
+
+int kgb_softmax_xent_fwd(int device, const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C,
+                         float* row_loss, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(rows >= 0 && C > 0 && C <= 1024, "softmax_xent: 0 < C <= 1024");
+  if (rows == 0) return KGB_OK;
+  KGB_REQUIRE(logits && labels && row_loss, "NULL pointer");
+  return launch_xent<false>(device, logits, ld, labels, rows, C, row_loss, nullptr, 0.f, nullptr, 0, (cudaStream_t)stream);
+}
+
+int kgb_softmax_xent_bwd(int device, const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C,
+                         const float* grad_loss, float scale, float* dlogits, int64_t ldd, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(rows >= 0 && C > 0 && C <= 1024, "softmax_xent: 0 < C <= 1024");
+  if (rows == 0) return KGB_OK;
+  KGB_REQUIRE(logits && labels && grad_loss && dlogits, "NULL pointer");
+  return launch_xent<true>(device, logits, ld, labels, rows, C, nullptr, grad_loss, scale, dlogits, ldd, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -158,9 +158,17 @@ class SAGEConv(MessagePassing):
                    and int(edge_index.shape[1]) > 0 and self.output_dim < int(x.shape[1])
                    and (act_is_relu or act_is_none)
                    and type(self).message is SAGEConv.message and self._uses_default("aggregate", "update"))
+        one_node = (not reorder and self.actual_aggregator in ("mean", "sum") and not dropping and num_nodes > 0
+                    and int(edge_index.shape[1]) > 0 and w_self is not None and (act_is_relu or act_is_none)
+                    and type(self).message is SAGEConv.message and self._uses_default("aggregate", "update")
+                    and ops.sage_layer_ok(x, w_neigh, w_self))
         if reorder:
             graph = get_graph(edge_index, num_nodes, num_nodes, 0)
             out = self._aggregate_after_transform(x, graph, w_neigh, w_self, bias, act_is_relu)
+        elif one_node:
+            # aggregate -> two accumulating GEMMs (bias + ReLU in the epilogue) recorded as one autograd node
+            out = ops.sage_layer(x, w_neigh, w_self, bias, get_graph(edge_index, num_nodes, num_nodes, 0),
+                                 self.actual_aggregator, act_is_relu)
         else:
             aggregated = self.aggregate_neighbors(x, edge_index, num_nodes, training=training)
             out = self._dense_update(aggregated, x, w_neigh, w_self, bias, dropping)
@@ -178,12 +186,15 @@ class SAGEConv(MessagePassing):
             w_neigh = torch.nn.functional.pad(w_neigh, (0, pad))
             w_self = torch.nn.functional.pad(w_self, (0, pad)) if w_self is not None else None
             bias = torch.nn.functional.pad(bias, (0, pad)) if bias is not None else None
-        z = ops.linear(x, w_neigh)
-        if exchange is not None:
-            z = exchange[0](z)          # halo all-to-all left in flight ...
-        root = ops.linear(x, w_self) if w_self is not None else None
-        if exchange is not None:
-            exchange[1]()               # ... while the root transform runs
+        if exchange is None and w_self is not None:
+            z, root = ops.linear_pair(x, w_neigh, w_self)
+        else:
+            z = ops.linear(x, w_neigh)
+            if exchange is not None:
+                z = exchange[0](z)          # halo all-to-all left in flight ...
+            root = ops.linear(x, w_self) if w_self is not None else None
+            if exchange is not None:
+                exchange[1]()               # ... while the root transform runs
         out = ops.gather_reduce(z, graph, self.actual_aggregator, addend=root, bias=bias,
                                 act="relu" if act_is_relu else None)
         return out[:, :fout] if pad else out

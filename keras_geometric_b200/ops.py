@@ -131,6 +131,78 @@ def relu_bwd(g: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _rows16(t: torch.Tensor) -> bool:
+    return (t.dim() == 2 and t.dtype == torch.float32 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+            and t.data_ptr() % 16 == 0 and t.shape[1] % 4 == 0 and 0 < t.shape[1] <= 1024)
+
+
+def relu_bwd_colsum(g: torch.Tensor, y: torch.Tensor | None, want_masked: bool = True):
+    """(g * (y > 0), column sums of that) in ONE pass over g (kgb_relu_bwd_colsum): the ReLU backward and the bias
+    gradient of a layer.  ``y`` None: no mask, returns ``(g, g.sum(0))``."""
+    rows = int(g.shape[0])
+    if rows == 0 or not _rows16(g) or (y is not None and not _rows16(y)):
+        gp = relu_bwd(g, y) if y is not None else g
+        return gp, gp.sum(dim=0)
+    lib = _lib.load()
+    F = int(g.shape[1])
+    dev = g.device
+    out = torch.empty((rows, F), dtype=torch.float32, device=dev) if y is not None else None
+    n_parts = int(lib.kgb_colsum_parts(dev.index, rows))
+    parts = torch.empty((n_parts, F), dtype=torch.float32, device=dev)
+    _lib.check(lib.kgb_relu_bwd_colsum(dev.index, g.data_ptr(), g.stride(0), _ptr(y), y.stride(0) if y is not None else 0,
+                                       rows, F, _ptr(out), F, parts.data_ptr(), n_parts, _stream(dev)),
+               "kgb_relu_bwd_colsum")
+    if n_parts == 1:
+        col = parts[0]
+    else:
+        col = torch.empty(F, dtype=torch.float32, device=dev)
+        _lib.check(lib.kgb_reduce_parts(dev.index, parts.data_ptr(), n_parts, F, col.data_ptr(), _stream(dev)),
+                   "kgb_reduce_parts")
+    return (out if y is not None else g), col
+
+
+class _SoftmaxXent(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        lib = _lib.load()
+        require_cuda(logits, "logits")
+        if logits.dtype != torch.float32 or logits.dim() != 2 or logits.stride(1) != 1:
+            logits = logits.to(torch.float32).contiguous()
+        labels = labels.to(torch.int64).contiguous()
+        rows, C = int(logits.shape[0]), int(logits.shape[1])
+        if labels.shape[0] != rows:
+            raise ValueError(f"softmax_cross_entropy: {rows} rows of logits but {labels.shape[0]} labels")
+        row_loss = torch.empty(rows, dtype=torch.float32, device=logits.device)
+        _lib.check(lib.kgb_softmax_xent_fwd(logits.device.index, logits.data_ptr(), logits.stride(0), labels.data_ptr(),
+                                            rows, C, row_loss.data_ptr(), _stream(logits.device)), "kgb_softmax_xent_fwd")
+        ctx.save_for_backward(logits, labels)
+        return row_loss.mean()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        logits, labels = ctx.saved_tensors
+        lib = _lib.load()
+        rows, C = int(logits.shape[0]), int(logits.shape[1])
+        ldd = (C + 3) // 4 * 4   # padded rows: the gradient of a [:, :C] slice of a padded buffer is then a view
+        buf = torch.empty((rows, ldd), dtype=torch.float32, device=logits.device)
+        if ldd != C:
+            buf[:, C:].zero_()
+        g = g.to(torch.float32).reshape(1).contiguous()
+        _lib.check(lib.kgb_softmax_xent_bwd(logits.device.index, logits.data_ptr(), logits.stride(0), labels.data_ptr(),
+                                            rows, C, g.data_ptr(), 1.0 / max(rows, 1), buf.data_ptr(), ldd,
+                                            _stream(logits.device)), "kgb_softmax_xent_bwd")
+        return buf[:, :C], None
+
+
+def softmax_cross_entropy(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """Mean softmax cross-entropy over integer labels (== torch.nn.functional.cross_entropy) in one pass forward
+    and one pass backward; C <= 1024."""
+    if int(logits.shape[1]) > 1024:
+        raise ValueError("softmax_cross_entropy supports up to 1024 classes")
+    return _SoftmaxXent.apply(logits, labels)
+
+
 def permute_f32(w: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(perm.shape[0], dtype=torch.float32, device=w.device)
@@ -195,10 +267,12 @@ class _GatherReduce(torch.autograd.Function):
         saved = list(ctx.saved_tensors)
         is_max = op in _lib.MAX_OPS
         out = saved[-1] if (is_max or ctx.act == "relu") else None
-        if ctx.act == "relu":
+        g_bias = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            g, g_bias = relu_bwd_colsum(g, out if ctx.act == "relu" else None)
+        elif ctx.act == "relu":
             g = relu_bwd(g, out)
         g_addend = (g * ctx.addend_scale if ctx.addend_scale != 1.0 else g) if ctx.has_addend else None
-        g_bias = g.sum(dim=0) if ctx.has_bias else None
         gx = None
         if ctx.needs_input_grad[0]:
             if is_max:
@@ -439,6 +513,23 @@ def linear_tc(a: torch.Tensor, w_hi: torch.Tensor, w_lo: torch.Tensor, n_out: in
     return out
 
 
+def _dw_tc(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """dW[K,N] = X^T G on the hand-written tcgen05 kernel: one node slice per CTA -> per-CTA partials (promoted to
+    fp32 every 256 nodes), added in CTA order (deterministic, no float atomics across CTAs).  K, N <= 256."""
+    lib = _lib.load()
+    M, K, N = int(x.shape[0]), int(x.shape[1]), int(g.shape[1])
+    n_parts = lib.kgb_linear_tc_dw_parts(x.device.index, M)
+    parts = torch.empty((n_parts, K, N), dtype=torch.float32, device=x.device)
+    _lib.check(lib.kgb_linear_tc_dw(x.device.index, x.data_ptr(), x.stride(0), g.data_ptr(), g.stride(0), M,
+                                    K, N, parts.data_ptr(), n_parts, _stream(x.device)), "kgb_linear_tc_dw")
+    if n_parts == 1:
+        return parts[0]
+    gw = torch.empty((K, N), dtype=torch.float32, device=x.device)
+    _lib.check(lib.kgb_reduce_parts(x.device.index, parts.data_ptr(), n_parts, K * N, gw.data_ptr(),
+                                    _stream(x.device)), "kgb_reduce_parts")
+    return gw
+
+
 class _Linear(torch.autograd.Function):
     """out = x @ w (+ addend) on the tensor cores (K8).  Forward and dX run the hand-written tcgen05 3xTF32 kernel
     (csrc/tc_gemm.cu), and so does dW = X^T G (MN-major operands, reduction over the node dimension) for widths up
@@ -478,7 +569,10 @@ class _Linear(torch.autograd.Function):
     def backward(ctx, g):
         x, w = ctx.saved_tensors[:2]
         g = _f32c(g, "grad")
-        if ctx.relu:
+        g_bias = None
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            g, g_bias = relu_bwd_colsum(g, ctx.saved_tensors[2] if ctx.relu else None)
+        elif ctx.relu:
             g = relu_bwd(g, ctx.saved_tensors[2])
         if g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
             g = g.contiguous()
@@ -495,19 +589,7 @@ class _Linear(torch.autograd.Function):
                 gx = torch.matmul(g, w.t())
         if ctx.needs_input_grad[1]:
             if fast and M >= 16 and K <= 256 and N <= 256:
-                # dW[K,N] = X^T G on the hand-written tcgen05 kernel: one node slice per CTA -> per-CTA partials
-                # (promoted to fp32 every 256 nodes), added in CTA order (deterministic, no float atomics across CTAs)
-                lib = _lib.load()
-                n_parts = lib.kgb_linear_tc_dw_parts(x.device.index, M)
-                parts = torch.empty((n_parts, K, N), dtype=torch.float32, device=x.device)
-                _lib.check(lib.kgb_linear_tc_dw(x.device.index, x.data_ptr(), x.stride(0), g.data_ptr(), g.stride(0), M,
-                                                K, N, parts.data_ptr(), n_parts, _stream(x.device)), "kgb_linear_tc_dw")
-                if n_parts == 1:
-                    gw = parts[0]
-                else:
-                    gw = torch.empty((K, N), dtype=torch.float32, device=x.device)
-                    _lib.check(lib.kgb_reduce_parts(x.device.index, parts.data_ptr(), n_parts, K * N, gw.data_ptr(),
-                                                    _stream(x.device)), "kgb_reduce_parts")
+                gw = _dw_tc(x, g)
             elif fast:
                 # wider than the hand-written kernel: batched bf16x9 kernel over node slices, partials added in order
                 S = _SPLIT_ROWS
@@ -526,10 +608,116 @@ class _Linear(torch.autograd.Function):
                                                             gw.data_ptr(), _stream(x.device)), "kgb_reduce_parts")
             else:
                 gw = torch.matmul(x.t(), g)
-        return gx, gw, (g if ctx.has_addend else None), (g.sum(dim=0) if ctx.has_bias else None), None
+        return gx, gw, (g if ctx.has_addend else None), g_bias, None
 
 
 def linear(x, w, addend=None, bias=None, act=None) -> torch.Tensor:
     """act(x @ w + addend + bias) - the dense node-feature transform of every conv layer (K8); ``act`` in
     (None, "relu").  Addend, bias and ReLU run in the GEMM epilogue."""
     return _Linear.apply(x, w, addend, bias, act)
+
+
+def sage_layer_ok(x: torch.Tensor, w_neigh: torch.Tensor, w_self: torch.Tensor) -> bool:
+    """Shapes the one-node SAGE layer (``sage_layer``) covers: everything on the hand-written tcgen05 kernels."""
+    M, K, N = int(x.shape[0]), int(x.shape[1]), int(w_neigh.shape[1])
+    return (_gemm_ok(x, w_neigh, w_self) and _tc_ok(M, N) and _tc_ok(M, K) and K <= 256 and N <= 256
+            and tuple(w_self.shape) == tuple(w_neigh.shape))
+
+
+class _SageLayer(torch.autograd.Function):
+    """act(OP_j(x_j) @ w_neigh + x @ w_self + bias) as ONE autograd node.  x feeds both the aggregation and the root
+    transform; as separate nodes autograd adds their two [N, F] gradients in an extra pass, here the root-weight
+    dX GEMM accumulates onto the transposed gather's output in its epilogue, and the bias gradient comes out of
+    the ReLU-backward pass."""
+
+    @staticmethod
+    def forward(ctx, x, w_neigh, w_self, bias, graph: GraphStructure, op_name: str, relu: bool):
+        op = _lib.OPS[op_name]
+        x = _f32c(x, "x")
+        w_neigh, w_self = _f32c(w_neigh, "w_neigh"), _f32c(w_self, "w_self")
+        bias_c = _f32c(bias, "bias").contiguous() if bias is not None else None
+        N = int(w_neigh.shape[1])
+        agg, _ = gather_reduce_raw(x, graph.csr, op)
+        hi, lo = _split_weight(w_neigh, transpose=True)
+        t = linear_tc(agg, hi, lo, N)
+        hi, lo = _split_weight(w_self, transpose=True)
+        out = linear_tc(x, hi, lo, N, c=t, bias=bias_c, relu=relu)
+        ctx.save_for_backward(x, agg, w_neigh, w_self, *([out] if relu else []))
+        ctx.graph, ctx.op, ctx.relu, ctx.has_bias = graph, op, relu, bias is not None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, agg, w_neigh, w_self = ctx.saved_tensors[:4]
+        out = ctx.saved_tensors[4] if ctx.relu else None
+        g = _f32c(g, "grad")
+        g_bias = None
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            g, g_bias = relu_bwd_colsum(g, out)
+        elif ctx.relu:
+            g = relu_bwd(g, out)
+        if g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
+            g = g.contiguous()
+        K = int(x.shape[1])
+        g_wn = _dw_tc(agg, g) if ctx.needs_input_grad[1] else None
+        g_ws = _dw_tc(x, g) if ctx.needs_input_grad[2] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            hi, lo = _split_weight(w_neigh, transpose=False)
+            d_agg = linear_tc(g, hi, lo, K)
+            kw = {"src_scale": ctx.graph.csr.inv_deg} if ctx.op == _lib.OP_MEAN else {}
+            gx, _ = gather_reduce_raw(d_agg, ctx.graph.csc, _lib.OP_SUM, **kw)
+            hi, lo = _split_weight(w_self, transpose=False)
+            gx = linear_tc(g, hi, lo, K, c=gx)
+        return gx, g_wn, g_ws, g_bias, None, None, None
+
+
+def sage_layer(x, w_neigh, w_self, bias, graph: GraphStructure, op: str, relu: bool) -> torch.Tensor:
+    if op not in ("mean", "sum"):
+        raise ValueError("sage_layer fuses the linear aggregators (mean, sum) only")
+    return _SageLayer.apply(x, w_neigh, w_self, bias, graph, op, relu)
+
+
+class _LinearPair(torch.autograd.Function):
+    """(x @ w_a, x @ w_b) as one autograd node: the second dX GEMM accumulates onto the first in its epilogue
+    instead of autograd adding two [N, F] gradients in a separate pass."""
+
+    @staticmethod
+    def forward(ctx, x, w_a, w_b):
+        x, w_a, w_b = _f32c(x, "x"), _f32c(w_a, "w_a"), _f32c(w_b, "w_b")
+        N = int(w_a.shape[1])
+        hi, lo = _split_weight(w_a, transpose=True)
+        a = linear_tc(x, hi, lo, N)
+        hi, lo = _split_weight(w_b, transpose=True)
+        b = linear_tc(x, hi, lo, N)
+        ctx.save_for_backward(x, w_a, w_b)
+        return a, b
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ga, gb):
+        x, w_a, w_b = ctx.saved_tensors
+        K = int(x.shape[1])
+
+        def prep(g):
+            g = _f32c(g, "grad")
+            return g.contiguous() if (g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16) else g
+
+        ga, gb = prep(ga), prep(gb)
+        g_wa = _dw_tc(x, ga) if ctx.needs_input_grad[1] else None
+        g_wb = _dw_tc(x, gb) if ctx.needs_input_grad[2] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            hi, lo = _split_weight(w_a, transpose=False)
+            gx = linear_tc(ga, hi, lo, K)
+            hi, lo = _split_weight(w_b, transpose=False)
+            gx = linear_tc(gb, hi, lo, K, c=gx)
+        return gx, g_wa, g_wb
+
+
+def linear_pair(x, w_a, w_b):
+    """(x @ w_a, x @ w_b) for two weights of the same shape; falls back to two ``linear`` calls off the fast path."""
+    if sage_layer_ok(x, w_a, w_b):
+        return _LinearPair.apply(x, w_a, w_b)
+    return linear(x, w_a), linear(x, w_b)

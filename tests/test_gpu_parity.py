@@ -344,6 +344,76 @@ def test_sage_reordered_fused_path():
             close(a_, b_, rtol=1e-4, atol_scale=2e-5, msg="sage reorder grad")
 
 
+@pytest.mark.parametrize("fin,fout,act", [(40, 64, "relu"), (64, 64, None), (100, 256, "relu"), (256, 48, "relu")])
+def test_sage_one_node_paths_vs_oracle(fin, fout, act):
+    """Sizes that take the single-autograd-node paths (ops.sage_layer / ops.linear_pair on the tcgen05 kernels):
+    output and all four gradients against the oracle's SAGEConv."""
+    from keras_geometric_b200 import SAGEConv
+    rng = np.random.default_rng(fin * 7 + fout)
+    n, e = 700, 9000
+    ei = rand_graph(rng, n, n, e, hub=1200)
+    x = rng.standard_normal((n, fin)).astype(np.float32)
+    wn, ws = (rng.standard_normal((fin, fout)).astype(np.float32) * 0.2 for _ in range(2))
+    b = rng.standard_normal(fout).astype(np.float32)
+    R = rng.standard_normal((n, fout)).astype(np.float32)
+    for aggr in ("mean", "sum"):
+        layer = SAGEConv(fout, aggregator=aggr, activation=act)
+        layer.build([(n, fin), (2, e)]); layer.built = True
+        _set(layer.lin_neigh.kernel, wn); _set(layer.lin_self.kernel, ws); _set(layer.bias, b)
+        xg = cuda(x).requires_grad_(True)
+        out = layer([xg, ei])
+        ts = [torch.from_numpy(t).requires_grad_(True) for t in (x, wn, ws, b)]
+        want = ref.sage_conv(ts[0], torch.from_numpy(ei), ts[1], ts[2], ts[3], aggr, torch.relu if act else None)
+        close(out, want, rtol=1e-4, atol_scale=2e-5, msg=f"sage one-node {aggr}")
+        got = torch.autograd.grad((out * cuda(R)).sum(), [xg, layer.lin_neigh.kernel, layer.lin_self.kernel, layer.bias])
+        exp = torch.autograd.grad((want * torch.from_numpy(R)).sum(), ts)
+        for a_, b_, nm in zip(got, exp, ("dx", "dWn", "dWs", "db")):
+            close(a_, b_, rtol=1e-4, atol_scale=3e-5, msg=f"sage one-node grad {nm} {aggr}")
+        # x without gradient (first layer of a model): weight gradients only
+        out2 = layer([cuda(x), ei])
+        got2 = torch.autograd.grad((out2 * cuda(R)).sum(), [layer.lin_neigh.kernel, layer.lin_self.kernel, layer.bias])
+        for a_, b_ in zip(got2, exp[1:]):
+            close(a_, b_, rtol=1e-4, atol_scale=3e-5, msg="sage one-node grad (x const)")
+
+
+@pytest.mark.parametrize("rows,F", [(1, 4), (63, 48), (1000, 100), (70001, 256), (5000, 1024)])
+def test_relu_bwd_colsum(rows, F):
+    from keras_geometric_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(rows + F)
+    g = torch.randn((rows, F), device="cuda", generator=gen)
+    y = torch.randn((rows, F), device="cuda", generator=gen)
+    gp, col = ops.relu_bwd_colsum(g, y)
+    want = torch.where(y > 0, g, torch.zeros_like(g))
+    assert torch.equal(gp, want)
+    close(col, want.double().sum(0).float(), rtol=1e-5, atol_scale=1e-5, msg="colsum")
+    gp2, col2 = ops.relu_bwd_colsum(g, y)
+    assert torch.equal(col, col2)          # fixed reduction order
+    same, col3 = ops.relu_bwd_colsum(g, None)
+    assert same is g
+    close(col3, g.double().sum(0).float(), rtol=1e-5, atol_scale=1e-5, msg="plain colsum")
+    # padded rows (a [:, :F] view of a wider buffer)
+    wide = torch.randn((rows, F + 4), device="cuda", generator=gen)
+    _, col4 = ops.relu_bwd_colsum(wide[:, :F], None)
+    close(col4, wide[:, :F].double().sum(0).float(), rtol=1e-5, atol_scale=1e-5, msg="strided colsum")
+
+
+@pytest.mark.parametrize("rows,C", [(1, 2), (100, 47), (5000, 47), (3000, 7), (2000, 130), (700, 1000)])
+def test_softmax_cross_entropy(rows, C):
+    from keras_geometric_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(rows * 3 + C)
+    pad = (-C) % 4
+    base = torch.randn((rows, C + pad), device="cuda", generator=gen) * 3
+    logits = base[:, :C].detach().requires_grad_(True)   # strided rows like a padded layer output
+    y = torch.randint(0, C, (rows,), device="cuda", generator=gen)
+    loss = ops.softmax_cross_entropy(logits, y)
+    (gl,) = torch.autograd.grad(loss * 1.7, [logits])
+    ref_logits = base[:, :C].double().detach().requires_grad_(True)
+    want = torch.nn.functional.cross_entropy(ref_logits, y)
+    (gw,) = torch.autograd.grad(want * 1.7, [ref_logits])
+    assert abs(float(loss) - float(want)) <= 1e-5 * max(1.0, abs(float(want)))
+    close(gl, gw.float(), rtol=1e-4, atol_scale=1e-5, msg="xent grad")
+
+
 @pytest.mark.parametrize("tag", ["sum", "mean_eps", "max"])
 def test_golden_gin(tag):
     from keras_geometric_b200 import GINConv
