@@ -284,6 +284,17 @@ int kgb_split_tf32(int device, const float* w, int32_t rows, int32_t cols, int64
 int kgb_linear_tc(int device, const float* A, int64_t lda, int32_t M, int32_t K, const float* wt_hi,
                   const float* wt_lo, int32_t N, const float* C, int64_t ldc, const float* bias, int32_t act,
                   float* D, int64_t ldd, kgb_stream_t stream);
+/* Same with an output leading dimension, to fill a column block of a wider (K-concatenated) split buffer. */
+int kgb_split_tf32_ld(int device, const float* w, int32_t rows, int32_t cols, int64_t ld, int32_t transpose,
+                      float* hi, float* lo, int64_t ldo, kgb_stream_t stream);
+/* D = [A1 | A2] * [W1 ; W2] (+ C) (+ bias) (ReLU): two node-feature operands that share the row dimension are
+ * multiplied in ONE pass (SAGEConv's lin_neigh(agg) + lin_self(x), sage_conv.py:411-433; the sum of two dX GEMMs).
+ * wt_hi / wt_lo are [kgb_linear_tc_rows(N), kgb_linear_tc2_k(K1, K2)]: W1^T in columns [0, K1), zeros up to the next
+ * multiple of 32, then W2^T.  K2 == 0 (A2 NULL) is kgb_linear_tc. */
+int32_t kgb_linear_tc2_k(int32_t K1, int32_t K2);
+int kgb_linear_tc2(int device, const float* A1, int64_t lda1, int32_t K1, const float* A2, int64_t lda2, int32_t K2,
+                   int32_t M, const float* wt_hi, const float* wt_lo, int32_t N, const float* C, int64_t ldc,
+                   const float* bias, int32_t act, float* D, int64_t ldd, kgb_stream_t stream);
 
 /* dW[Kx,N] = X[M,Kx]^T * G[M,N] with the same tcgen05 3xTF32 machinery (both operands MN-major, both split in
  * shared memory).  The node dimension is cut into kgb_linear_tc_dw_parts() contiguous slices, one per CTA; slice p

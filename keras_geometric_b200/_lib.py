@@ -97,6 +97,11 @@ SIGNATURES = {
     "kgb_split_tf32": (c_int, [c_int, c_void_p, c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "kgb_linear_tc": (c_int, [c_int, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
                               c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
+    "kgb_split_tf32_ld": (c_int, [c_int, c_void_p, c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_int64,
+                                  c_void_p]),
+    "kgb_linear_tc2_k": (c_int32, [c_int32, c_int32]),
+    "kgb_linear_tc2": (c_int, [c_int, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                               c_int32, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
     "kgb_linear_tc_dw_parts": (c_int32, [c_int, c_int64]),
     "kgb_linear_tc_dw": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p,
                                  c_int32, c_void_p]),

@@ -100,6 +100,8 @@ struct TcParams {
   int relu;
   float* D; int64_t ldd;
   int n_tiles;
+  int kblocks;  // k-blocks in total
+  int kb1;      // k-blocks read through map_a; the rest comes from map_a2 (second A operand, K-concatenated)
 };
 
 template <int BN>
@@ -115,8 +117,9 @@ struct TcCfg {
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-               const __grid_constant__ CUtensorMap map_blo, const TcParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+               const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+               const TcParams p) {
   using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -131,7 +134,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+  const int kblocks = p.kblocks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -170,7 +173,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t ph = (it / S) & 1;
           mbar_wait(empty + s, ph ^ 1);
           mbar_expect_tx(full + s, Cfg::A_BYTES + 2 * Cfg::B_BYTES);
-          tma_load_2d(sA(s), &map_a, full + s, kb * TC_BK, tile * TC_BM);
+          if (kb < p.kb1) tma_load_2d(sA(s), &map_a, full + s, kb * TC_BK, tile * TC_BM);
+          else tma_load_2d(sA(s), &map_a2, full + s, (kb - p.kb1) * TC_BK, tile * TC_BM);
           tma_load_2d(sBhi(s), &map_bhi, full + s, kb * TC_BK, 0);
           tma_load_2d(sBlo(s), &map_blo, full + s, kb * TC_BK, 0);
         }
@@ -535,14 +539,14 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
 
 // W [rows, cols] (row-major, ld) -> hi/lo tf32 parts, optionally transposed: out is [cols, rows] when transpose
 __global__ void split_tf32_kernel(const float* __restrict__ w, int rows, int cols, int64_t ld, int transpose,
-                                  float* __restrict__ hi, float* __restrict__ lo) {
+                                  float* __restrict__ hi, float* __restrict__ lo, int64_t ldo) {
   const int64_t n = (int64_t)rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i % cols);
     const float v = w[(int64_t)r * ld + c];
     float h, l;
     split_tf32(v, h, l);
-    const int64_t o = transpose ? (int64_t)c * rows + r : i;
+    const int64_t o = transpose ? (int64_t)c * ldo + r : (int64_t)r * ldo + c;
     hi[o] = h;
     lo[o] = l;
   }
@@ -588,8 +592,8 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t col
 }
 
 template <int BN>
-static int tc_launch(int device, const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p,
-                     cudaStream_t st) {
+static int tc_launch(int device, const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mh,
+                     const CUtensorMap& ml, const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool attr_done[64] = {};
   if (device < 64 && !attr_done[device]) {
@@ -598,7 +602,7 @@ static int tc_launch(int device, const CUtensorMap& ma, const CUtensorMap& mh, c
   }
   int grid = sm_count(device);
   if (grid > p.n_tiles) grid = p.n_tiles;
-  tc_gemm_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mh, ml, p);
+  tc_gemm_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, ma2, mh, ml, p);
   KGB_CHECK_LAUNCH();
   return KGB_OK;
 }
@@ -661,45 +665,70 @@ int kgb_linear_tc_dw(int device, const float* X, int64_t ldx, const float* G, in
 
 int32_t kgb_linear_tc_rows(int32_t N) { return N <= 64 ? 64 : (N <= 128 ? 128 : 256); }
 
-int kgb_split_tf32(int device, const float* w, int32_t rows, int32_t cols, int64_t ld, int32_t transpose, float* hi,
-                   float* lo, kgb_stream_t stream) {
+int kgb_split_tf32_ld(int device, const float* w, int32_t rows, int32_t cols, int64_t ld, int32_t transpose, float* hi,
+                      float* lo, int64_t ldo, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(w && hi && lo && rows > 0 && cols > 0 && ld >= cols, "bad arguments");
+  KGB_REQUIRE(ldo >= (transpose ? rows : cols), "output leading dimension too small");
   const int64_t n = (int64_t)rows * cols;
   int grid = (int)((n + 255) / 256);
   if (grid > 1184) grid = 1184;
-  split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, rows, cols, ld, transpose, hi, lo);
+  split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, rows, cols, ld, transpose, hi, lo, ldo);
   KGB_CHECK_LAUNCH();
   return KGB_OK;
+}
+
+int kgb_split_tf32(int device, const float* w, int32_t rows, int32_t cols, int64_t ld, int32_t transpose, float* hi,
+                   float* lo, kgb_stream_t stream) {
+  return kgb_split_tf32_ld(device, w, rows, cols, ld, transpose, hi, lo, transpose ? rows : cols, stream);
+}
+
+int32_t kgb_linear_tc2_k(int32_t K1, int32_t K2) { return (K1 + TC_BK - 1) / TC_BK * TC_BK + K2; }
+
+int kgb_linear_tc2(int device, const float* A1, int64_t lda1, int32_t K1, const float* A2, int64_t lda2, int32_t K2,
+                   int32_t M, const float* wt_hi, const float* wt_lo, int32_t N, const float* C, int64_t ldc,
+                   const float* bias, int32_t act, float* D, int64_t ldd, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "bad sizes");
+  if (M == 0) return KGB_OK;
+  KGB_REQUIRE(M >= TC_BM, "kgb_linear_tc needs at least %d rows", TC_BM);
+  KGB_REQUIRE(A1 && wt_hi && wt_lo && D && (K2 == 0 || A2), "NULL operand");
+  KGB_REQUIRE(N <= 256 && N % 4 == 0 && K1 % 4 == 0 && K2 % 4 == 0, "kgb_linear_tc needs N <= 256 and N, K multiples of 4");
+  KGB_REQUIRE(aligned16(A1) && (!A2 || aligned16(A2)) && aligned16(wt_hi) && aligned16(wt_lo) && aligned16(D) &&
+                  (!C || aligned16(C)) && (!bias || aligned16(bias)) && lda1 % 4 == 0 && (!A2 || lda2 % 4 == 0) &&
+                  ldd % 4 == 0 && (!C || ldc % 4 == 0),
+              "operands must be 16-byte aligned with leading dimensions multiple of 4");
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int kb1 = (K1 + TC_BK - 1) / TC_BK;
+  const int Kcat = K2 > 0 ? kb1 * TC_BK + K2 : K1;   // the split weights are [BN, Kcat]
+  CUtensorMap ma, ma2, mh, ml;
+  int rc = make_map(&ma, A1, M, K1, lda1, TC_BM);
+  if (rc != KGB_OK) return rc;
+  if (K2 > 0) {
+    rc = make_map(&ma2, A2, M, K2, lda2, TC_BM);
+    if (rc != KGB_OK) return rc;
+  } else {
+    ma2 = ma;
+  }
+  rc = make_map(&mh, wt_hi, BN, Kcat, Kcat, BN);  // zero-padded to BN rows (kgb_linear_tc_rows)
+  if (rc != KGB_OK) return rc;
+  rc = make_map(&ml, wt_lo, BN, Kcat, Kcat, BN);
+  if (rc != KGB_OK) return rc;
+  TcParams p;
+  p.M = M; p.N = N; p.K = Kcat; p.C = C; p.ldc = ldc; p.bias = bias; p.relu = (act == KGB_ACT_RELU);
+  p.D = D; p.ldd = ldd; p.n_tiles = (M + TC_BM - 1) / TC_BM;
+  p.kb1 = kb1;
+  p.kblocks = kb1 + (K2 + TC_BK - 1) / TC_BK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 64) return tc_launch<64>(device, ma, ma2, mh, ml, p, st);
+  if (BN == 128) return tc_launch<128>(device, ma, ma2, mh, ml, p, st);
+  return tc_launch<256>(device, ma, ma2, mh, ml, p, st);
 }
 
 int kgb_linear_tc(int device, const float* A, int64_t lda, int32_t M, int32_t K, const float* wt_hi, const float* wt_lo,
                   int32_t N, const float* C, int64_t ldc, const float* bias, int32_t act, float* D, int64_t ldd,
                   kgb_stream_t stream) {
-  KGB_USE_DEVICE(device);
-  KGB_REQUIRE(M >= 0 && N > 0 && K > 0, "bad sizes");
-  if (M == 0) return KGB_OK;
-  KGB_REQUIRE(M >= TC_BM, "kgb_linear_tc needs at least %d rows", TC_BM);
-  KGB_REQUIRE(A && wt_hi && wt_lo && D, "NULL operand");
-  KGB_REQUIRE(N <= 256 && N % 4 == 0 && K % 4 == 0, "kgb_linear_tc needs N <= 256 and N, K multiples of 4");
-  KGB_REQUIRE(aligned16(A) && aligned16(wt_hi) && aligned16(wt_lo) && aligned16(D) && (!C || aligned16(C)) &&
-                  (!bias || aligned16(bias)) && lda % 4 == 0 && ldd % 4 == 0 && (!C || ldc % 4 == 0),
-              "operands must be 16-byte aligned with leading dimensions multiple of 4");
-  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  CUtensorMap ma, mh, ml;
-  int rc = make_map(&ma, A, M, K, lda, TC_BM);
-  if (rc != KGB_OK) return rc;
-  rc = make_map(&mh, wt_hi, BN, K, K, BN);  // the split buffers are zero-padded to BN rows (kgb_linear_tc_rows)
-  if (rc != KGB_OK) return rc;
-  rc = make_map(&ml, wt_lo, BN, K, K, BN);
-  if (rc != KGB_OK) return rc;
-  TcParams p;
-  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.relu = (act == KGB_ACT_RELU);
-  p.D = D; p.ldd = ldd; p.n_tiles = (M + TC_BM - 1) / TC_BM;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 64) return tc_launch<64>(device, ma, mh, ml, p, st);
-  if (BN == 128) return tc_launch<128>(device, ma, mh, ml, p, st);
-  return tc_launch<256>(device, ma, mh, ml, p, st);
+  return kgb_linear_tc2(device, A, lda, K, nullptr, 0, 0, M, wt_hi, wt_lo, N, C, ldc, bias, act, D, ldd, stream);
 }
 
 }  // extern "C"

@@ -500,6 +500,43 @@ def _split_weight(w: torch.Tensor, transpose: bool):
     return buf[0], buf[1]
 
 
+def _split_weight_pair(w1: torch.Tensor, w2: torch.Tensor, transpose: bool):
+    """tf32 hi/lo parts of [W1 ; W2] stacked along the reduction dimension for kgb_linear_tc2: [n_out, K1p + K2]
+    with W1's block zero-padded to a multiple of 32 columns."""
+    lib = _lib.load()
+    outs = []
+    for w in (w1, w2):
+        rows, cols = int(w.shape[0]), int(w.shape[1])
+        outs.append((cols, rows) if transpose else (rows, cols))
+    (n_out, k1), (n_out2, k2) = outs
+    if n_out != n_out2:
+        raise ValueError("the two weights must produce the same output width")
+    kcat = int(lib.kgb_linear_tc2_k(k1, k2))
+    bn = lib.kgb_linear_tc_rows(n_out)
+    buf = torch.zeros((2, bn, kcat), dtype=torch.float32, device=w1.device)
+    off = 0
+    for w, k in ((w1, k1), (w2, k2)):
+        _lib.check(lib.kgb_split_tf32_ld(w.device.index, w.data_ptr(), int(w.shape[0]), int(w.shape[1]), w.stride(0),
+                                         int(transpose), buf[0, :, off:].data_ptr(), buf[1, :, off:].data_ptr(), kcat,
+                                         _stream(w.device)), "kgb_split_tf32_ld")
+        off = kcat - k2
+    return buf[0], buf[1]
+
+
+def linear_tc2(a1: torch.Tensor, a2: torch.Tensor, w_hi: torch.Tensor, w_lo: torch.Tensor, n_out: int, *, c=None,
+               bias=None, relu: bool = False) -> torch.Tensor:
+    """One kgb_linear_tc2 launch: [a1 | a2] @ [W1 ; W2] (+ c) (+ bias) (ReLU) on tcgen05 (3xTF32)."""
+    lib = _lib.load()
+    M = int(a1.shape[0])
+    out = torch.empty((M, n_out), dtype=torch.float32, device=a1.device)
+    _lib.check(lib.kgb_linear_tc2(a1.device.index, a1.data_ptr(), a1.stride(0), int(a1.shape[1]), a2.data_ptr(),
+                                  a2.stride(0), int(a2.shape[1]), M, w_hi.data_ptr(), w_lo.data_ptr(), n_out, _ptr(c),
+                                  c.stride(0) if c is not None else 0, _ptr(bias),
+                                  _lib.ACT_RELU if relu else _lib.ACT_NONE, out.data_ptr(), out.stride(0),
+                                  _stream(a1.device)), "kgb_linear_tc2")
+    return out
+
+
 def linear_tc(a: torch.Tensor, w_hi: torch.Tensor, w_lo: torch.Tensor, n_out: int, *, c=None, bias=None,
               relu: bool = False) -> torch.Tensor:
     """One kgb_linear_tc launch: a [M,K] @ Wt[n_out,K]^T (+ c) (+ bias) (ReLU) on tcgen05 (3xTF32)."""
@@ -638,10 +675,8 @@ class _SageLayer(torch.autograd.Function):
         bias_c = _f32c(bias, "bias").contiguous() if bias is not None else None
         N = int(w_neigh.shape[1])
         agg, _ = gather_reduce_raw(x, graph.csr, op)
-        hi, lo = _split_weight(w_neigh, transpose=True)
-        t = linear_tc(agg, hi, lo, N)
-        hi, lo = _split_weight(w_self, transpose=True)
-        out = linear_tc(x, hi, lo, N, c=t, bias=bias_c, relu=relu)
+        hi, lo = _split_weight_pair(w_neigh, w_self, transpose=True)   # [agg | x] @ [w_neigh ; w_self] in one pass
+        out = linear_tc2(agg, x, hi, lo, N, bias=bias_c, relu=relu)
         ctx.save_for_backward(x, agg, w_neigh, w_self, *([out] if relu else []))
         ctx.graph, ctx.op, ctx.relu, ctx.has_bias = graph, op, relu, bias is not None
         return out
@@ -709,10 +744,8 @@ class _LinearPair(torch.autograd.Function):
         g_wb = _dw_tc(x, gb) if ctx.needs_input_grad[2] else None
         gx = None
         if ctx.needs_input_grad[0]:
-            hi, lo = _split_weight(w_a, transpose=False)
-            gx = linear_tc(ga, hi, lo, K)
-            hi, lo = _split_weight(w_b, transpose=False)
-            gx = linear_tc(gb, hi, lo, K, c=gx)
+            hi, lo = _split_weight_pair(w_a, w_b, transpose=False)      # [ga | gb] @ [w_a^T ; w_b^T] in one pass
+            gx = linear_tc2(ga, gb, hi, lo, K)
         return gx, g_wa, g_wb
 
 

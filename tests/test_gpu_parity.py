@@ -577,6 +577,31 @@ def test_linear_tensor_core_gemm(M, K, N):
     close(gad, R, msg="gemm d addend")
 
 
+@pytest.mark.parametrize("M,K1,K2,N", [(128, 4, 4, 4), (1000, 100, 100, 256), (4097, 256, 256, 256), (3000, 48, 48, 256),
+                                       (2000, 32, 64, 64), (777, 36, 8, 132)])
+def test_linear_two_operands_one_pass(M, K1, K2, N):
+    """[A1 | A2] @ [W1 ; W2] + bias (ReLU) through kgb_linear_tc2 (K-concatenated operands) vs float64."""
+    from keras_geometric_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(M + K1 + N)
+    a1 = torch.randn((M, K1), device="cuda", generator=gen)
+    a2 = torch.randn((M, K2), device="cuda", generator=gen)
+    w1 = torch.randn((K1, N), device="cuda", generator=gen) * 0.2
+    w2 = torch.randn((K2, N), device="cuda", generator=gen) * 0.2
+    b = torch.randn(N, device="cuda", generator=gen)
+    want = a1.double() @ w1.double() + a2.double() @ w2.double() + b.double()
+    hi, lo = ops._split_weight_pair(w1, w2, transpose=True)
+    close(ops.linear_tc2(a1, a2, hi, lo, N, bias=b), want.float(), rtol=1e-5, atol_scale=1e-5, msg="tc2")
+    close(ops.linear_tc2(a1, a2, hi, lo, N, bias=b, relu=True), torch.relu(want).float(), rtol=1e-5, atol_scale=1e-5,
+          msg="tc2 relu")
+    # the untransposed pairing used by the backward: [G1 | G2] @ [W1^T ; W2^T]
+    g1 = torch.randn((M, N), device="cuda", generator=gen)
+    g2 = torch.randn((M, N), device="cuda", generator=gen)
+    if K1 == K2:
+        hi, lo = ops._split_weight_pair(w1, w2, transpose=False)
+        want = g1.double() @ w1.double().t() + g2.double() @ w2.double().t()
+        close(ops.linear_tc2(g1, g2, hi, lo, K1), want.float(), rtol=1e-5, atol_scale=1e-5, msg="tc2 dX")
+
+
 # ------------------------------------------------------------------ SURVEY 8(f) next-1 / next-2
 def test_golden_pooling():
     from keras_geometric_b200.layers import BatchGlobalPooling, GlobalPooling
