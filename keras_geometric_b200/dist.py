@@ -108,9 +108,10 @@ class PartitionedGraph:
         self.n_local, self.n_halo, self.n_ext = p.n_local, p.n_halo, p.n_local + p.n_halo
         self.group, self.world, self.rank = group, world, rank
         self.n_global = int(n_global)
-        ei = p.edge_index_local()
-        # self-loops i->i are local edges on the owned rows (ids [0, n_local) in both spaces)
-        self.graph = GraphStructure(ei, self.n_local, self.n_ext, self.n_local if n_loops_local else 0)
+        self.device = src_global.device
+        self._n_loops = self.n_local if n_loops_local else 0
+        self._graph = None
+        self._split = None
         # deterministic backward of the pack: CSR of send_idx (which packed rows came from local row r)
         if p.n_send:
             s_ei = torch.stack([torch.zeros_like(p.send_idx), p.send_idx]).contiguous()
@@ -118,6 +119,33 @@ class PartitionedGraph:
         else:
             self.send_csr = None
         self._dis_ext = None
+
+    @property
+    def graph(self):
+        """All in-edges of the owned rows over the [local | halo] source space (built on first use)."""
+        if self._graph is None:
+            from .graph import GraphStructure
+            # self-loops i->i are local edges on the owned rows (ids [0, n_local) in both spaces)
+            self._graph = GraphStructure(self.plan.edge_index_local(), self.n_local, self.n_ext, self._n_loops)
+        return self._graph
+
+    @property
+    def split(self):
+        """(graph_local, graph_halo, inv_deg): the same edges as two structures - sources this rank owns
+        ([0, n_local)) and halo sources ([0, n_halo), rows of the exchanged buffer) - so that a linear aggregator
+        can reduce the local part while the halo rows are still in flight.  inv_deg = 1 / max(total in-degree, 1e-8)."""
+        if self._split is None:
+            from .graph import GraphStructure
+            ei = self.plan.edge_index_local()
+            is_halo = ei[0] >= self.n_local
+            ei_l = ei[:, ~is_halo].contiguous()
+            ei_h = ei[:, is_halo].clone()
+            ei_h[0] -= self.n_local
+            g_l = GraphStructure(ei_l, self.n_local, self.n_local, 0)
+            g_h = GraphStructure(ei_h.contiguous(), self.n_local, max(self.n_halo, 1), 0)
+            deg = (g_l.csr.deg + g_h.csr.deg).to(torch.float32)
+            self._split = (g_l, g_h, 1.0 / torch.clamp(deg, min=1e-8))
+        return self._split
 
     # ---- forward/backward exchange ------------------------------------------------------------
     # The exchange (pack kernel, all-to-all, and in the backward the reverse all-to-all + segmented sum) runs on a
@@ -127,14 +155,14 @@ class PartitionedGraph:
     def _comm_stream(self) -> torch.cuda.Stream:
         cs = getattr(self, "_cs", None)
         if cs is None:
-            cs = self._cs = torch.cuda.Stream(device=self.graph.device)
+            cs = self._cs = torch.cuda.Stream(device=self.device)
         return cs
 
     def exchange_start(self, x_local: torch.Tensor) -> torch.Tensor:
         """[n_local, F] -> [n_local + n_halo, F] (autograd-aware), left in flight on the communication stream.
         Call ``exchange_finish`` before the first use of the result on the current stream."""
         self.exchange_finish()
-        cur = torch.cuda.current_stream(self.graph.device)
+        cur = torch.cuda.current_stream(self.device)
         cs = self._comm_stream()
         cs.wait_stream(cur)
         with torch.cuda.stream(cs):
@@ -146,7 +174,7 @@ class PartitionedGraph:
     def exchange_finish(self) -> None:
         x_ext, self._pending = getattr(self, "_pending", None), None
         if x_ext is not None:
-            cur = torch.cuda.current_stream(self.graph.device)
+            cur = torch.cuda.current_stream(self.device)
             cur.wait_stream(self._comm_stream())
             x_ext.record_stream(cur)
 
@@ -154,6 +182,21 @@ class PartitionedGraph:
         x_ext = self.exchange_start(x_local)
         self.exchange_finish()
         return x_ext
+
+    def halo_start(self, x_local: torch.Tensor) -> torch.Tensor:
+        """[n_local, F] -> the [n_halo, F] halo rows only (autograd-aware), in flight on the communication stream;
+        pair with the ``split`` structures and call ``halo_finish`` before the first use on the current stream."""
+        self.exchange_finish()
+        cur = torch.cuda.current_stream(self.device)
+        cs = self._comm_stream()
+        cs.wait_stream(cur)
+        with torch.cuda.stream(cs):
+            halo = _HaloRows.apply(x_local, self)
+        x_local.record_stream(cs)
+        self._pending = halo
+        return halo
+
+    halo_finish = exchange_finish
 
     def exchange_vector(self, v_local: torch.Tensor) -> torch.Tensor:
         """Per-node scalar (e.g. GCN dis) -> [n_ext]; no autograd."""
@@ -208,4 +251,46 @@ class _HaloExchange(torch.autograd.Function):
             if p.n_send:
                 add, _ = ops.gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm)
                 g_local += add
+        return g_local, None
+
+
+class _HaloRows(torch.autograd.Function):
+    """x_local [n_local, F] -> halo [n_halo, F]: pack + all-to-all; backward = reverse all-to-all + the deterministic
+    segmented sum of the returned gradient rows into their owners (zero for rows nobody asked for)."""
+
+    @staticmethod
+    def forward(ctx, x_local, pg: PartitionedGraph):
+        from . import ops
+        ctx.pg = pg
+        p = pg.plan
+        x_local = x_local.contiguous()
+        F = int(x_local.shape[1])
+        halo = torch.empty((max(pg.n_halo, 1), F), dtype=x_local.dtype, device=x_local.device)
+        if pg.n_halo == 0:
+            halo.zero_()
+        if pg.world > 1:
+            send = ops.gather_rows(x_local, p.send_idx) if p.n_send else x_local.new_empty((0, F))
+            dist.all_to_all_single(halo[:pg.n_halo], send, output_split_sizes=p.recv_counts,
+                                   input_split_sizes=p.send_counts, group=pg.group)
+        return halo
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_halo):
+        from . import _lib, ops
+        pg = ctx.pg
+        p = pg.plan
+        g_halo = g_halo.contiguous()
+        g_halo.record_stream(torch.cuda.current_stream(g_halo.device))  # produced on the compute stream
+        F = int(g_halo.shape[1])
+        if pg.world > 1 and p.n_send:
+            back = torch.empty((p.n_send, F), dtype=g_halo.dtype, device=g_halo.device)
+            dist.all_to_all_single(back, g_halo[:pg.n_halo], output_split_sizes=p.send_counts,
+                                   input_split_sizes=p.recv_counts, group=pg.group)
+            g_local, _ = ops.gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm)
+        else:
+            if pg.world > 1:
+                dist.all_to_all_single(g_halo.new_empty((0, F)), g_halo[:pg.n_halo], output_split_sizes=p.send_counts,
+                                       input_split_sizes=p.recv_counts, group=pg.group)
+            g_local = torch.zeros((pg.n_local, F), dtype=g_halo.dtype, device=g_halo.device)
         return g_local, None

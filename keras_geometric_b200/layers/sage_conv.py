@@ -227,7 +227,36 @@ class SAGEConv(MessagePassing):
         act_is_relu = self._activation_id == "relu"
         act_is_none = self._activation_id in (None, "linear")
         linear_agg = self.actual_aggregator in ("mean", "sum")
-        if linear_agg and self.output_dim < int(x.shape[1]) and (act_is_relu or act_is_none):
+        fuse_act = act_is_relu or act_is_none
+        if linear_agg and pg.world > 1 and pg.n_halo > 0 and int(x.shape[0]) > 0:
+            # local-source edges are reduced while the halo rows are in flight; the halo part is added on top
+            g_local, g_halo, inv_deg = pg.split
+            scale = (None, inv_deg) if self.actual_aggregator == "mean" else None
+            act = "relu" if act_is_relu else None
+            if self.output_dim < int(x.shape[1]) and fuse_act:   # aggregate after lin_neigh (narrower rows travel)
+                fout = int(w_neigh.shape[1])
+                pad = (-fout) % 4
+                if pad:
+                    w_neigh = torch.nn.functional.pad(w_neigh, (0, pad))
+                    w_self = torch.nn.functional.pad(w_self, (0, pad)) if w_self is not None else None
+                    bias = torch.nn.functional.pad(bias, (0, pad)) if bias is not None else None
+                z = ops.linear(x, w_neigh)
+                halo = pg.halo_start(z)
+                root = ops.linear(x, w_self) if w_self is not None else None
+                part = ops.gather_reduce(z, g_local, "sum", weight=scale, addend=root)
+                pg.halo_finish()
+                out = ops.gather_reduce(halo, g_halo, "sum", weight=scale, addend=part, bias=bias, act=act)
+                out = out[:, :fout] if pad else out
+            else:
+                halo = pg.halo_start(x)
+                root = ops.linear(x, w_self) if w_self is not None else None
+                part = ops.gather_reduce(x, g_local, "sum", weight=scale)
+                pg.halo_finish()
+                aggregated = ops.gather_reduce(halo, g_halo, "sum", weight=scale, addend=part)
+                out = ops.linear(aggregated, w_neigh, addend=root, bias=bias, act=act if fuse_act else None)
+                if self.activation is not None and not fuse_act:
+                    out = self.activation(out)
+        elif linear_agg and self.output_dim < int(x.shape[1]) and fuse_act:
             out = self._aggregate_after_transform(x, pg.graph, w_neigh, w_self, bias, act_is_relu,
                                                    exchange=(pg.exchange_start, pg.exchange_finish))
         else:

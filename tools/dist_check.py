@@ -20,6 +20,8 @@ eid = torch.from_numpy(ei).cuda()
 ok = True
 for name, mk, loops in [("sage_mean_reorder", lambda: SAGEConv(12, aggregator="mean"), False),
                         ("sage_mean_wide", lambda: SAGEConv(64, aggregator="mean"), False),
+                        ("sage_sum_wide", lambda: SAGEConv(64, aggregator="sum", activation="relu"), False),
+                        ("sage_sum_reorder", lambda: SAGEConv(12, aggregator="sum", activation="relu"), False),
                         ("sage_max", lambda: SAGEConv(64, aggregator="max"), False),
                         ("gcn", lambda: GCNConv(12), True)]:
     torch.manual_seed(7)
