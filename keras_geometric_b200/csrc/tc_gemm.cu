@@ -15,6 +15,8 @@
 // W stays in L2.  SASS: UTCHMMA-class UTCMMA (tf32), UTMALDG, LDTM.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace kgb {
@@ -103,6 +105,72 @@ struct TcParams {
   int kblocks;  // k-blocks in total
   int kb1;      // k-blocks read through map_a; the rest comes from map_a2 (second A operand, K-concatenated)
 };
+
+// TMEM -> registers: 32 consecutive fp32 columns of this thread's accumulator row (asynchronous until tcgen05.wait::ld)
+#define KGB_TMEM_LD32(r, addr)                                                                                       \
+  asm volatile(                                                                                                      \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                      \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                      \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                      \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),      \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),     \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                   \
+      : "r"(addr))
+
+// Epilogue of one 128 x BN accumulator, one 32-column chunk at a time: TMEM -> registers -> padded shared tile
+// (transpose) -> (+C, +bias, ReLU) -> global.  Each thread holds 32 consecutive columns of ITS row; storing that
+// directly would touch 32 different rows per instruction, so the chunk goes through a padded shared tile and every
+// global access covers whole 128-byte row segments (4 rows x 128 B per warp instruction).
+// (Software-pipelining the TMEM reads over two register sets was measured slower: 168 registers, 0.70 -> 0.83 ms.)
+template <int BN, int EPI_LD>
+__device__ __forceinline__ void tc_epilogue_tile(uint32_t taddr, float* stg, int lane, int64_t tile_row0, int M, int N,
+                                                 const float* C, int64_t ldc, const float* bias, int relu, float* D,
+                                                 int64_t ldd) {
+  const int cv = (lane & 7) * 4;        // column (within the chunk) of this lane's float4
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    if (c0 >= N) break;
+    const bool col_ok = (c0 + cv) < N;  // N is a multiple of 4
+    // addend rows of this chunk: issued before the TMEM read so their DRAM latency hides behind it (loading them
+    // next to the store would serialise 8 dependent round trips per chunk: D may alias C as far as the compiler knows)
+    float4 cc[8];
+    if (C) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int64_t grow = tile_row0 + it * 4 + (lane >> 3);
+        cc[it] = (grow < M && col_ok) ? ld_stream4(C + grow * ldc + c0 + cv) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    uint32_t r[32];
+    KGB_TMEM_LD32(r, taddr + c0);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int v = 0; v < 8; ++v)
+      *reinterpret_cast<float4*>(stg + lane * EPI_LD + v * 4) =
+          make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                      __uint_as_float(r[4 * v + 3]));
+    __syncwarp();
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias && col_ok) bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + cv));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      const int64_t grow = tile_row0 + rr;
+      float4 o = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + cv);
+      if (grow < M && col_ok) {
+        if (C) { o.x += cc[it].x; o.y += cc[it].y; o.z += cc[it].z; o.w += cc[it].w; }
+        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+        if (relu) {
+          o.x = o.x <= 0.f ? 0.f : o.x; o.y = o.y <= 0.f ? 0.f : o.y;
+          o.z = o.z <= 0.f ? 0.f : o.z; o.w = o.w <= 0.f ? 0.f : o.w;
+        }
+        *reinterpret_cast<float4*>(D + grow * ldd + c0 + cv) = o;
+      }
+    }
+    __syncwarp();  // the staging tile is reused by the next column chunk
+  }
+}
 
 template <int BN>
 struct TcCfg {
@@ -249,61 +317,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const int64_t tile_row0 = (int64_t)tile * TC_BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (c0 >= p.N) break;
-        // addend rows of this chunk: issued before the TMEM read so their DRAM latency hides behind it (loading them
-        // next to the store would serialise 8 dependent round trips per chunk: D may alias C as far as the compiler knows)
-        const int cv = (lane & 7) * 4;        // column (within the chunk) of this lane's float4
-        const bool col_ok = (c0 + cv) < p.N;  // N is a multiple of 4
-        float4 cc[8];
-        if (p.C) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int64_t grow = (int64_t)tile_row0 + it * 4 + (lane >> 3);
-            cc[it] = (grow < p.M && col_ok) ? ld_stream4(p.C + grow * p.ldc + c0 + cv) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        uint32_t r[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr + c0));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // Each thread holds 32 consecutive columns of ITS row; storing that directly would touch 32 different rows
-        // per instruction.  Transpose through a padded shared tile so every global access covers whole 128-byte
-        // row segments (4 rows x 128 B per warp instruction).
-        float* stg = epi_stage + q * 32 * Cfg::EPI_LD;
-#pragma unroll
-        for (int v = 0; v < 8; ++v)
-          *reinterpret_cast<float4*>(stg + lane * Cfg::EPI_LD + v * 4) =
-              make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
-                          __uint_as_float(r[4 * v + 3]));
-        __syncwarp();
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok) bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + cv));
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + (lane >> 3);
-          const int64_t grow = (int64_t)tile_row0 + rr;
-          float4 o = *reinterpret_cast<const float4*>(stg + rr * Cfg::EPI_LD + cv);
-          if (grow < p.M && col_ok) {
-            if (p.C) { o.x += cc[it].x; o.y += cc[it].y; o.z += cc[it].z; o.w += cc[it].w; }
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            if (p.relu) {
-              o.x = o.x <= 0.f ? 0.f : o.x; o.y = o.y <= 0.f ? 0.f : o.y;
-              o.z = o.z <= 0.f ? 0.f : o.z; o.w = o.w <= 0.f ? 0.f : o.w;
-            }
-            *reinterpret_cast<float4*>(p.D + grow * p.ldd + c0 + cv) = o;
-          }
-        }
-        __syncwarp();  // the tile is reused by the next column chunk
-      }
+      tc_epilogue_tile<BN, Cfg::EPI_LD>(taddr, epi_stage + q * 32 * Cfg::EPI_LD, lane, tile_row0, p.M, p.N, p.C, p.ldc,
+                                        p.bias, p.relu, p.D, p.ldd);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + b);
@@ -314,6 +329,207 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// CTA-pair variant of the kernel above (tcgen05 cta_group::2): a cluster of two CTAs on one TPC owns a 256-row tile
+// pair.  Each CTA stages ITS 128 rows of A (and splits them) plus ITS half of the weight rows; one thread of the
+// leader CTA issues M=256 MMAs that read both CTAs' shared memory, each CTA's TMEM receives its 128 rows.  The weight
+// tile is therefore fetched from L2 once per 256 rows instead of once per 128 (the 1-CTA kernel moves 5x more weight
+// bytes than A bytes through the L2->SM path and is bound by it), and a stage shrinks to 64 KB (3 stages instead of 2).
+//   full[s]   (local)   this CTA's TMA bytes landed                       -> its transform warps
+//   ready[s]  (leader)  8 arrivals: 4 transform warps x 2 CTAs            -> MMA issuer
+//   empty[s]  (local)   multicast tcgen05.commit: stage consumed          -> this CTA's TMA producer
+//   tfull[b]  (local)   multicast tcgen05.commit: accumulator complete    -> this CTA's epilogue warps
+//   tempty[b] (leader)  8 arrivals: 4 epilogue warps x 2 CTAs             -> MMA issuer
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint64_t* bar) {  // arrives on the same barrier offset in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+template <int BN>
+struct Tc2Cfg {
+  static constexpr int STAGES = BN == 256 ? 3 : 4;
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;         // this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * TC_BK * 4;      // this CTA's half of the weight rows
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int EPI_LD = 36;
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                const TcParams p) {
+  using Cfg = Tc2Cfg<BN>;
+  constexpr int S = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* epi_stage = reinterpret_cast<float*>(smem + S * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+  uint64_t* full = bars;
+  uint64_t* ready = bars + S;
+  uint64_t* empty = bars + 2 * S;
+  uint64_t* tfull = bars + 3 * S;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int kblocks = p.kblocks;
+  const int n_pairs = (p.n_tiles + 1) / 2;
+  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(ready + s, 8);
+      mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b, 1);
+      mbar_init(tempty + b, 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                 "r"(2 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  auto sA = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
+  auto sAlo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+  auto sBhi = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES; };
+  auto sBlo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES + Cfg::B_BYTES; };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int pair = pair0; pair < n_pairs; pair += pair_stride) {
+        const int tile = pair * 2 + (int)rank;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_expect_tx(full + s, Cfg::A_BYTES + 2 * Cfg::B_BYTES);
+          if (kb < p.kb1) tma_load_2d(sA(s), &map_a, full + s, kb * TC_BK, tile * TC_BM);
+          else tma_load_2d(sA(s), &map_a2, full + s, (kb - p.kb1) * TC_BK, tile * TC_BM);
+          tma_load_2d(sBhi(s), &map_bhi, full + s, kb * TC_BK, (int)rank * (BN / 2));
+          tma_load_2d(sBlo(s), &map_blo, full + s, kb * TC_BK, (int)rank * (BN / 2));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // D fp32, A/B tf32, K-major, N = BN (both halves), M = 256 (128 rows per CTA)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      uint32_t it = 0;
+      int j = 0;
+      for (int pair = pair0; pair < n_pairs; pair += pair_stride, ++j) {
+        const int b = j & 1;
+        mbar_wait(tempty + b, ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + b * BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(ready + s, ph);
+          tc_fence_after();
+          const uint64_t da_hi = make_desc(smem_u32(sA(s))), da_lo = make_desc(smem_u32(sAlo(s)));
+          const uint64_t db_hi = make_desc(smem_u32(sBhi(s))), db_lo = make_desc(smem_u32(sBlo(s)));
+#pragma unroll
+          for (int k4 = 0; k4 < TC_BK / 8; ++k4) {
+            const uint64_t adv = (uint64_t)(k4 * 2);
+            umma2_tf32(tmem_c, da_lo + adv, db_hi + adv, idesc, (kb | k4) != 0);
+            umma2_tf32(tmem_c, da_hi + adv, db_lo + adv, idesc, 1);
+            umma2_tf32(tmem_c, da_hi + adv, db_hi + adv, idesc, 1);
+          }
+          umma_commit2(empty + s);
+        }
+        umma_commit2(tfull + b);
+      }
+    }
+  } else if (warp < 6) {
+    const int t = threadIdx.x - 64;
+    uint32_t it = 0;
+    for (int pair = pair0; pair < n_pairs; pair += pair_stride) {
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(full + s, ph);
+        float4* src = reinterpret_cast<float4*>(sA(s));
+        float4* dst = reinterpret_cast<float4*>(sAlo(s));
+#pragma unroll
+        for (int i = 0; i < Cfg::A_BYTES / 16 / 128; ++i) {
+          const float4 v = src[t + i * 128];
+          float4 h, r;
+          split_tf32(v.x, h.x, r.x);
+          split_tf32(v.y, h.y, r.y);
+          split_tf32(v.z, h.z, r.z);
+          split_tf32(v.w, h.w, r.w);
+          src[t + i * 128] = h;
+          dst[t + i * 128] = r;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ready + s, 0);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int j = 0;
+    for (int pair = pair0; pair < n_pairs; pair += pair_stride, ++j) {
+      const int b = j & 1;
+      mbar_wait(tfull + b, (j >> 1) & 1);
+      tc_fence_after();
+      const int64_t tile_row0 = (int64_t)(pair * 2 + (int)rank) * TC_BM + q * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN;
+      tc_epilogue_tile<BN, Cfg::EPI_LD>(taddr, epi_stage + q * 32 * Cfg::EPI_LD, lane, tile_row0, p.M, p.N, p.C, p.ldc,
+                                        p.bias, p.relu, p.D, p.ldd);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty + b, 0);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer can still signal it or read its shared memory
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
   }
 }
 
@@ -608,6 +824,30 @@ static int tc_launch(int device, const CUtensorMap& ma, const CUtensorMap& ma2, 
 }
 
 
+template <int BN>
+static int tc2_launch(int device, const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mh,
+                      const CUtensorMap& ml, const TcParams& p, cudaStream_t st) {
+  using Cfg = Tc2Cfg<BN>;
+  static int clusters[64] = {};
+  if (device < 64 && clusters[device] == 0) {
+    KGB_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sm_count(device) / 2 * 2);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    int n = 0;
+    KGB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, tc_gemm2_kernel<BN>, &cfg));  // co-resident CTA pairs
+    clusters[device] = n > 0 ? n : -1;
+  }
+  const int resident = device < 64 ? clusters[device] : sm_count(device) / 2;
+  if (resident <= 0) return KGB_ERR_UNSUPPORTED;
+  int pairs = (p.n_tiles + 1) / 2;
+  if (pairs > resident) pairs = resident;
+  tc_gemm2_kernel<BN><<<2 * pairs, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, ma2, mh, ml, p);
+  KGB_CHECK_LAUNCH();
+  return KGB_OK;
+}
+
 template <int BN, int MT>
 static int dw_launch(int device, const CUtensorMap& mx, const CUtensorMap& mg, const DwParams& p, int grid,
                      cudaStream_t st) {
@@ -710,9 +950,13 @@ int kgb_linear_tc2(int device, const float* A1, int64_t lda1, int32_t K1, const 
   } else {
     ma2 = ma;
   }
-  rc = make_map(&mh, wt_hi, BN, Kcat, Kcat, BN);  // zero-padded to BN rows (kgb_linear_tc_rows)
+  // CTA pairs (cta_group::2) once there are enough 256-row tile pairs to fill the machine twice over
+  static const int pair_env = [] { const char* e = getenv("KGB_TC_PAIR"); return e ? atoi(e) : 1; }();
+  // (only the 256-wide tile gains: 1.63 -> 1.58 ms at 2.45 M x 256 x 256; narrower tiles are slower paired)
+  const bool use_pair = pair_env != 0 && BN == 256 && M >= 4 * TC_BM * sm_count(device);
+  rc = make_map(&mh, wt_hi, BN, Kcat, Kcat, use_pair ? BN / 2 : BN);  // zero-padded to BN rows (kgb_linear_tc_rows)
   if (rc != KGB_OK) return rc;
-  rc = make_map(&ml, wt_lo, BN, Kcat, Kcat, BN);
+  rc = make_map(&ml, wt_lo, BN, Kcat, Kcat, use_pair ? BN / 2 : BN);
   if (rc != KGB_OK) return rc;
   TcParams p;
   p.M = M; p.N = N; p.K = Kcat; p.C = C; p.ldc = ldc; p.bias = bias; p.relu = (act == KGB_ACT_RELU);
@@ -720,6 +964,7 @@ int kgb_linear_tc2(int device, const float* A1, int64_t lda1, int32_t K1, const 
   p.kb1 = kb1;
   p.kblocks = kb1 + (K2 + TC_BK - 1) / TC_BK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_pair) return tc2_launch<256>(device, ma, ma2, mh, ml, p, st);
   if (BN == 64) return tc_launch<64>(device, ma, ma2, mh, ml, p, st);
   if (BN == 128) return tc_launch<128>(device, ma, ma2, mh, ml, p, st);
   return tc_launch<256>(device, ma, ma2, mh, ml, p, st);

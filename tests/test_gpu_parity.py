@@ -557,7 +557,8 @@ def test_full_size_properties_products_slice():
 
 # ---------------------------------------------------------------------------------------- K8
 @pytest.mark.parametrize("M,K,N", [(1, 4, 4), (300, 100, 256), (5000, 256, 48), (20001, 48, 256), (70000, 64, 64),
-                                   (513, 12, 7), (1000, 1433, 16), (128, 32, 64), (40000, 260, 132), (9999, 512, 300)])
+                                   (513, 12, 7), (1000, 1433, 16), (128, 32, 64), (40000, 260, 132), (9999, 512, 300),
+                                   (90001, 256, 256), (80000, 100, 200)])   # the last two take the CTA-pair kernel
 def test_linear_tensor_core_gemm(M, K, N):
     """X @ W (+ addend) and its two gradient GEMMs vs float64; shapes with a dimension not divisible by 4 take the
     library fallback on the GPU and must agree as well."""
@@ -578,7 +579,7 @@ def test_linear_tensor_core_gemm(M, K, N):
 
 
 @pytest.mark.parametrize("M,K1,K2,N", [(128, 4, 4, 4), (1000, 100, 100, 256), (4097, 256, 256, 256), (3000, 48, 48, 256),
-                                       (2000, 32, 64, 64), (777, 36, 8, 132)])
+                                       (2000, 32, 64, 64), (777, 36, 8, 132), (77001, 100, 100, 256)])
 def test_linear_two_operands_one_pass(M, K1, K2, N):
     """[A1 | A2] @ [W1 ; W2] + bias (ReLU) through kgb_linear_tc2 (K-concatenated operands) vs float64."""
     from keras_geometric_b200 import ops
