@@ -55,6 +55,10 @@ def test_sass_has_vector_loads():
     sass = subprocess.run([cuobjdump, "-sass", _build.build()], capture_output=True, text=True).stdout
     assert "code for sm_100a" in sass
     assert sass.count("LDG.E.128") > 100  # float4 feature-row loads in the gather kernels
+    # the dense transforms run on the 5th-generation tensor cores: tcgen05 MMAs (also the CTA-pair form),
+    # TMA tile loads, TMEM reads, multicast commits
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG.2D", "LDTM", "UTCBAR.2CTA.MULTICAST"):
+        assert mnemonic in sass, mnemonic
 
 
 def test_no_cpu_fallback():
