@@ -198,6 +198,28 @@ class PartitionedGraph:
 
     halo_finish = exchange_finish
 
+    # ---- raw (no autograd) halves of the exchange, for nodes that schedule the overlap themselves ----
+    def halo_rows_raw(self, x_local: torch.Tensor) -> torch.Tensor:
+        """pack + all-to-all on the CURRENT stream: [n_local, F] -> [n_halo, F]."""
+        from . import ops
+        p = self.plan
+        F = int(x_local.shape[1])
+        halo = torch.empty((max(self.n_halo, 1), F), dtype=x_local.dtype, device=x_local.device)
+        send = ops.gather_rows(x_local, p.send_idx) if p.n_send else x_local.new_empty((0, F))
+        dist.all_to_all_single(halo[:self.n_halo], send, output_split_sizes=p.recv_counts,
+                               input_split_sizes=p.send_counts, group=self.group)
+        return halo
+
+    def halo_grad_raw(self, g_halo: torch.Tensor) -> torch.Tensor:
+        """reverse all-to-all on the CURRENT stream: [n_halo, F] gradient rows -> [n_send, F] rows at their owners
+        (to be summed per owner row with ``send_csr``)."""
+        p = self.plan
+        F = int(g_halo.shape[1])
+        back = torch.empty((max(p.n_send, 1), F), dtype=g_halo.dtype, device=g_halo.device)
+        dist.all_to_all_single(back[:p.n_send], g_halo[:self.n_halo], output_split_sizes=p.send_counts,
+                               input_split_sizes=p.recv_counts, group=self.group)
+        return back
+
     def exchange_vector(self, v_local: torch.Tensor) -> torch.Tensor:
         """Per-node scalar (e.g. GCN dis) -> [n_ext]; no autograd."""
         return _exchange_fwd(v_local.reshape(-1, 1).contiguous(), self).reshape(-1)

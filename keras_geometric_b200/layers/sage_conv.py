@@ -233,13 +233,18 @@ class SAGEConv(MessagePassing):
             g_local, g_halo, inv_deg = pg.split
             scale = (None, inv_deg) if self.actual_aggregator == "mean" else None
             act = "relu" if act_is_relu else None
-            if self.output_dim < int(x.shape[1]) and fuse_act:   # aggregate after lin_neigh (narrower rows travel)
-                fout = int(w_neigh.shape[1])
-                pad = (-fout) % 4
-                if pad:
-                    w_neigh = torch.nn.functional.pad(w_neigh, (0, pad))
-                    w_self = torch.nn.functional.pad(w_self, (0, pad)) if w_self is not None else None
-                    bias = torch.nn.functional.pad(bias, (0, pad)) if bias is not None else None
+            reorder = self.output_dim < int(x.shape[1]) and fuse_act
+            fout = int(w_neigh.shape[1])
+            pad = ((-fout) % 4) if reorder else 0
+            if pad:
+                w_neigh = torch.nn.functional.pad(w_neigh, (0, pad))
+                w_self = torch.nn.functional.pad(w_self, (0, pad)) if w_self is not None else None
+                bias = torch.nn.functional.pad(bias, (0, pad)) if bias is not None else None
+            if fuse_act and w_self is not None and ops.sage_layer_ok(x, w_neigh, w_self):
+                # one autograd node that schedules the exchange / compute overlap itself (both directions)
+                out = ops.sage_partitioned(x, w_neigh, w_self, bias, pg, self.actual_aggregator, act_is_relu, reorder)
+                out = out[:, :fout] if pad else out
+            elif reorder:   # aggregate after lin_neigh (narrower rows travel)
                 z = ops.linear(x, w_neigh)
                 halo = pg.halo_start(z)
                 root = ops.linear(x, w_self) if w_self is not None else None

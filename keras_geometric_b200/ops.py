@@ -754,3 +754,126 @@ def linear_pair(x, w_a, w_b):
     if sage_layer_ok(x, w_a, w_b):
         return _LinearPair.apply(x, w_a, w_b)
     return linear(x, w_a), linear(x, w_b)
+
+
+class _SagePartitioned(torch.autograd.Function):
+    """SAGEConv (mean / sum) on a 1-D node partition as ONE autograd node that schedules its own overlap.
+
+    forward:  halo rows travel on the communication stream while the local-source edges are reduced (and, with
+              ``reorder``, the root transform runs); the halo part is added on top and the two GEMMs run as one.
+    backward: the gradient of the halo rows is produced FIRST and sent back; the weight-gradient GEMMs, the
+              local-source transposed gather and the root dX GEMM run while it travels; the returned rows are summed
+              into their owners by the deterministic segmented sum, accumulating onto the local result.
+    ``reorder``: aggregate after lin_neigh (narrower rows travel): out = act(A (x Wn) + x Ws + b)."""
+
+    @staticmethod
+    def forward(ctx, x, w_neigh, w_self, bias, pg, op_name: str, relu: bool, reorder: bool):
+        x = _f32c(x, "x")
+        w_neigh, w_self = _f32c(w_neigh, "w_neigh"), _f32c(w_self, "w_self")
+        bias_c = _f32c(bias, "bias").contiguous() if bias is not None else None
+        g_l, g_h, inv = pg.split
+        scale = inv if op_name == "mean" else None
+        N = int(w_neigh.shape[1])
+        dev = x.device
+        cur, cs = torch.cuda.current_stream(dev), pg._comm_stream()
+        act = _lib.ACT_RELU if relu else _lib.ACT_NONE
+        if reorder:
+            hi, lo = _split_weight(w_neigh, transpose=True)
+            z = linear_tc(x, hi, lo, N)
+            cs.wait_stream(cur)
+            with torch.cuda.stream(cs):
+                halo = pg.halo_rows_raw(z)
+            z.record_stream(cs)
+            hi, lo = _split_weight(w_self, transpose=True)
+            root = linear_tc(x, hi, lo, N)
+            part, _ = gather_reduce_raw(z, g_l.csr, _lib.OP_SUM, out_scale=scale, addend=root)
+            cur.wait_stream(cs)
+            halo.record_stream(cur)
+            out, _ = gather_reduce_raw(halo, g_h.csr, _lib.OP_SUM, out_scale=scale, addend=part, bias=bias_c, act=act)
+            ctx.save_for_backward(x, w_neigh, w_self, *([out] if relu else []))
+        else:
+            cs.wait_stream(cur)
+            with torch.cuda.stream(cs):
+                halo = pg.halo_rows_raw(x)
+            x.record_stream(cs)
+            part, _ = gather_reduce_raw(x, g_l.csr, _lib.OP_SUM, out_scale=scale)
+            cur.wait_stream(cs)
+            halo.record_stream(cur)
+            agg, _ = gather_reduce_raw(halo, g_h.csr, _lib.OP_SUM, out_scale=scale, addend=part)
+            hi, lo = _split_weight_pair(w_neigh, w_self, transpose=True)
+            out = linear_tc2(agg, x, hi, lo, N, bias=bias_c, relu=relu)
+            ctx.save_for_backward(x, w_neigh, w_self, agg, *([out] if relu else []))
+        ctx.pg, ctx.scale, ctx.relu, ctx.reorder, ctx.has_bias = pg, scale, relu, reorder, bias is not None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        pg, scale = ctx.pg, ctx.scale
+        g_l, g_h, _ = pg.split
+        saved = ctx.saved_tensors
+        x, w_neigh, w_self = saved[:3]
+        out = saved[-1] if ctx.relu else None
+        g = _f32c(g, "grad")
+        g_bias = None
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            g, g_bias = relu_bwd_colsum(g, out)
+        elif ctx.relu:
+            g = relu_bwd(g, out)
+        if g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
+            g = g.contiguous()
+        dev = x.device
+        cur, cs = torch.cuda.current_stream(dev), pg._comm_stream()
+        K = int(x.shape[1])
+        need_x = ctx.needs_input_grad[0]
+        send_csr = pg.send_csr
+
+        def send_back(rows):   # gradient of the halo rows -> their owners, on the communication stream
+            cs.wait_stream(cur)
+            with torch.cuda.stream(cs):
+                back = pg.halo_grad_raw(rows)
+            rows.record_stream(cs)
+            return back
+
+        def land(back, acc):   # + per-owner segmented sum of the returned rows
+            cur.wait_stream(cs)
+            back.record_stream(cur)
+            if send_csr is None:
+                return acc
+            res, _ = gather_reduce_raw(back, send_csr, _lib.OP_SUM, col=send_csr.perm, addend=acc)
+            return res
+
+        if ctx.reorder:
+            # out = act(S A_l z + S A_h halo(z) + x Ws + b), z = x Wn:  dz = A^T (S g) needs the exchange even when x
+            # itself needs no gradient (it feeds dWn)
+            g_halo, _ = gather_reduce_raw(g, g_h.csc, _lib.OP_SUM, src_scale=scale)
+            back = send_back(g_halo)
+            g_ws = _dw_tc(x, g) if ctx.needs_input_grad[2] else None
+            dz, _ = gather_reduce_raw(g, g_l.csc, _lib.OP_SUM, src_scale=scale)
+            dz = land(back, dz)
+            g_wn = _dw_tc(x, dz) if ctx.needs_input_grad[1] else None
+            gx = None
+            if need_x:
+                hi, lo = _split_weight_pair(w_neigh, w_self, transpose=False)
+                gx = linear_tc2(dz, g, hi, lo, K)
+            return gx, g_wn, g_ws, g_bias, None, None, None, None
+        agg = saved[3]
+        gx = None
+        back = None
+        if need_x:
+            hi, lo = _split_weight(w_neigh, transpose=False)
+            d_agg = linear_tc(g, hi, lo, K)
+            g_halo, _ = gather_reduce_raw(d_agg, g_h.csc, _lib.OP_SUM, src_scale=scale)
+            back = send_back(g_halo)
+        g_wn = _dw_tc(agg, g) if ctx.needs_input_grad[1] else None
+        g_ws = _dw_tc(x, g) if ctx.needs_input_grad[2] else None
+        if need_x:
+            gx, _ = gather_reduce_raw(d_agg, g_l.csc, _lib.OP_SUM, src_scale=scale)
+            hi, lo = _split_weight(w_self, transpose=False)
+            gx = linear_tc(g, hi, lo, K, c=gx)
+            gx = land(back, gx)
+        return gx, g_wn, g_ws, g_bias, None, None, None, None
+
+
+def sage_partitioned(x, w_neigh, w_self, bias, pg, op: str, relu: bool, reorder: bool) -> torch.Tensor:
+    return _SagePartitioned.apply(x, w_neigh, w_self, bias, pg, op, relu, reorder)
