@@ -72,10 +72,39 @@ class GATv2Conv(MessagePassing):
             x, edge_index = inputs[0], inputs[1]
         else:
             raise ValueError(f"Expected inputs to be [x, edge_index], got {inputs}")
+        from ..dist import PartitionedGraph
+        if isinstance(edge_index, PartitionedGraph):
+            return self._call_partitioned(x, edge_index, training)
         if not (isinstance(edge_index, torch.Tensor) and edge_index.is_cuda and edge_index.dtype == torch.int32):
             edge_index = self._cast_edge_index(edge_index)
         return self._gatv2_propagate(x=x, edge_index=edge_index, training=training,
                                      n_loops_from_flag=self.add_self_loops_flag)
+
+    def _call_partitioned(self, x, pg, training=None):
+        """Same layer on a 1-D node partition: ``h = x W`` is computed by the owner, the halo rows of ``h`` are
+        exchanged (width H*C) and the fused edge kernel runs on the rank's rows over the [local | halo] sources."""
+        x = to_device_tensor(x, what="x")
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)
+        if bool(pg.graph.n_loops) != bool(self.add_self_loops_flag):
+            raise ValueError("PartitionedGraph(n_loops_local=...) must match GATv2Conv(add_self_loops=...)")
+        if self.dropout_layer is not None and training:
+            raise NotImplementedError("partitioned GATv2Conv does not support attention dropout")
+        if self.linear_transform is None or self.att is None:
+            self.build(tuple(x.shape))
+            self.built = True
+        n, H, C = int(x.shape[0]), self.heads, self.features_per_head
+        h = ops.linear(x, value_of(self.linear_transform.kernel))
+        h_ext = pg.exchange(h)
+        att = value_of(self.att)
+        bias = value_of(self.bias) if (self.use_bias and self.bias is not None) else None
+        fuse_bias = bias is not None and (self.concat or H == 1)
+        out = ops.gatv2_aggregate(h_ext, h, att, pg.graph, H, C, self.negative_slope, bias if fuse_bias else None)
+        if not self.concat and H > 1:
+            out = out.reshape(n, H, C).mean(dim=1)
+            if bias is not None:
+                out = out + bias
+        return out
 
     def propagate(self, x, edge_index, edge_attr=None, size=None, **kwargs):  # gatv2_conv.py:162-174
         return self._gatv2_propagate(x=x, edge_index=edge_index, training=kwargs.get("training", None))

@@ -85,6 +85,9 @@ class GINConv(MessagePassing):
         if x.is_floating_point() and x.dtype != torch.float32:
             x = x.to(torch.float32)
         num_nodes = int(x.shape[0])
+        from ..dist import PartitionedGraph
+        if isinstance(inputs[1], PartitionedGraph):
+            return self._call_partitioned(x, inputs[1], training)
         if num_nodes == 0:
             return torch.zeros((0, self.output_dim), dtype=x.dtype, device=x.device)
         edge_index = inputs[1]
@@ -103,6 +106,34 @@ class GINConv(MessagePassing):
             h = ops.gather_reduce(x, graph, self.aggregator, addend=x, addend_scale=1.0 + float(self.eps_init))
             return self.mlp(h, training=training)
         return self.propagate(x=x, edge_index=edge_index, edge_attr=edge_attr, training=training)
+
+    def _call_partitioned(self, x, pg, training=None):
+        """Same layer on a 1-D node partition: ``x`` is this rank's [n_local, F] slice.  sum / mean reduce the
+        local-source edges while the halo rows are in flight and add the halo part on top; max uses the
+        concatenated [local | halo] source space."""
+        if not self.built:
+            self.build([tuple(x.shape), (2, 0)])
+            self.built = True
+        if self.mlp is None:
+            raise RuntimeError("MLP not initialized. This indicates a build issue.")
+        if not (type(self).message is GINConv.message and type(self).update is GINConv.update
+                and self._uses_default("pre_aggregate", "aggregate", "post_update")):
+            raise NotImplementedError("partitioned GINConv supports the default message/aggregate/update hooks")
+        eps = value_of(self.eps) if self.train_eps else float(self.eps_init)
+        if self.aggregator in ("sum", "mean") and pg.world > 1 and pg.n_halo > 0 and int(x.shape[0]) > 0:
+            g_local, g_halo, inv_deg = pg.split
+            scale = (None, inv_deg) if self.aggregator == "mean" else None
+            halo = pg.halo_start(x)
+            if self.train_eps:
+                part = ops.gather_reduce(x, g_local, "sum", weight=scale) + (1 + eps) * x
+            else:
+                part = ops.gather_reduce(x, g_local, "sum", weight=scale, addend=x, addend_scale=1.0 + eps)
+            pg.halo_finish()
+            h = ops.gather_reduce(halo, g_halo, "sum", weight=scale, addend=part)
+        else:
+            x_ext = pg.exchange(x)
+            h = (1 + eps) * x + ops.gather_reduce(x_ext, pg.graph, self.aggregator)
+        return self.mlp(h, training=training)
 
     def compute_output_shape(self, input_shape):  # gin_conv.py:303-322
         x_shape = input_shape[0] if isinstance(input_shape, list) else (

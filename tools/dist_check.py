@@ -2,7 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
-from keras_geometric_b200 import SAGEConv, GCNConv
+from keras_geometric_b200 import SAGEConv, GCNConv, GINConv, GATv2Conv
 from keras_geometric_b200.dist import PartitionedGraph, partition_bounds
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -23,7 +23,12 @@ for name, mk, loops in [("sage_mean_reorder", lambda: SAGEConv(12, aggregator="m
                         ("sage_sum_wide", lambda: SAGEConv(64, aggregator="sum", activation="relu"), False),
                         ("sage_sum_reorder", lambda: SAGEConv(12, aggregator="sum", activation="relu"), False),
                         ("sage_max", lambda: SAGEConv(64, aggregator="max"), False),
-                        ("gcn", lambda: GCNConv(12), True)]:
+                        ("gcn", lambda: GCNConv(12), True),
+                        ("gin_sum", lambda: GINConv(12, mlp_hidden=[16], aggregator="sum"), False),
+                        ("gin_mean_eps", lambda: GINConv(12, mlp_hidden=[16], aggregator="mean", train_eps=True, eps_init=0.3), False),
+                        ("gin_max", lambda: GINConv(64, aggregator="max"), False),
+                        ("gatv2_concat", lambda: GATv2Conv(16, heads=4), True),
+                        ("gatv2_head_mean", lambda: GATv2Conv(12, heads=2, concat=False), True)]:
     torch.manual_seed(7)
     layer = mk()
     xf = torch.from_numpy(x).cuda().requires_grad_(True)
