@@ -58,12 +58,6 @@ def rmat_edge_index(n_nodes: int, n_edges: int, scale: int, seed: int, device) -
     return ei
 
 
-def gather_bytes(nnz: int, n_rows: int, F: int, extra_edge: int = 0, extra_row: int = 0) -> int:
-    """Algorithmic bytes of one gather-reduce launch (SURVEY 8(d) / DESIGN.md):
-    nnz*(4F + 4 col [+4 per-edge weight or scale]) + n_rows*4F written + (n_rows+1)*8 rowptr."""
-    return nnz * (4 * F + 4 + extra_edge) + n_rows * (4 * F + extra_row) + (n_rows + 1) * 8
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 

@@ -166,7 +166,6 @@ class GraphStructure:
         self.csr = build_csr(edge_index, self.n_dst, self.n_src, self.n_loops, by_source=False)
         self._csc = None
         self._gcn = None
-        self._dst_sorted = None
 
     @property
     def csc(self) -> Csr:
