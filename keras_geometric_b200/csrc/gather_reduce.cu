@@ -451,26 +451,43 @@ __global__ void __launch_bounds__(256) hub_finish_kernel(const GRP p) {
     const int64_t row = __ldg(p.hub_row + h);
     const int64_t base = __ldg(p.hub_chunk_base + h);
     const int nch = __ldg(p.hub_nchunks + h);
-    for (int c = 0; c < nch; ++c) {
+    // chunk partials are merged in chunk order (fixed summation order); HU of them are loaded ahead of the adds
+    // so the merge of a 500-chunk hub is not one dependent round trip per chunk
+    constexpr int HU = (NCH >= 4 || IS_MAX) ? 2 : 4;
+    for (int c0 = 0; c0 < nch; c0 += HU) {
+      float v[HU][NCH][VEC];
+      int32_t pa[HU][NCH][VEC];
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        if (!on[ch]) continue;
-        const int f0 = (gl + ch * G) * VEC;
-        float v[VEC];
-        ld_vec<VEC>(p.partial + (base + c) * (int64_t)p.F + f0, v);
-        if constexpr (IS_MAX) {
-          int32_t pa[VEC];
-          ld_vec_i<VEC>(p.partial_arg + (base + c) * (int64_t)p.F + f0, pa);
+      for (int u = 0; u < HU; ++u) {
+        const int64_t c = (c0 + u < nch) ? (c0 + u) : (nch - 1);   // clamped (re-read, not re-added)
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            float& m = acc[ch][e];
-            if (v[e] != v[e]) m = v[e];
-            else if (v[e] > m) { m = v[e]; aidx[ch][e] = pa[e]; }
-            else if (v[e] == m && pa[e] != -1 && pa[e] != aidx[ch][e]) aidx[ch][e] = -2;
+        for (int ch = 0; ch < NCH; ++ch) {
+          if (!on[ch]) continue;
+          const int f0 = (gl + ch * G) * VEC;
+          ld_vec<VEC>(p.partial + (base + c) * (int64_t)p.F + f0, v[u][ch]);
+          if constexpr (IS_MAX) ld_vec_i<VEC>(p.partial_arg + (base + c) * (int64_t)p.F + f0, pa[u][ch]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < HU; ++u) {
+        if (c0 + u >= nch) break;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          if (!on[ch]) continue;
+          if constexpr (IS_MAX) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+              float& m = acc[ch][e];
+              const float ve = v[u][ch][e];
+              const int32_t pe = pa[u][ch][e];
+              if (ve != ve) m = ve;
+              else if (ve > m) { m = ve; aidx[ch][e] = pe; }
+              else if (ve == m && pe != -1 && pe != aidx[ch][e]) aidx[ch][e] = -2;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[ch][e] = __fadd_rn(acc[ch][e], v[u][ch][e]);
           }
-        } else {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) acc[ch][e] = __fadd_rn(acc[ch][e], v[e]);
         }
       }
     }

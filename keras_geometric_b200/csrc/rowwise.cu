@@ -59,8 +59,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// PER = ceil(C / 32) logits per lane kept in registers (C <= 32 * PER)
-template <int PER, bool BWD>
+// PER = ceil(C / 32) logits per lane kept in registers (C <= 32 * PER); a warp works on R rows at a time so that R
+// rows of loads are in flight per warp (a row of 47 classes is only 188 bytes).
+template <int PER, int R, bool BWD>
 __global__ void __launch_bounds__(256)
 softmax_xent_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels, int64_t rows, int C,
                     float* __restrict__ row_loss, const float* __restrict__ gup, float scale,
@@ -69,36 +70,47 @@ softmax_xent_kernel(const float* __restrict__ logits, int64_t ld, const int64_t*
   const int64_t wpb = blockDim.x >> 5;
   float gs = 0.f;
   if (BWD) gs = __ldg(gup) * scale;
-  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
-    float v[PER];
-    float m = -INFINITY;
+  for (int64_t r0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * R; r0 < rows; r0 += (int64_t)gridDim.x * wpb * R) {
+    float v[R][PER];
+    int64_t lab[R];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      const int c = lane + i * 32;
-      v[i] = (c < C) ? __ldg(logits + r * ld + c) : -INFINITY;
-      m = fmaxf(m, v[i]);
-    }
-    m = warp_max(m);
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      v[i] = (lane + i * 32 < C) ? expf(v[i] - m) : 0.f;
-      s += v[i];
-    }
-    s = warp_sum(s);
-    const int64_t lab = __ldg(labels + r);
-    if (!BWD) {
-      // loss = logsumexp - logit[label]
-      float picked = 0.f;
-      if (lab >= 0 && lab < C && (lab & 31) == lane) picked = __ldg(logits + r * ld + lab);
-      picked = warp_sum(picked);
-      if (lane == 0) row_loss[r] = (logf(s) + m) - picked;
-    } else {
-      const float inv = 1.f / s;
+    for (int j = 0; j < R; ++j) {
+      const int64_t r = r0 + j;
+      lab[j] = (r < rows) ? __ldg(labels + r) : 0;
 #pragma unroll
       for (int i = 0; i < PER; ++i) {
         const int c = lane + i * 32;
-        if (c < C) dlogits[r * ldd + c] = (v[i] * inv - ((int64_t)c == lab ? 1.f : 0.f)) * gs;
+        v[j][i] = (c < C && r < rows) ? __ldg(logits + r * ld + c) : -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int64_t r = r0 + j;
+      if (r >= rows) break;   // warp-uniform
+      float m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) m = fmaxf(m, v[j][i]);
+      m = warp_max(m);
+      float picked = 0.f;   // logit of the label (forward only)
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = lane + i * 32;
+        if (!BWD && c < C && (int64_t)c == lab[j]) picked = v[j][i];
+        v[j][i] = (c < C) ? expf(v[j][i] - m) : 0.f;
+        s += v[j][i];
+      }
+      s = warp_sum(s);
+      if (!BWD) {
+        picked = warp_sum(picked);   // loss = logsumexp - logit[label]; labels outside [0, C) contribute 0
+        if (lane == 0) row_loss[r] = (logf(s) + m) - picked;
+      } else {
+        const float inv = 1.f / s;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const int c = lane + i * 32;
+          if (c < C) dlogits[r * ldd + c] = (v[j][i] * inv - ((int64_t)c == lab[j] ? 1.f : 0.f)) * gs;
+        }
       }
     }
   }
@@ -107,17 +119,20 @@ softmax_xent_kernel(const float* __restrict__ logits, int64_t ld, const int64_t*
 template <bool BWD>
 static int launch_xent(int device, const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int C,
                        float* row_loss, const float* gup, float scale, float* dlogits, int64_t ldd, cudaStream_t st) {
-  int64_t grid = ceil_div(rows, 8);
   const int64_t cap = (int64_t)sm_count(device) * 8;
-  if (grid > cap) grid = cap;
-#define KGB_XENT(P)                                                                                             \
-  softmax_xent_kernel<P, BWD><<<(int)grid, 256, 0, st>>>(logits, ld, labels, rows, C, row_loss, gup, scale, dlogits, ldd)
-  if (C <= 32) KGB_XENT(1);
-  else if (C <= 64) KGB_XENT(2);
-  else if (C <= 128) KGB_XENT(4);
-  else if (C <= 256) KGB_XENT(8);
-  else if (C <= 512) KGB_XENT(16);
-  else KGB_XENT(32);
+#define KGB_XENT(P, R_)                                                                                          \
+  do {                                                                                                           \
+    int64_t grid = ceil_div(rows, 8 * (R_));                                                                     \
+    if (grid > cap) grid = cap;                                                                                  \
+    softmax_xent_kernel<P, R_, BWD><<<(int)grid, 256, 0, st>>>(logits, ld, labels, rows, C, row_loss, gup, scale, \
+                                                               dlogits, ldd);                                    \
+  } while (0)
+  if (C <= 32) KGB_XENT(1, 4);
+  else if (C <= 64) KGB_XENT(2, 4);
+  else if (C <= 128) KGB_XENT(4, 2);
+  else if (C <= 256) KGB_XENT(8, 1);
+  else if (C <= 512) KGB_XENT(16, 1);
+  else KGB_XENT(32, 1);
 #undef KGB_XENT
   KGB_CHECK_LAUNCH();
   return KGB_OK;
