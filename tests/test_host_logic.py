@@ -223,3 +223,28 @@ def test_processed_npz_format_round_trip(tmp_path):
     np.testing.assert_array_equal(graphs[1]["edge_index"], ref_file["edge_index_1"])
     assert graphs[1]["edge_attr"] is None and graphs[0]["edge_attr"].shape == (8, 2)
     np.testing.assert_array_equal(graphs[0]["y"], ref_file["y_0"])
+
+
+def test_scripts_parse_and_partition_bounds():
+    """bench / tools scripts are at least syntactically valid here (they need a GPU to run), and the weak-scaling
+    arm's cost-balanced contiguous ranges cover [0, n) monotonically."""
+    import ast
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in [os.path.join(root, "bench.py"), os.path.join(root, "bench_dist.py"),
+                 os.path.join(root, "__graft_entry__.py")] + glob.glob(os.path.join(root, "tools", "*.py")):
+        ast.parse(open(path).read(), filename=path)
+    import sys
+    sys.path.insert(0, root)
+    import bench_dist
+    gen = torch.Generator().manual_seed(0)
+    n = 1000
+    dst = (torch.rand(20000, generator=gen) ** 3 * n).long().clamp_(max=n - 1)   # skewed in-degrees
+    for world in (1, 2, 3, 8):
+        b = bench_dist.edge_balanced_bounds(dst, n, world)
+        assert b[0] == 0 and b[-1] == n and len(b) == world + 1
+        assert all(b[i] <= b[i + 1] for i in range(world))
+        if world > 1:
+            deg = torch.bincount(dst, minlength=n) + bench_dist.NODE_WEIGHT
+            costs = [float(deg[b[i]:b[i + 1]].sum()) for i in range(world)]
+            assert max(costs) <= 1.5 * (sum(costs) / world)
