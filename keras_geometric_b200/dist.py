@@ -91,6 +91,16 @@ class HaloPlan:
     def edge_index_local(self) -> torch.Tensor:
         return torch.stack([self.col_local, self.dst_local]).contiguous()
 
+    def split_edges(self):
+        """The rank's edges as two COO lists that keep the original edge order: sources this rank owns (source ids
+        in [0, n_local)) and halo sources (ids in [0, n_halo): rows of the exchanged buffer)."""
+        ei = self.edge_index_local()
+        is_halo = ei[0] >= self.n_local
+        ei_l = ei[:, ~is_halo].contiguous()
+        ei_h = ei[:, is_halo].clone()
+        ei_h[0] -= self.n_local
+        return ei_l, ei_h.contiguous()
+
 
 class PartitionedGraph:
     """Halo plan + device structures of one rank.  Pass it to SAGEConv / GCNConv instead of
@@ -136,13 +146,9 @@ class PartitionedGraph:
         can reduce the local part while the halo rows are still in flight.  inv_deg = 1 / max(total in-degree, 1e-8)."""
         if self._split is None:
             from .graph import GraphStructure
-            ei = self.plan.edge_index_local()
-            is_halo = ei[0] >= self.n_local
-            ei_l = ei[:, ~is_halo].contiguous()
-            ei_h = ei[:, is_halo].clone()
-            ei_h[0] -= self.n_local
+            ei_l, ei_h = self.plan.split_edges()
             g_l = GraphStructure(ei_l, self.n_local, self.n_local, 0)
-            g_h = GraphStructure(ei_h.contiguous(), self.n_local, max(self.n_halo, 1), 0)
+            g_h = GraphStructure(ei_h, self.n_local, max(self.n_halo, 1), 0)
             deg = (g_l.csr.deg + g_h.csr.deg).to(torch.float32)
             self._split = (g_l, g_h, 1.0 / torch.clamp(deg, min=1e-8))
         return self._split

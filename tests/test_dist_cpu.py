@@ -49,6 +49,16 @@ def _worker(rank, world, port, n, e, F, seed, q):
             got = ref.aggregate(op, x_ext[eil[0].long()], eil[1], plan.n_local).numpy()
             full = ref.aggregate(op, torch.from_numpy(x[ei[0]]), torch.from_numpy(ei[1]), n).numpy()
             np.testing.assert_allclose(got, full[lo:hi], rtol=1e-5, atol=1e-6)
+        # the split used to overlap the exchange: local-source part + halo-source part == the whole aggregation,
+        # with the halo part indexing the received buffer directly (no [local | halo] concatenation)
+        ei_l, ei_h = plan.split_edges()
+        assert ei_l.shape[1] + ei_h.shape[1] == eil.shape[1]
+        assert ei_l.shape[1] == 0 or int(ei_l[0].max()) < plan.n_local
+        assert ei_h.shape[1] == 0 or (int(ei_h[0].min()) >= 0 and int(ei_h[0].max()) < plan.n_halo)
+        part_l = ref.aggregate("sum", x_local[ei_l[0].long()], ei_l[1], plan.n_local).numpy()
+        part_h = ref.aggregate("sum", recv[ei_h[0].long()], ei_h[1], plan.n_local).numpy()
+        full = ref.aggregate("sum", torch.from_numpy(x[ei[0]]), torch.from_numpy(ei[1]), n).numpy()
+        np.testing.assert_allclose(part_l + part_h, full[lo:hi], rtol=1e-5, atol=1e-5)
         # reverse direction: halo gradients go back to their owners and are summed per local row
         g_ext = torch.from_numpy(rng.standard_normal((plan.n_local + plan.n_halo, F)).astype(np.float32))
         back = torch.empty((plan.n_send, F))
