@@ -231,3 +231,90 @@ def test_golden_pooling_and_batch_graphs():
     np.testing.assert_array_equal(bx, g["bx"])
     np.testing.assert_array_equal(bei, g["bei"])
     np.testing.assert_array_equal(bb, g["bbatch"])
+
+
+# ---------------------------------------------------- independent restatement by explicit edge loops (float64)
+def _loop_aggregate(name, msgs, dst, n):
+    """Per-target lists built edge by edge, reduced with the formulas of layers/aggregators.py:56-228."""
+    buckets = [[] for _ in range(n)]
+    for e, i in enumerate(dst):
+        if 0 <= i < n:
+            buckets[i].append(msgs[e].astype(np.float64))
+    out = np.zeros((n, msgs.shape[1]))
+    for i, b in enumerate(buckets):
+        if not b:
+            continue  # empty segment: 0 for every aggregator (max/min: -inf/+inf rewritten to 0)
+        m = np.stack(b)
+        if name == "sum":
+            out[i] = m.sum(0)
+        elif name == "mean":
+            out[i] = m.sum(0) / max(float(len(b)), 1e-8)
+        elif name == "max":
+            out[i] = np.where(np.isinf(m.max(0)), 0.0, m.max(0))
+        elif name == "min":
+            out[i] = np.where(np.isinf(m.min(0)), 0.0, m.min(0))
+        elif name == "std":
+            out[i] = 0.0 if len(b) <= 1 else np.sqrt(np.maximum(((m - m.mean(0)) ** 2).mean(0), 0.0))
+    return out
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_matches_edge_loops(seed):
+    """The oracle's aggregators, GCN, SAGE, GIN-style sum and GATv2 against a restatement that shares no code with
+    it: Python loops over edges in float64, written from the formulas in SURVEY.md Appendix A."""
+    rng = np.random.default_rng(100 + seed)
+    n, e, fin, fout = 23, 140, 6, 5
+    ei = np.stack([rng.integers(0, n, e), rng.integers(0, n - 3, e)]).astype(np.int32)  # last rows stay empty
+    x = rng.standard_normal((n, fin)).astype(np.float32)
+    msgs = rng.standard_normal((e, 4)).astype(np.float32)
+    for name in ("sum", "mean", "max", "min", "std"):
+        got = ref.aggregate(name, t(msgs), t(ei[1]), n).numpy()
+        np.testing.assert_allclose(got, _loop_aggregate(name, msgs, ei[1], n), rtol=1e-5, atol=2e-6, err_msg=name)
+
+    # GCN: out_i = sum_e dis[i] dis[j] (x_j W) + b over edges + appended self-loops, dis = (deg + 1e-12)^-1/2
+    w = (rng.standard_normal((fin, fout)) * 0.4).astype(np.float32)
+    b = rng.standard_normal(fout).astype(np.float32)
+    src = np.concatenate([ei[0], np.arange(n)])
+    dst = np.concatenate([ei[1], np.arange(n)])
+    deg = np.zeros(n)
+    for i in dst:
+        deg[i] += 1
+    dis = (deg + 1e-12) ** -0.5
+    xw = x.astype(np.float64) @ w.astype(np.float64)
+    want = np.tile(b.astype(np.float64), (n, 1))
+    for j, i in zip(src, dst):
+        want[i] += dis[i] * dis[j] * xw[j]
+    np.testing.assert_allclose(ref.gcn_conv(t(x), t(ei), t(w), t(b)).numpy(), want, rtol=1e-5, atol=1e-5)
+
+    # SAGE (mean, relu): act(x W_self + mean_j(x_j) W_neigh + b)
+    ws = (rng.standard_normal((fin, fout)) * 0.4).astype(np.float32)
+    agg = _loop_aggregate("mean", x[ei[0]], ei[1], n)
+    want = np.maximum(x.astype(np.float64) @ ws + agg @ w.astype(np.float64) + b, 0.0)
+    got = ref.sage_conv(t(x), t(ei), t(w), t(ws), t(b), "mean", torch.relu).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+
+    # GATv2: s = att . LeakyReLU(h_i + h_j); alpha = exp(s - max_i) / (sum_i exp + 1e-10); out_i = sum alpha h_j
+    H, C = 2, 3
+    wg = (rng.standard_normal((fin, H * C)) * 0.5).astype(np.float32)
+    att = (rng.standard_normal((1, H, C)) * 0.5).astype(np.float32)
+    bg = rng.standard_normal(H * C).astype(np.float32)
+    h = (x.astype(np.float64) @ wg.astype(np.float64)).reshape(n, H, C)
+    s_e = np.zeros((len(src), H))
+    for k, (j, i) in enumerate(zip(src, dst)):
+        z = h[i] + h[j]
+        z = np.where(z > 0, z, 0.2 * z)
+        s_e[k] = (z * att[0]).sum(-1)
+    mx = np.full((n, H), -np.inf)
+    for k, i in enumerate(dst):
+        mx[i] = np.maximum(mx[i], s_e[k])
+    den = np.zeros((n, H))
+    for k, i in enumerate(dst):
+        den[i] += np.exp(s_e[k] - mx[i])
+    want = np.zeros((n, H, C))
+    for k, (j, i) in enumerate(zip(src, dst)):
+        alpha = np.exp(s_e[k] - mx[i]) / (den[i] + 1e-10)
+        want[i] += alpha[:, None] * h[j]
+    got = ref.gatv2_conv(t(x), t(ei), t(wg), t(att), t(bg), heads=H, concat=True).numpy()
+    np.testing.assert_allclose(got, want.reshape(n, H * C) + bg, rtol=1e-5, atol=1e-5)
+    got = ref.gatv2_conv(t(x), t(ei), t(wg), t(att), t(bg[:C]), heads=H, concat=False).numpy()
+    np.testing.assert_allclose(got, want.mean(1) + bg[:C], rtol=1e-5, atol=1e-5)
