@@ -1,4 +1,5 @@
-"""torchrun --nproc-per-node N tools/dist_check.py : partitioned SAGE/GCN layers vs the single-GPU layers."""
+"""torchrun --nproc-per-node N tools/dist_check.py : partitioned SAGE / GCN / GIN / GATv2 layers (outputs, input and
+weight gradients) vs the single-GPU layers."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist

@@ -1,5 +1,7 @@
+"""Single-rank sanity of PartitionedGraph.split: local part + (empty) halo part reproduce the plain mean aggregation."""
 import torch, numpy as np, sys
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from keras_geometric_b200.dist import PartitionedGraph
 from keras_geometric_b200 import ops
 from keras_geometric_b200.graph import GraphStructure
