@@ -121,7 +121,8 @@ def run(args, world, rank, local_rank):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C4 x {world}: 3-layer SAGEConv(mean) 100->256->256->47, RMAT graph 1-D "
-                                   "node-partitioned (edge-balanced ranges), NCCL all_to_all halo exchange per layer",
+                                   "node-partitioned (cost-balanced ranges), NCCL all_to_all halo exchange per layer overlapped "
+                                   "with the local-source part of the aggregation and the weight-gradient GEMMs",
                        "nodes": n_global, "edges": e_global, "layers": n_layers, "rmat": list(RMAT), "seed": 0,
                        "per_rank": {"n_local": [int(s[0]) for s in allstats], "n_halo": halo_rows,
                                     "edges": [int(s[2]) for s in allstats], "n_send": [int(s[3]) for s in allstats]},
