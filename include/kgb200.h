@@ -182,11 +182,18 @@ struct kgb_hub_table;
  * between tied maxima).  gx must be zero-initialised by the caller; accumulates
  *   gx[arg[r,f], f] += g[r,f]                       (unique extremum)
  *   gx[col[k],  f] += g[r,f] / n_ties               for every tied edge (arg == -2)
- * `out` is the forward result, x the forward input.  Same CSR as the forward. */
+ * `out` is the forward result, x the forward input.  Same CSR as the forward.
+ * Deterministic: several targets may select the same source entry, so the contributions are accumulated as 64-bit
+ * FIXED-POINT integers (grid 2^-s chosen from max|g| and the row count so that no sum can overflow; integer addition
+ * is associative, the order in which the atomics land cannot change a bit of the result) in the caller-provided
+ * workspace `acc_ws` (kgb_gather_max_bwd_acc_bytes(n_src_rows, F), contents arbitrary on entry) and converted to
+ * fp32 once per element at the end.  NaN / +-inf gradients bypass the grid (their sum is order-independent anyway). */
+size_t kgb_gather_max_bwd_acc_bytes(int64_t n_src_rows, int32_t F);
 int kgb_gather_max_bwd(int device, const float* g, int64_t ldg, const int32_t* arg,
                        const float* out, int64_t ldo, const float* x, int64_t ldx,
                        const int64_t* rowptr, const int32_t* col, const int32_t* row_ids,
                        int64_t n_rows, int32_t F, int32_t op, float* gx, int64_t ldgx,
+                       int64_t n_src_rows, void* acc_ws,
                        const struct kgb_hub_table* hubs, kgb_stream_t stream);
 /* `hubs` (optional) lets tied entries of hub rows be resolved chunk-parallel; its `partial` workspace must
  * hold kgb_gather_max_bwd_workspace_bytes(n_hubs, n_chunks, F) bytes. */
@@ -256,27 +263,17 @@ int kgb_reduce_parts(int device, const float* part, int32_t n_parts, int32_t F, 
  * K8  dense node-feature transform on the tensor cores (tcgen05.mma, TMEM accumulators, TMA operands).
  * Replaces ops.matmul (layers/gcn_conv.py:233,335) and layers.Dense (layers/sage_conv.py:201-221,
  * layers/gin_conv.py:133-156, layers/gatv2_conv.py:95-101).
- *   D = alpha * op(A) * op(B) + beta * C          fp32 in / fp32 out, fp32-accurate
- * (each fp32 operand is split in-kernel into three bf16 terms; five product bands, fp32 accumulate).
- *   KGB_GEMM_NN: A [M,K] row-major (lda), B [K,N] row-major (ldb)            forward  X * W
- *   KGB_GEMM_NT: A [M,K] row-major (lda), B stored [N,K] row-major (ldb)     dX = G * W^T
- *   KGB_GEMM_TN: A stored [K,M] row-major (lda), B [K,N] row-major (ldb)     dW = X^T * G
- * C/D are [M,N] row-major with leading dimension ldd; C may alias D, may be NULL when beta == 0.
- * L >= 1 batches with element strides batch_a/b/d (used to split the long reduction of dW).
- * All pointers 16-byte aligned, all leading dimensions / batch strides multiples of 4 floats.
+ * Every width goes through the hand-written tcgen05 kernels below (csrc/tc_gemm.cu): the host side pads the output
+ * width to a multiple of 4 and loops 256-wide column slabs of the weights for wider layers; there is no library
+ * (cuBLAS / CUTLASS) GEMM behind this ABI.
  * ------------------------------------------------------------------------------------- */
-enum { KGB_GEMM_NN = 0, KGB_GEMM_NT = 1, KGB_GEMM_TN = 2 };
-size_t kgb_dense_gemm_workspace_bytes(int mode, int M, int N, int K, int L);
-int kgb_dense_gemm(int device, int mode, const float* A, int64_t lda, int64_t batch_a, const float* B,
-                   int64_t ldb, int64_t batch_b, const float* C, float* D, int64_t ldd, int64_t batch_d,
-                   int M, int N, int K, int L, float alpha, float beta, void* ws, size_t ws_bytes,
-                   kgb_stream_t stream);
 
-/* K8, hand-written variant (csrc/tc_gemm.cu): D[M,N] = A[M,K] * Wt[N,K]^T (+ C) (+ bias) (ReLU) with
+/* D[M,N] = A[M,K] * Wt[N,K]^T (+ C) (+ bias) (ReLU) with
  * tcgen05.mma.kind::tf32 and a 3xTF32 split (fp32-accurate), TMA operand staging, TMEM accumulators, one persistent
  * warp-specialised CTA per SM.  Wt must be pre-split by kgb_split_tf32 into wt_hi / wt_lo, each a dense
- * [kgb_linear_tc_rows(N), K] fp32 matrix whose rows >= N are zero.  Needs M >= 128, N <= 256, N % 4 == K % 4 == 0,
- * 16-byte aligned pointers and leading dimensions that are multiples of 4. */
+ * [kgb_linear_tc_rows(N), kgb_linear_tc2_k(K, 0)] fp32 matrix whose rows >= N and columns >= K are zero.
+ * Any M >= 1 and any K (TMA zero-fills rows past M and columns past K); N <= 256 and N % 4 == 0 (pad the output),
+ * 16-byte aligned pointers and leading dimensions that are multiples of 4 floats. */
 int32_t kgb_linear_tc_rows(int32_t N);
 /* hi = tf32-truncated W, lo = W - hi; written transposed ([cols, rows]) when transpose != 0 */
 int kgb_split_tf32(int device, const float* w, int32_t rows, int32_t cols, int64_t ld, int32_t transpose,
@@ -290,7 +287,8 @@ int kgb_split_tf32_ld(int device, const float* w, int32_t rows, int32_t cols, in
 /* D = [A1 | A2] * [W1 ; W2] (+ C) (+ bias) (ReLU): two node-feature operands that share the row dimension are
  * multiplied in ONE pass (SAGEConv's lin_neigh(agg) + lin_self(x), sage_conv.py:411-433; the sum of two dX GEMMs).
  * wt_hi / wt_lo are [kgb_linear_tc_rows(N), kgb_linear_tc2_k(K1, K2)]: W1^T in columns [0, K1), zeros up to the next
- * multiple of 32, then W2^T.  K2 == 0 (A2 NULL) is kgb_linear_tc. */
+ * multiple of 32, then W2^T (zero-padded to a multiple of 4 columns).  K2 == 0 (A2 NULL) is kgb_linear_tc, whose
+ * row length kgb_linear_tc2_k(K, 0) is K rounded up to a multiple of 4. */
 int32_t kgb_linear_tc2_k(int32_t K1, int32_t K2);
 int kgb_linear_tc2(int device, const float* A1, int64_t lda1, int32_t K1, const float* A2, int64_t lda2, int32_t K2,
                    int32_t M, const float* wt_hi, const float* wt_lo, int32_t N, const float* C, int64_t ldc,
@@ -299,7 +297,8 @@ int kgb_linear_tc2(int device, const float* A1, int64_t lda1, int32_t K1, const 
 /* dW[Kx,N] = X[M,Kx]^T * G[M,N] with the same tcgen05 3xTF32 machinery (both operands MN-major, both split in
  * shared memory).  The node dimension is cut into kgb_linear_tc_dw_parts() contiguous slices, one per CTA; slice p
  * writes partials[p, :, :] and the caller adds the partials in order with kgb_reduce_parts (deterministic).
- * Needs M >= 16, Kx, N <= 256 and multiples of 4, 16-byte aligned operands. */
+ * Needs M >= 1, Kx, N <= 256 and multiples of 4 (wider / ragged shapes: the caller loops 256-wide slabs over padded
+ * operands), 16-byte aligned operands. */
 int32_t kgb_linear_tc_dw_parts(int device, int64_t M);
 int kgb_linear_tc_dw(int device, const float* X, int64_t ldx, const float* G, int64_t ldg, int32_t M, int32_t Kx,
                      int32_t N, float* partials, int32_t n_parts, kgb_stream_t stream);

@@ -24,20 +24,6 @@ NVCC_FLAGS = [
 ]
 
 
-def _cutlass_include() -> str | None:
-    """CuTe/CUTLASS header tree vendored in the image (used by the tcgen05 GEMM templates only)."""
-    import sysconfig
-    cands = []
-    for base in {sysconfig.get_paths().get("purelib"), sysconfig.get_paths().get("platlib")}:
-        if base:
-            cands += [os.path.join(base, "flashinfer", "data", "cutlass", "include"),
-                      os.path.join(base, "tilelang", "3rdparty", "cutlass", "include")]
-    for c in cands:
-        if os.path.exists(os.path.join(c, "cutlass", "gemm", "collective", "builders", "sm100_9xBF16_umma_builder.inl")):
-            return c
-    return None
-
-
 def _nvcc() -> str:
     cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(cand):
@@ -119,14 +105,8 @@ def _build_locked(nvcc: str, force: bool, verbose: bool) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-        extra = []
-        if os.path.basename(src).startswith("dense_gemm_") and not src.endswith("_api.cu"):
-            inc = _cutlass_include()
-            if inc is None:
-                raise RuntimeError("CUTLASS/CuTe headers not found (flashinfer/data/cutlass/include)")
-            extra = ["--expt-relaxed-constexpr", "-I", inc]
-        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
-        if os.path.exists(obj) and os.path.exists(obj + ".sha"):  # per-object cache: the GEMM templates take minutes
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        if os.path.exists(obj) and os.path.exists(obj + ".sha"):  # per-object cache
             with open(obj + ".sha") as fh:
                 if fh.read() == _file_digest(src, cmd):
                     return obj

@@ -61,6 +61,33 @@ def value_of(v):
     return v.value if hasattr(v, "value") else v
 
 
+def apply_dense(layer, x: torch.Tensor) -> torch.Tensor:
+    """``Dense`` forward on the hand-written tensor-core kernels (K8): ``act(x @ kernel + bias)`` with bias and ReLU
+    in the GEMM epilogue.  Takes the layer's WEIGHTS, not its ``call``, so it is the same code whether ``layer`` is
+    the local shim or a real ``keras.layers.Dense`` (whose own call would run cuBLAS through ``torch.matmul``)."""
+    from . import ops
+    kernel, bias = value_of(layer.kernel), value_of(getattr(layer, "bias", None))
+    act = getattr(layer, "activation", None)
+    name = getattr(act, "__name__", None) if act is not None else "linear"
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1]) if x.dim() != 2 else x
+    if name in ("relu", "linear"):
+        y = ops.linear(x2, kernel, bias=bias, act=None if name == "linear" else "relu")
+    else:
+        y = act(ops.linear(x2, kernel, bias=bias))
+    return y if x.dim() == 2 else y.reshape(*lead, y.shape[-1])
+
+
+def apply_mlp(seq, x: torch.Tensor, training=None) -> torch.Tensor:
+    """A ``Sequential`` of Dense / Dropout layers (GINConv.mlp, gin_conv.py:129-159) with every Dense on K8."""
+    for lyr in seq.layers:
+        if getattr(lyr, "kernel", None) is not None and hasattr(lyr, "units"):
+            x = apply_dense(lyr, x)
+        else:
+            x = lyr(x, training=training)
+    return x
+
+
 if HAVE_KERAS:  # pragma: no cover
     from keras import activations, constraints, initializers, regularizers  # noqa: F401
     from keras.layers import Dense, Dropout, Layer  # noqa: F401
@@ -359,17 +386,7 @@ else:
             self.built = True
 
         def call(self, x, training=None):
-            if x.is_cuda and x.dim() == 2:
-                from . import ops  # tensor-core transform (K8) with bias / ReLU in the epilogue
-                name = getattr(self.activation, "__name__", None)
-                if name in ("relu", "linear"):
-                    return ops.linear(x, self.kernel, bias=self.bias, act=None if name == "linear" else "relu")
-                y = ops.linear(x, self.kernel, bias=self.bias)
-                return self.activation(y)
-            y = torch.matmul(x, self.kernel)
-            if self.bias is not None:
-                y = y + self.bias
-            return self.activation(y)
+            return apply_dense(self, x)
 
         def compute_output_shape(self, input_shape):
             return tuple(input_shape[:-1]) + (self.units,)

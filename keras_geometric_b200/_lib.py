@@ -69,9 +69,10 @@ SIGNATURES = {
     "kgb_permute_f32": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "kgb_gather_reduce_partial_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "kgb_gather_reduce": (c_int, [c_int, POINTER(GatherReduceArgs), c_void_p]),
+    "kgb_gather_max_bwd_acc_bytes": (c_size_t, [c_int64, c_int32]),
     "kgb_gather_max_bwd": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                    c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64,
-                                   POINTER(HubTable), c_void_p]),
+                                   c_int64, c_void_p, POINTER(HubTable), c_void_p]),
     "kgb_gather_unit_rows": (c_int32, []),
     "kgb_gatv2_unit_rows": (c_int32, []),
     "kgb_gather_max_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
@@ -89,10 +90,6 @@ SIGNATURES = {
                                   c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   POINTER(HubTable), c_void_p]),
     "kgb_reduce_parts": (c_int, [c_int, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
-    "kgb_dense_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
-    "kgb_dense_gemm": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
-                               c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
-                               c_size_t, c_void_p]),
     "kgb_linear_tc_rows": (c_int32, [c_int32]),
     "kgb_split_tf32": (c_int, [c_int, c_void_p, c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "kgb_linear_tc": (c_int, [c_int, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
@@ -106,7 +103,7 @@ SIGNATURES = {
     "kgb_linear_tc_dw": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p,
                                  c_int32, c_void_p]),
 }
-GEMM_NN, GEMM_NT, GEMM_TN = 0, 1, 2
+ABI_VERSION = 200  # must equal kgb_version() of the loaded library (bumped with every ABI change)
 
 _lock = threading.Lock()
 _lib = None
@@ -126,17 +123,24 @@ def load(build_if_missing: bool = True):
             return _lib
         path = os.environ.get("KGB200_LIB") or _build.LIB  # KGB200_LIB: tuning builds of the same ABI
         if path == _build.LIB and build_if_missing and not _build.is_fresh():
+            # the sources (or the header) changed since the library was linked: the ctypes mirrors below may no
+            # longer match the binary, so a failed rebuild is an error even when an old .so is lying around
             try:
                 _build.build()
             except Exception as e:  # noqa: BLE001
-                if not os.path.exists(path):
-                    raise RuntimeError(
-                        "keras_geometric_b200: libkgb200.so is not built and could not be compiled "
-                        f"({e}). There is no CPU fallback for the message-passing hot path.") from e
+                raise RuntimeError(
+                    "keras_geometric_b200: libkgb200.so is missing or stale and could not be (re)compiled "
+                    f"({e}). There is no CPU fallback for the message-passing hot path.") from e
         if not os.path.exists(path):
             raise RuntimeError("keras_geometric_b200: libkgb200.so not found; run "
                                "`python -m keras_geometric_b200._build`. There is no CPU fallback.")
         lib = ctypes.CDLL(path)
+        lib.kgb_version.restype = c_int
+        lib.kgb_version.argtypes = []
+        got = int(lib.kgb_version())
+        if got != ABI_VERSION:
+            raise RuntimeError(f"keras_geometric_b200: {path} exports ABI version {got}, this package binds "
+                               f"version {ABI_VERSION}; rebuild with `python -m keras_geometric_b200._build --force`")
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = res

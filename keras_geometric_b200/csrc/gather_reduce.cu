@@ -510,7 +510,34 @@ struct MaxBwdP {
   float* cnt_partial;  // [n_chunks, F]
   float* cnt_total;    // [n_hubs, F]
   int32_t* hub_tie;    // [n_hubs]
+  // deterministic scatter: contributions are added as 64-bit fixed-point integers (integer addition is associative,
+  // so the order in which the atomics land cannot change the result); gmax_bits = bit pattern of max |g| over the
+  // finite entries, written by max_bwd_absmax_kernel before the scatter kernels run
+  long long* acc; int64_t ldacc; uint32_t* gmax_bits; int cnt_bits;  // gmax_bits[1]: a non-finite gradient was seen
 };
+
+// exponent s of the fixed-point grid 2^-s: max|g| < 2^e and at most 2^cnt_bits contributions of magnitude <= max|g|
+// reach one slot, so |sum * 2^s| < 2^62
+__device__ __forceinline__ int max_bwd_shift(const MaxBwdP& p) {
+  const float gm = __uint_as_float(__ldg(p.gmax_bits));
+  if (!(gm > 0.f)) return 0;
+  int e;
+  frexpf(gm, &e);  // gm = m * 2^e, 0.5 <= m < 1
+  return 62 - e - p.cnt_bits;
+}
+
+// gx[row, f] += v, deterministically.  Non-finite contributions (NaN / +-inf gradients) go to the fp32 buffer with a
+// float atomic: any order of a multiset of NaN / inf values gives the same result.
+__device__ __forceinline__ void max_bwd_add(const MaxBwdP& p, int shift, int64_t row, int f, float v) {
+  if (v == 0.f) return;
+  if (fabsf(v) <= 3.4028234e38f) {
+    const long long q = __double2ll_rn(ldexp((double)v, shift));
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.acc + row * p.ldacc + f), (unsigned long long)q);
+  } else {
+    atomicAdd(p.gx + row * p.ldgx + f, v);
+    p.gmax_bits[1] = 1u;
+  }
+}
 
 // Walk CSR slots [k0, k1): phase 0 counts, per element, the edges whose source value equals o; phase 1
 // adds gv / cnt to those sources.  Only elements with a == -2 take part.
@@ -518,7 +545,7 @@ template <int VEC, int G, int NCH, int PHASE>
 __device__ __forceinline__ void tie_walk(const MaxBwdP& p, int64_t k0, int64_t k1, int gl, unsigned gmask,
                                          const bool (&on)[NCH], const int32_t (&a)[NCH][VEC],
                                          const float (&o)[NCH][VEC], const float (&gv)[NCH][VEC],
-                                         float (&cnt)[NCH][VEC]) {
+                                         float (&cnt)[NCH][VEC], int shift = 0) {
   constexpr int U = (G < 4) ? G : 4;
   int loff[NCH];
 #pragma unroll
@@ -548,7 +575,7 @@ __device__ __forceinline__ void tie_walk(const MaxBwdP& p, int64_t k0, int64_t k
           for (int e = 0; e < VEC; ++e) {
             if (a[ch][e] == -2 && v[u][ch][e] == o[ch][e]) {
               if (PHASE == 0) cnt[ch][e] += 1.f;
-              else atomicAdd(p.gx + (int64_t)c[u] * p.ldgx + (gl + ch * G) * VEC + e, __fdiv_rn(gv[ch][e], cnt[ch][e]));
+              else max_bwd_add(p, shift, (int64_t)c[u], (gl + ch * G) * VEC + e, __fdiv_rn(gv[ch][e], cnt[ch][e]));
             }
           }
         }
@@ -558,7 +585,7 @@ __device__ __forceinline__ void tie_walk(const MaxBwdP& p, int64_t k0, int64_t k
 }
 
 template <int VEC, int G, int NCH>
-__device__ __forceinline__ bool max_bwd_load_row(const MaxBwdP& p, int64_t r, int gl, unsigned gmask,
+__device__ __forceinline__ bool max_bwd_load_row(const MaxBwdP& p, int shift, int64_t r, int gl, unsigned gmask,
                                                  const bool (&on)[NCH], float (&gv)[NCH][VEC], int32_t (&a)[NCH][VEC]) {
   bool tie = false;
 #pragma unroll
@@ -571,7 +598,7 @@ __device__ __forceinline__ bool max_bwd_load_row(const MaxBwdP& p, int64_t r, in
     ld_vec_i<VEC>(p.arg + r * p.ldo + f0, a[ch]);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      if (a[ch][e] >= 0) atomicAdd(p.gx + (int64_t)a[ch][e] * p.ldgx + f0 + e, gv[ch][e]);
+      if (a[ch][e] >= 0) max_bwd_add(p, shift, (int64_t)a[ch][e], f0 + e, gv[ch][e]);
       tie |= (a[ch][e] == -2);
     }
   }
@@ -593,6 +620,7 @@ __global__ void __launch_bounds__(256) gather_max_bwd_kernel(const MaxBwdP p) {
   for (int ch = 0; ch < NCH; ++ch) on[ch] = (gl + ch * G) < nv;
   const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
   const int64_t n_items = MODE == 0 ? p.n_rows : (int64_t)p.n_hubs;
+  const int shift = max_bwd_shift(p);
   for (int64_t it = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; it < n_items;
        it += (int64_t)gridDim.x * gpb) {
     const int64_t s = MODE == 0 ? it : (int64_t)__ldg(p.hub_row + it);
@@ -601,7 +629,7 @@ __global__ void __launch_bounds__(256) gather_max_bwd_kernel(const MaxBwdP p) {
     const int64_t r = p.row_ids ? (int64_t)__ldg(p.row_ids + s) : s;
     float gv[NCH][VEC];
     int32_t a[NCH][VEC];
-    const bool any_tie = max_bwd_load_row<VEC, G, NCH>(p, r, gl, gmask, on, gv, a);
+    const bool any_tie = max_bwd_load_row<VEC, G, NCH>(p, shift, r, gl, gmask, on, gv, a);
     if (!any_tie) continue;
     if (MODE == 1) {
       if (gl == 0) p.hub_tie[it] = 1;
@@ -615,7 +643,7 @@ __global__ void __launch_bounds__(256) gather_max_bwd_kernel(const MaxBwdP p) {
       if (on[ch]) ld_vec<VEC>(p.out + r * p.ldo + (gl + ch * G) * VEC, o[ch]);
     }
     tie_walk<VEC, G, NCH, 0>(p, rs, re, gl, gmask, on, a, o, gv, cnt);
-    tie_walk<VEC, G, NCH, 1>(p, rs, re, gl, gmask, on, a, o, gv, cnt);
+    tie_walk<VEC, G, NCH, 1>(p, rs, re, gl, gmask, on, a, o, gv, cnt, shift);
   }
 }
 
@@ -633,6 +661,7 @@ __global__ void __launch_bounds__(256) max_bwd_hub_chunk_kernel(const MaxBwdP p)
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) on[ch] = (gl + ch * G) < nv;
   const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
+  const int shift = (PHASE == 1) ? max_bwd_shift(p) : 0;
   for (int64_t t = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; t < p.n_chunks;
        t += (int64_t)gridDim.x * gpb) {
     const int h = __ldg(p.chunk_hub + t);
@@ -656,7 +685,7 @@ __global__ void __launch_bounds__(256) max_bwd_hub_chunk_kernel(const MaxBwdP p)
       ld_vec<VEC>(p.out + r * p.ldo + f0, o[ch]);
       if (PHASE == 1) ld_vec<VEC>(p.cnt_total + (int64_t)h * p.F + f0, cnt[ch]);
     }
-    tie_walk<VEC, G, NCH, PHASE>(p, k0, k1, gl, gmask, on, a, o, gv, cnt);
+    tie_walk<VEC, G, NCH, PHASE>(p, k0, k1, gl, gmask, on, a, o, gv, cnt, shift);
     if (PHASE == 0) {
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch)
@@ -676,6 +705,41 @@ __global__ void __launch_bounds__(256) max_bwd_hub_total_kernel(const MaxBwdP p)
     float s = 0.f;
     for (int c = 0; c < nch; ++c) s += p.cnt_partial[(base + c) * p.F + f];
     p.cnt_total[i] = s;
+  }
+}
+
+// max |g| over the finite entries of g [rows, F] (bit patterns of non-negative floats order like unsigned integers)
+__global__ void __launch_bounds__(256) max_bwd_absmax_kernel(const float* __restrict__ g, int64_t ldg, int64_t rows,
+                                                             int F, uint32_t* __restrict__ out_bits) {
+  const int64_t total = rows * (int64_t)F;
+  uint32_t m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F;
+    const uint32_t b = __float_as_uint(__ldg(g + r * ldg + (i - r * F))) & 0x7fffffffu;
+    if (b < 0x7f800000u && b > m) m = b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = t > m ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out_bits, m);
+}
+
+// gx += acc * 2^-shift (the fixed-point sums back to fp32, one correctly rounded conversion per element)
+__global__ void __launch_bounds__(256) max_bwd_convert_kernel(const MaxBwdP p, int64_t n_src) {
+  const int shift = max_bwd_shift(p);
+  const bool nonfinite = p.gmax_bits[1] != 0u;
+  const int64_t total = n_src * (int64_t)p.F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / p.F;
+    const int f = (int)(i - r * p.F);
+    const long long q = p.acc[r * p.ldacc + f];
+    if (q != 0) {  // gx is zero on entry except where non-finite gradients landed (flagged, rare)
+      float* dst = p.gx + r * p.ldgx + f;
+      const float v = (float)ldexp((double)q, -shift);
+      *dst = nonfinite ? __fadd_rn(*dst, v) : v;
+    }
   }
 }
 
@@ -905,16 +969,37 @@ size_t kgb_gather_max_bwd_workspace_bytes(int32_t n_hubs, int32_t n_chunks, int3
          align_up((size_t)n_hubs * sizeof(int32_t), 256);
 }
 
+size_t kgb_gather_max_bwd_acc_bytes(int64_t n_src_rows, int32_t F) {
+  if (n_src_rows <= 0 || F <= 0) return 0;
+  return align_up((size_t)n_src_rows * (size_t)F * sizeof(long long), 256) + 256;
+}
+
 int kgb_gather_max_bwd(int device, const float* g, int64_t ldg, const int32_t* arg, const float* out,
                        int64_t ldo, const float* x, int64_t ldx, const int64_t* rowptr,
                        const int32_t* col, const int32_t* row_ids, int64_t n_rows, int32_t F,
-                       int32_t op, float* gx, int64_t ldgx, const kgb_hub_table* hubs, kgb_stream_t stream) {
+                       int32_t op, float* gx, int64_t ldgx, int64_t n_src_rows, void* acc_ws,
+                       const kgb_hub_table* hubs, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(op == KGB_OP_MAX || op == KGB_OP_MIN || op == KGB_OP_MAX_RAW, "op must be MAX or MIN");
-  KGB_REQUIRE(F > 0 && n_rows >= 0, "bad sizes");
-  if (n_rows == 0) return KGB_OK;
-  KGB_REQUIRE(g && arg && out && x && rowptr && col && gx, "NULL pointer");
+  KGB_REQUIRE(F > 0 && n_rows >= 0 && n_src_rows >= 0, "bad sizes");
+  if (n_rows == 0 || n_src_rows == 0) return KGB_OK;
+  KGB_REQUIRE(g && arg && out && x && rowptr && col && gx && acc_ws, "NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  // fixed-point accumulators [n_src_rows, F] + the max|g| scalar behind them (zero on entry to the kernels)
+  const size_t acc_bytes = kgb_gather_max_bwd_acc_bytes(n_src_rows, F);
+  long long* acc = reinterpret_cast<long long*>(acc_ws);
+  uint32_t* gmax_bits = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(acc_ws) + acc_bytes - 256);
+  KGB_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, acc_bytes, st));
+  {
+    int64_t tg = ceil_div(n_rows * (int64_t)F, 256 * 8);
+    const int64_t cap = (int64_t)sm_count(device) * 8;
+    if (tg > cap) tg = cap;
+    if (tg < 1) tg = 1;
+    max_bwd_absmax_kernel<<<(int)tg, 256, 0, st>>>(g, ldg, n_rows, F, gmax_bits);
+    KGB_CHECK_LAUNCH();
+  }
+  int cnt_bits = 1;
+  while (((int64_t)1 << cnt_bits) < n_rows) ++cnt_bits;
   const bool use_hubs = hubs && hubs->n_hubs > 0 && hubs->n_chunks > 0 && hubs->partial;
   const bool can4 = aligned16(g) && aligned16(arg) && aligned16(out) && aligned16(x) && ldg % 4 == 0 &&
                     ldo % 4 == 0 && ldx % 4 == 0 && (!use_hubs || aligned16(hubs->partial));
@@ -925,6 +1010,7 @@ int kgb_gather_max_bwd(int device, const float* g, int64_t ldg, const int32_t* a
     MaxBwdP p = {};
     p.g = g + f0; p.ldg = ldg; p.arg = arg + f0; p.out = out + f0; p.ldo = ldo; p.x = x + f0; p.ldx = ldx;
     p.rowptr = rowptr; p.col = col; p.row_ids = row_ids; p.n_rows = n_rows; p.F = Fs; p.gx = gx + f0; p.ldgx = ldgx;
+    p.acc = acc + f0; p.ldacc = F; p.gmax_bits = gmax_bits; p.cnt_bits = cnt_bits;
     if (use_hubs) {
       p.hub_row = hubs->hub_row; p.hub_chunk_base = hubs->hub_chunk_base; p.hub_nchunks = hubs->hub_nchunks;
       p.chunk_hub = hubs->chunk_hub; p.n_hubs = hubs->n_hubs; p.n_chunks = hubs->n_chunks;
@@ -953,6 +1039,14 @@ int kgb_gather_max_bwd(int device, const float* g, int64_t ldg, const int32_t* a
       max_bwd_hub_total_kernel<<<(int)tg, 256, 0, st>>>(p);
       KGB_CHECK_LAUNCH();
       KGB_DISPATCH_SHAPE(s, (max_bwd_hub_chunk_kernel<V, G_, N_, 1><<<cgrid, 256, 0, st>>>(p)));
+      KGB_CHECK_LAUNCH();
+    }
+    {
+      int64_t tg = ceil_div(n_src_rows * (int64_t)Fs, 256 * 4);
+      const int64_t cap = (int64_t)sm_count(device) * 16;
+      if (tg > cap) tg = cap;
+      if (tg < 1) tg = 1;
+      max_bwd_convert_kernel<<<(int)tg, 256, 0, st>>>(p, n_src_rows);
       KGB_CHECK_LAUNCH();
     }
   }

@@ -879,7 +879,7 @@ int32_t kgb_linear_tc_dw_parts(int device, int64_t M) {
 int kgb_linear_tc_dw(int device, const float* X, int64_t ldx, const float* G, int64_t ldg, int32_t M, int32_t Kx,
                      int32_t N, float* partials, int32_t n_parts, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
-  KGB_REQUIRE(M >= DW_R && Kx > 0 && N > 0, "kgb_linear_tc_dw needs M >= %d", DW_R);
+  KGB_REQUIRE(M >= 1 && Kx > 0 && N > 0, "kgb_linear_tc_dw needs M >= 1 and positive widths");  // rows past M: TMA zero fill
   KGB_REQUIRE(X && G && partials, "NULL operand");
   KGB_REQUIRE(Kx <= 256 && N <= 256 && Kx % 4 == 0 && N % 4 == 0, "needs Kx, N <= 256 and multiples of 4");
   KGB_REQUIRE(aligned16(X) && aligned16(G) && aligned16(partials) && ldx % 4 == 0 && ldg % 4 == 0, "alignment");
@@ -923,7 +923,11 @@ int kgb_split_tf32(int device, const float* w, int32_t rows, int32_t cols, int64
   return kgb_split_tf32_ld(device, w, rows, cols, ld, transpose, hi, lo, transpose ? rows : cols, stream);
 }
 
-int32_t kgb_linear_tc2_k(int32_t K1, int32_t K2) { return (K1 + TC_BK - 1) / TC_BK * TC_BK + K2; }
+// row length of the split weights: [W1 ; W2] with W1's block padded to whole k-blocks, and a multiple of 4 floats
+// overall (TMA rows are 16-byte multiples); the A operands themselves may have any width (TMA zero-fills past K)
+int32_t kgb_linear_tc2_k(int32_t K1, int32_t K2) {
+  return K2 > 0 ? (K1 + TC_BK - 1) / TC_BK * TC_BK + (K2 + 3) / 4 * 4 : (K1 + 3) / 4 * 4;
+}
 
 int kgb_linear_tc2(int device, const float* A1, int64_t lda1, int32_t K1, const float* A2, int64_t lda2, int32_t K2,
                    int32_t M, const float* wt_hi, const float* wt_lo, int32_t N, const float* C, int64_t ldc,
@@ -931,16 +935,15 @@ int kgb_linear_tc2(int device, const float* A1, int64_t lda1, int32_t K1, const 
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "bad sizes");
   if (M == 0) return KGB_OK;
-  KGB_REQUIRE(M >= TC_BM, "kgb_linear_tc needs at least %d rows", TC_BM);
   KGB_REQUIRE(A1 && wt_hi && wt_lo && D && (K2 == 0 || A2), "NULL operand");
-  KGB_REQUIRE(N <= 256 && N % 4 == 0 && K1 % 4 == 0 && K2 % 4 == 0, "kgb_linear_tc needs N <= 256 and N, K multiples of 4");
+  KGB_REQUIRE(N <= 256 && N % 4 == 0, "kgb_linear_tc needs N <= 256 and a multiple of 4 (pad the output)");
   KGB_REQUIRE(aligned16(A1) && (!A2 || aligned16(A2)) && aligned16(wt_hi) && aligned16(wt_lo) && aligned16(D) &&
                   (!C || aligned16(C)) && (!bias || aligned16(bias)) && lda1 % 4 == 0 && (!A2 || lda2 % 4 == 0) &&
                   ldd % 4 == 0 && (!C || ldc % 4 == 0),
               "operands must be 16-byte aligned with leading dimensions multiple of 4");
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
   const int kb1 = (K1 + TC_BK - 1) / TC_BK;
-  const int Kcat = K2 > 0 ? kb1 * TC_BK + K2 : K1;   // the split weights are [BN, Kcat]
+  const int Kcat = kgb_linear_tc2_k(K1, K2);          // the split weights are [BN, Kcat]
   CUtensorMap ma, ma2, mh, ml;
   int rc = make_map(&ma, A1, M, K1, lda1, TC_BM);
   if (rc != KGB_OK) return rc;

@@ -9,7 +9,7 @@ from abc import ABC, abstractmethod
 import torch
 
 from .. import ops
-from .._compat import to_device_tensor
+from .._compat import apply_dense, to_device_tensor
 from ..graph import GraphStructure
 
 _hint = threading.local()
@@ -133,10 +133,15 @@ class PoolingAggregator(Aggregator):
     def aggregate(self, messages, target_idx, dim_size: int):
         messages = to_device_tensor(messages, what="messages")
         if messages.shape[0] == 0:
-            width = self.pool_mlp(torch.zeros((1, messages.shape[1]), dtype=messages.dtype,
-                                              device=messages.device)).shape[1]
+            width = self._transform(torch.zeros((1, messages.shape[1]), dtype=messages.dtype,
+                                                device=messages.device)).shape[1]
             return torch.zeros((dim_size, width), dtype=messages.dtype, device=messages.device)
-        return MaxAggregator().aggregate(self.pool_mlp(messages), target_idx, dim_size)
+        return MaxAggregator().aggregate(self._transform(messages), target_idx, dim_size)
+
+    def _transform(self, messages):
+        if getattr(self.pool_mlp, "kernel", None) is not None and hasattr(self.pool_mlp, "units"):
+            return apply_dense(self.pool_mlp, messages)   # Dense on the tensor-core kernel (K8)
+        return self.pool_mlp(messages)
 
     @property
     def name(self) -> str:

@@ -99,7 +99,7 @@ class GCNConv(MessagePassing):
 
     # generic-path hooks, kept for API compatibility (gcn_conv.py:208-272)
     def message(self, x_i, x_j, edge_attr=None, edge_index=None, size=None, **kwargs):
-        x_j_t = torch.matmul(x_j, value_of(self.kernel))
+        x_j_t = ops.linear(x_j, value_of(self.kernel))
         if self.dropout_rate > 0 and self._current_training:
             x_j_t = Dropout(self.dropout_rate)(x_j_t, training=self._current_training)
         if edge_attr is not None:
@@ -129,7 +129,7 @@ class GCNConv(MessagePassing):
         num_edges = int(edge_index.shape[1]) + n_loops
         dropping = self.dropout_rate > 0 and bool(training)
         if num_edges == 0:  # gcn_conv.py:332-347
-            out = torch.matmul(x, kernel)
+            out = ops.linear(x, kernel)
             if dropping:
                 out = Dropout(self.dropout_rate)(out, training=training)
             return out + bias if bias is not None else out

@@ -8,7 +8,7 @@ from typing import Any
 import torch
 
 from .. import ops
-from .._compat import Dense, Dropout, Sequential, initializers, to_device_tensor, value_of
+from .._compat import Dense, Dropout, Sequential, apply_mlp, initializers, to_device_tensor, value_of
 from ..graph import get_graph
 from .message_passing import MessagePassing
 
@@ -74,7 +74,7 @@ class GINConv(MessagePassing):
         if self.mlp is None:
             raise RuntimeError("MLP not initialized. Call build() first.")
         eps = value_of(self.eps) if self.train_eps else self.eps_init
-        return self.mlp((1 + eps) * x + aggregated)
+        return apply_mlp(self.mlp, (1 + eps) * x + aggregated, training=getattr(self, "_current_training", None))
 
     def call(self, inputs, edge_attr=None, training=None):  # gin_conv.py:228-300
         if not isinstance(inputs, (list, tuple)):
@@ -85,6 +85,7 @@ class GINConv(MessagePassing):
         if x.is_floating_point() and x.dtype != torch.float32:
             x = x.to(torch.float32)
         num_nodes = int(x.shape[0])
+        self._current_training = training
         from ..dist import PartitionedGraph
         if isinstance(inputs[1], PartitionedGraph):
             return self._call_partitioned(x, inputs[1], training)
@@ -97,14 +98,14 @@ class GINConv(MessagePassing):
             raise RuntimeError("MLP not initialized. This indicates a build issue.")
         if int(edge_index.shape[1]) == 0:  # gin_conv.py:269-280
             eps = value_of(self.eps) if self.train_eps else self.eps_init
-            return self.mlp((1 + eps) * x, training=training)
+            return apply_mlp(self.mlp, (1 + eps) * x, training=training)
         fused = (not self.train_eps and self.aggregator in ("sum", "mean")
                  and type(self).message is GINConv.message and type(self).update is GINConv.update
                  and self._uses_default("pre_aggregate", "aggregate", "post_update"))
         if fused:
             graph = get_graph(edge_index, num_nodes, num_nodes, 0)
             h = ops.gather_reduce(x, graph, self.aggregator, addend=x, addend_scale=1.0 + float(self.eps_init))
-            return self.mlp(h, training=training)
+            return apply_mlp(self.mlp, h, training=training)
         return self.propagate(x=x, edge_index=edge_index, edge_attr=edge_attr, training=training)
 
     def _call_partitioned(self, x, pg, training=None):
@@ -133,7 +134,7 @@ class GINConv(MessagePassing):
         else:
             x_ext = pg.exchange(x)
             h = (1 + eps) * x + ops.gather_reduce(x_ext, pg.graph, self.aggregator)
-        return self.mlp(h, training=training)
+        return apply_mlp(self.mlp, h, training=training)
 
     def compute_output_shape(self, input_shape):  # gin_conv.py:303-322
         x_shape = input_shape[0] if isinstance(input_shape, list) else (

@@ -14,7 +14,8 @@ from typing import Any
 import torch
 
 from .. import ops
-from .._compat import Dense, Dropout, activations, constraints, initializers, regularizers, to_device_tensor, value_of
+from .._compat import (Dense, Dropout, activations, apply_dense, constraints, initializers, regularizers,
+                       to_device_tensor, value_of)
 from ..graph import get_graph
 from .aggregators import AggregatorFactory
 from .gcn_conv import canonical_edge_index, input_dim_from_shape
@@ -110,7 +111,7 @@ class SAGEConv(MessagePassing):
                 return ops.gather_reduce(x, graph, agg_name)
             if agg_name == "pooling":
                 # Dense+act commute with the row gather: transform once per node, then fused max
-                return ops.gather_reduce(self.pool_mlp(x), graph, "max")
+                return ops.gather_reduce(apply_dense(self.pool_mlp, x), graph, "max")
         # generic path: per-edge dropout, std, user-overridden hooks
         x_j = ops.take_rows(x, graph, "src")
         x_i = ops.take_rows(x, graph, "dst")

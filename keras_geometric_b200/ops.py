@@ -98,10 +98,12 @@ def _max_bwd(g, arg, out, x, csr: Csr, col, op: int, n_src_rows: int):
     if csr.n_rows and F:
         st = _stream(g.device)
         hubs = csr.hub_table(lib.kgb_gather_max_bwd_workspace_bytes(csr.n_hubs, csr.n_chunks, F), st)
+        # fixed-point accumulators of the deterministic scatter (freed right after the call; stream-ordered)
+        acc = torch.empty(lib.kgb_gather_max_bwd_acc_bytes(n_src_rows, F), dtype=torch.uint8, device=g.device)
         _lib.check(lib.kgb_gather_max_bwd(g.device.index, g.data_ptr(), g.stride(0), arg.data_ptr(), out.data_ptr(),
                                           out.stride(0), x.data_ptr(), x.stride(0), csr.rowptr.data_ptr(),
                                           col.data_ptr(), None, csr.n_rows, F, op, gx.data_ptr(), gx.stride(0),
-                                          ctypes.byref(hubs), st), "kgb_gather_max_bwd")
+                                          n_src_rows, acc.data_ptr(), ctypes.byref(hubs), st), "kgb_gather_max_bwd")
     return gx
 
 
@@ -444,18 +446,15 @@ def gatv2_aggregate(h_src, h_dst, att, graph: GraphStructure, heads: int, channe
 
 
 # ------------------------------------------------------------------------------------------ K8
-_GEMM_WS = {}
+_TC_SLAB = 256  # widest output tile of the tcgen05 kernels; wider layers loop column slabs of the weights
 
 
-def _gemm_ws(dev):
-    ws = _GEMM_WS.get(dev)
-    if ws is None:
-        ws = torch.empty(_lib.load().kgb_dense_gemm_workspace_bytes(0, 0, 0, 0, 1), dtype=torch.uint8, device=dev)
-        _GEMM_WS[dev] = ws
-    return ws
+def _align4(v: int) -> int:
+    return (int(v) + 3) // 4 * 4
 
 
 def _gemm_ok(*tensors) -> bool:
+    """Operands the TMA descriptors can address in place (no padded copy needed)."""
     for t in tensors:
         if t is None:
             continue
@@ -466,37 +465,32 @@ def _gemm_ok(*tensors) -> bool:
     return True
 
 
-def dense_gemm(mode: int, a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, c=None, out=None,
-               beta: float = 0.0, alpha: float = 1.0, L: int = 1, batch=(0, 0, 0)) -> torch.Tensor:
-    """One kgb_dense_gemm launch (tcgen05, fp32-accurate).  ``a``/``b`` are the stored operands of ``mode``."""
-    lib = _lib.load()
-    dev = a.device
-    if out is None:
-        out = torch.empty((M, N) if L == 1 else (L, M, N), dtype=torch.float32, device=dev)
-    ws = _gemm_ws(dev)
-    ldd = out.stride(-2)
-    _lib.check(lib.kgb_dense_gemm(dev.index, mode, a.data_ptr(), a.stride(0), batch[0], b.data_ptr(), b.stride(0),
-                                  batch[1], _ptr(c), out.data_ptr(), ldd, batch[2], M, N, K, L, float(alpha),
-                                  float(beta), ws.data_ptr(), ws.numel(), _stream(dev)), "kgb_dense_gemm")
-    return out
-
-
-_SPLIT_ROWS = 8192  # rows of the long (node) dimension reduced by one CTA column in dW = X^T G
-
-
-def _tc_ok(M: int, n_out: int) -> bool:
-    return M >= 128 and n_out <= 256
+def _tma_rows(t: torch.Tensor, pad_cols: bool = True) -> torch.Tensor:
+    """[rows, cols] fp32 operand a TMA descriptor can address: unit column stride, 16-byte aligned base, row stride a
+    multiple of 4 floats.  Anything else is copied (kgb_gather_rows) into a buffer whose rows are padded to a multiple
+    of 4 floats, pad columns zero; the returned view keeps the logical width.  ``pad_cols``: also guarantee that the
+    columns up to the next multiple of 4 are addressable (they hold zeros or the parent buffer's own data)."""
+    t = _f32c(t, "gemm operand")
+    rows, cols = int(t.shape[0]), int(t.shape[1])
+    if t.stride(1) == 1 and t.data_ptr() % 16 == 0 and t.stride(0) % 4 == 0 and (rows > 1 or cols % 4 == 0):
+        return t  # a row stride that is a multiple of 4 floats also covers the pad columns
+    ld = _align4(cols)
+    buf = torch.empty((rows, ld), dtype=torch.float32, device=t.device)
+    if ld != cols:
+        buf[:, cols:].zero_()
+    return gather_rows(t, None, out=buf[:, :cols])
 
 
 def _split_weight(w: torch.Tensor, transpose: bool):
-    """tf32 hi/lo parts of a weight matrix laid out [n_out, k] (zero-padded rows) for kgb_linear_tc."""
+    """tf32 hi/lo parts of a weight matrix laid out [n_out, k] (zero-padded rows and columns) for kgb_linear_tc."""
     lib = _lib.load()
     rows, cols = int(w.shape[0]), int(w.shape[1])
     n_out, k = (cols, rows) if transpose else (rows, cols)
     bn = lib.kgb_linear_tc_rows(n_out)
-    buf = torch.zeros((2, bn, k), dtype=torch.float32, device=w.device)
-    _lib.check(lib.kgb_split_tf32(w.device.index, w.data_ptr(), rows, cols, w.stride(0), int(transpose),
-                                  buf[0].data_ptr(), buf[1].data_ptr(), _stream(w.device)), "kgb_split_tf32")
+    kp = int(lib.kgb_linear_tc2_k(k, 0))
+    buf = torch.zeros((2, bn, kp), dtype=torch.float32, device=w.device)
+    _lib.check(lib.kgb_split_tf32_ld(w.device.index, w.data_ptr(), rows, cols, w.stride(0), int(transpose),
+                                     buf[0].data_ptr(), buf[1].data_ptr(), kp, _stream(w.device)), "kgb_split_tf32_ld")
     return buf[0], buf[1]
 
 
@@ -514,12 +508,10 @@ def _split_weight_pair(w1: torch.Tensor, w2: torch.Tensor, transpose: bool):
     kcat = int(lib.kgb_linear_tc2_k(k1, k2))
     bn = lib.kgb_linear_tc_rows(n_out)
     buf = torch.zeros((2, bn, kcat), dtype=torch.float32, device=w1.device)
-    off = 0
-    for w, k in ((w1, k1), (w2, k2)):
+    for w, off in ((w1, 0), (w2, (k1 + 31) // 32 * 32)):
         _lib.check(lib.kgb_split_tf32_ld(w.device.index, w.data_ptr(), int(w.shape[0]), int(w.shape[1]), w.stride(0),
                                          int(transpose), buf[0, :, off:].data_ptr(), buf[1, :, off:].data_ptr(), kcat,
                                          _stream(w.device)), "kgb_split_tf32_ld")
-        off = kcat - k2
     return buf[0], buf[1]
 
 
@@ -538,11 +530,13 @@ def linear_tc2(a1: torch.Tensor, a2: torch.Tensor, w_hi: torch.Tensor, w_lo: tor
 
 
 def linear_tc(a: torch.Tensor, w_hi: torch.Tensor, w_lo: torch.Tensor, n_out: int, *, c=None, bias=None,
-              relu: bool = False) -> torch.Tensor:
-    """One kgb_linear_tc launch: a [M,K] @ Wt[n_out,K]^T (+ c) (+ bias) (ReLU) on tcgen05 (3xTF32)."""
+              relu: bool = False, out=None) -> torch.Tensor:
+    """One kgb_linear_tc launch: a [M,K] @ Wt[n_out,K]^T (+ c) (+ bias) (ReLU) on tcgen05 (3xTF32); ``n_out`` is a
+    multiple of 4 and at most 256, ``out`` may be a column block of a wider buffer."""
     lib = _lib.load()
     M, K = int(a.shape[0]), int(a.shape[1])
-    out = torch.empty((M, n_out), dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float32, device=a.device)
     _lib.check(lib.kgb_linear_tc(a.device.index, a.data_ptr(), a.stride(0), M, K, w_hi.data_ptr(), w_lo.data_ptr(),
                                  n_out, _ptr(c), c.stride(0) if c is not None else 0, _ptr(bias),
                                  _lib.ACT_RELU if relu else _lib.ACT_NONE, out.data_ptr(), out.stride(0),
@@ -550,28 +544,71 @@ def linear_tc(a: torch.Tensor, w_hi: torch.Tensor, w_lo: torch.Tensor, n_out: in
     return out
 
 
+def _matmul_tc(a: torch.Tensor, w: torch.Tensor, transpose_w: bool, *, c=None, bias=None, relu: bool = False):
+    """a [M,K] @ W (+ c) (+ bias) (ReLU) for ANY shape on the hand-written tcgen05 kernel.  ``w`` is [K,N]
+    (``transpose_w`` False) or [N,K] (True: the dX = G W^T case).  The output is allocated with its width padded to a
+    multiple of 4 floats (pad columns are exact zeros) and the logical [:, :N] view is returned; widths above 256 loop
+    256-wide column slabs of the weights (the node-feature operand is re-read from L2/HBM once per slab)."""
+    M = int(a.shape[0])
+    N = int(w.shape[0] if transpose_w else w.shape[1])
+    n4 = _align4(N)
+    out = torch.empty((M, n4), dtype=torch.float32, device=a.device)
+    if M == 0 or N == 0:
+        return out[:, :N]
+    a = _tma_rows(a)
+    if bias is not None and n4 != N:
+        bias = torch.nn.functional.pad(bias, (0, n4 - N))
+    if c is not None:
+        c = _tma_rows(c, pad_cols=True)
+    for n0 in range(0, n4, _TC_SLAB):
+        ns = min(_TC_SLAB, n4 - n0)
+        nr = min(ns, N - n0)  # real weight columns of this slab
+        ws = w[n0:n0 + nr, :] if transpose_w else w[:, n0:n0 + nr]
+        hi, lo = _split_weight(ws, transpose=not transpose_w)
+        linear_tc(a, hi, lo, ns, c=c[:, n0:] if c is not None else None, bias=bias[n0:] if bias is not None else None,
+                  relu=relu, out=out[:, n0:])
+    return out[:, :N]
+
+
 def _dw_tc(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     """dW[K,N] = X^T G on the hand-written tcgen05 kernel: one node slice per CTA -> per-CTA partials (promoted to
-    fp32 every 256 nodes), added in CTA order (deterministic, no float atomics across CTAs).  K, N <= 256."""
+    fp32 every 256 nodes), added in CTA order (deterministic, no float atomics across CTAs).  Widths above 256 / not
+    multiples of 4 loop 256-wide slabs of zero-padded operands."""
     lib = _lib.load()
     M, K, N = int(x.shape[0]), int(x.shape[1]), int(g.shape[1])
-    n_parts = lib.kgb_linear_tc_dw_parts(x.device.index, M)
-    parts = torch.empty((n_parts, K, N), dtype=torch.float32, device=x.device)
-    _lib.check(lib.kgb_linear_tc_dw(x.device.index, x.data_ptr(), x.stride(0), g.data_ptr(), g.stride(0), M,
-                                    K, N, parts.data_ptr(), n_parts, _stream(x.device)), "kgb_linear_tc_dw")
-    if n_parts == 1:
-        return parts[0]
-    gw = torch.empty((K, N), dtype=torch.float32, device=x.device)
-    _lib.check(lib.kgb_reduce_parts(x.device.index, parts.data_ptr(), n_parts, K * N, gw.data_ptr(),
-                                    _stream(x.device)), "kgb_reduce_parts")
+    dev = x.device
+    if M == 0 or K == 0 or N == 0:
+        return torch.zeros((K, N), dtype=torch.float32, device=dev)
+    x, g = _tma_rows(x, pad_cols=True), _tma_rows(g, pad_cols=True)
+    n_parts = lib.kgb_linear_tc_dw_parts(dev.index, M)
+    single = K <= _TC_SLAB and N <= _TC_SLAB and K % 4 == 0 and N % 4 == 0
+    gw = None if single else torch.empty((K, N), dtype=torch.float32, device=dev)
+    for k0 in range(0, K, _TC_SLAB):
+        ks = min(_TC_SLAB, K - k0)
+        ks4 = _align4(ks)
+        for n0 in range(0, N, _TC_SLAB):
+            ns = min(_TC_SLAB, N - n0)
+            ns4 = _align4(ns)
+            parts = torch.empty((n_parts, ks4, ns4), dtype=torch.float32, device=dev)
+            _lib.check(lib.kgb_linear_tc_dw(dev.index, x[:, k0:].data_ptr(), x.stride(0), g[:, n0:].data_ptr(),
+                                            g.stride(0), M, ks4, ns4, parts.data_ptr(), n_parts, _stream(dev)),
+                       "kgb_linear_tc_dw")
+            if n_parts == 1:
+                slab = parts[0]
+            else:
+                slab = torch.empty((ks4, ns4), dtype=torch.float32, device=dev)
+                _lib.check(lib.kgb_reduce_parts(dev.index, parts.data_ptr(), n_parts, ks4 * ns4, slab.data_ptr(),
+                                                _stream(dev)), "kgb_reduce_parts")
+            if single:
+                return slab
+            gather_rows(slab[:ks, :ns], None, out=gw[k0:k0 + ks, n0:n0 + ns])
     return gw
 
 
 class _Linear(torch.autograd.Function):
-    """out = x @ w (+ addend) on the tensor cores (K8).  Forward and dX run the hand-written tcgen05 3xTF32 kernel
-    (csrc/tc_gemm.cu), and so does dW = X^T G (MN-major operands, reduction over the node dimension) for widths up
-    to 256; wider shapes use the bf16x9 kernels instantiated from CuTe/CUTLASS templates (csrc/dense_gemm_*.cu).  torch.matmul (cuBLAS, on the GPU) is used only for shapes the TMA alignment rules
-    exclude (a dimension not divisible by 4)."""
+    """out = act(x @ w + addend + bias) on the tensor cores (K8).  Forward, dX = G W^T and dW = X^T G all run the
+    hand-written tcgen05 3xTF32 kernels (csrc/tc_gemm.cu) for every shape: ragged widths are zero-padded to multiples
+    of 4 floats, widths above 256 loop column slabs, short row counts rely on the TMA's out-of-bounds zero fill."""
 
     @staticmethod
     def forward(ctx, x, w, addend, bias, act):
@@ -580,23 +617,11 @@ class _Linear(torch.autograd.Function):
         relu = act == "relu"
         if act not in (None, "linear", "relu"):
             raise ValueError(f"linear: unsupported fused activation {act!r}")
+        if x.dim() != 2 or w.dim() != 2 or int(x.shape[1]) != int(w.shape[0]):
+            raise ValueError(f"linear: cannot multiply {tuple(x.shape)} by {tuple(w.shape)}")
         bias_c = _f32c(bias, "bias").contiguous() if bias is not None else None
-        ctx.fast = _gemm_ok(x, w, addend) and x.shape[0] > 0
-        M, K, N = int(x.shape[0]), int(x.shape[1]), int(w.shape[1])
-        if ctx.fast and _tc_ok(M, N):
-            hi, lo = _split_weight(w, transpose=True)
-            out = linear_tc(x, hi, lo, N, c=addend, bias=bias_c, relu=relu)  # epilogue fused in the GEMM
-        else:
-            if ctx.fast:
-                out = dense_gemm(_lib.GEMM_NN, x, w, M, N, K, c=addend, beta=1.0 if addend is not None else 0.0)
-            else:
-                out = torch.matmul(x, w)
-                if addend is not None:
-                    out = out + addend
-            if bias_c is not None:
-                out = out + bias_c
-            if relu:
-                out = torch.relu(out)
+        x = _tma_rows(x, pad_cols=True)   # the padded copy (if one was needed) is what the backward's dW reads
+        out = _matmul_tc(x, w, False, c=_f32c(addend, "addend") if addend is not None else None, bias=bias_c, relu=relu)
         ctx.save_for_backward(x, w, *([out] if relu else []))
         ctx.has_addend, ctx.has_bias, ctx.relu = addend is not None, bias is not None, relu
         return out
@@ -611,40 +636,9 @@ class _Linear(torch.autograd.Function):
             g, g_bias = relu_bwd_colsum(g, ctx.saved_tensors[2] if ctx.relu else None)
         elif ctx.relu:
             g = relu_bwd(g, ctx.saved_tensors[2])
-        if g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
-            g = g.contiguous()
-        gx = gw = None
-        M, K, N = int(x.shape[0]), int(x.shape[1]), int(w.shape[1])
-        fast = ctx.fast and _gemm_ok(g)
-        if ctx.needs_input_grad[0]:
-            if fast and _tc_ok(M, K):
-                hi, lo = _split_weight(w, transpose=False)  # dX = G @ W^T: W [K,N] already is "Wt" for output width K
-                gx = linear_tc(g, hi, lo, K)
-            elif fast:
-                gx = dense_gemm(_lib.GEMM_NT, g, w, M, K, N)
-            else:
-                gx = torch.matmul(g, w.t())
-        if ctx.needs_input_grad[1]:
-            if fast and M >= 16 and K <= 256 and N <= 256:
-                gw = _dw_tc(x, g)
-            elif fast:
-                # wider than the hand-written kernel: batched bf16x9 kernel over node slices, partials added in order
-                S = _SPLIT_ROWS
-                L, rem = divmod(M, S)
-                parts = torch.empty((L + (1 if rem else 0), K, N), dtype=torch.float32, device=x.device)
-                if L:
-                    dense_gemm(_lib.GEMM_TN, x, g, K, N, S, out=parts[:L], L=L,
-                               batch=(S * x.stride(0), S * g.stride(0), K * N))
-                if rem:
-                    dense_gemm(_lib.GEMM_TN, x[L * S:], g[L * S:], K, N, rem, out=parts[L])
-                if parts.shape[0] == 1:
-                    gw = parts[0]
-                else:
-                    gw = torch.empty((K, N), dtype=torch.float32, device=x.device)
-                    _lib.check(_lib.load().kgb_reduce_parts(x.device.index, parts.data_ptr(), parts.shape[0], K * N,
-                                                            gw.data_ptr(), _stream(x.device)), "kgb_reduce_parts")
-            else:
-                gw = torch.matmul(x.t(), g)
+        g = _tma_rows(g, pad_cols=True)
+        gx = _matmul_tc(g, w, True) if ctx.needs_input_grad[0] else None
+        gw = _dw_tc(x, g) if ctx.needs_input_grad[1] else None
         return gx, gw, (g if ctx.has_addend else None), g_bias, None
 
 
@@ -657,7 +651,7 @@ def linear(x, w, addend=None, bias=None, act=None) -> torch.Tensor:
 def sage_layer_ok(x: torch.Tensor, w_neigh: torch.Tensor, w_self: torch.Tensor) -> bool:
     """Shapes the one-node SAGE layer (``sage_layer``) covers: everything on the hand-written tcgen05 kernels."""
     M, K, N = int(x.shape[0]), int(x.shape[1]), int(w_neigh.shape[1])
-    return (_gemm_ok(x, w_neigh, w_self) and _tc_ok(M, N) and _tc_ok(M, K) and K <= 256 and N <= 256
+    return (_gemm_ok(x, w_neigh, w_self) and M >= 1 and K <= _TC_SLAB and N <= _TC_SLAB
             and tuple(w_self.shape) == tuple(w_neigh.shape))
 
 

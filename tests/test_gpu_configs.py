@@ -1,0 +1,165 @@
+"""GPU parity at the FULL size of BASELINE.json's configs C1, C2 and C3: the public layers on the
+sm_100a kernels against the CPU oracle (oracle/reference_path.py) on the same seeded synthetic inputs - forward
+outputs and every gradient (inputs and all weights), tolerance 1e-5 relative to the output scale as the north star
+states (|got - want| <= 1e-5 * (|want| + max|want|)).  C4's step runs in bench.py / smoke; its kernels are covered at
+5 M edges by test_full_size_properties_products_slice and the per-kernel oracle tests.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_path as ref
+from test_gpu_parity import close, cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def sym_graph(rng, n, e_directed, no_self_loops=True):
+    """e_directed / 2 distinct undirected pairs, both directions, no self-loops, no duplicates."""
+    half = e_directed // 2
+    pairs = set()
+    while len(pairs) < half:
+        a = rng.integers(0, n, half)
+        b = rng.integers(0, n, half)
+        for u, v in zip(a.tolist(), b.tolist()):
+            if u == v and no_self_loops:
+                continue
+            pairs.add((min(u, v), max(u, v)))
+            if len(pairs) == half:
+                break
+    p = np.array(sorted(pairs), dtype=np.int64)
+    p = p[rng.permutation(half)]
+    return np.stack([np.concatenate([p[:, 0], p[:, 1]]), np.concatenate([p[:, 1], p[:, 0]])]).astype(np.int32)
+
+
+def cpu_param(p):
+    return p.detach().cpu().clone().requires_grad_(True)
+
+
+def check_all(out_gpu, out_cpu, params_gpu, params_cpu, names, R, tag):
+    close(out_gpu, out_cpu, msg=f"{tag} forward")
+    g_gpu = torch.autograd.grad((out_gpu * cuda(R)).sum(), params_gpu)
+    g_cpu = torch.autograd.grad((out_cpu * torch.from_numpy(R)).sum(), params_cpu)
+    for nm, a, b in zip(names, g_gpu, g_cpu):
+        close(a.reshape(b.shape), b, msg=f"{tag} grad {nm}")
+
+
+def test_c1_cora_shaped_two_layer_gcn():
+    """C1: 2,708 nodes, 10,556 directed edges, 1,433 bag-of-words features, GCNConv(16) -> ReLU -> GCNConv(7).
+    The 1433 -> 16 -> 7 transforms have K % 4 != 0 and N % 4 != 0: they must run on the tcgen05 kernel (padded)."""
+    import keras_geometric_b200 as kg
+    from keras_geometric_b200 import _lib
+    rng = np.random.default_rng(0)
+    n, e, fin = 2708, 10556, 1433
+    ei = sym_graph(rng, n, e)
+    assert ei.shape == (2, e)
+    x = (rng.random((n, fin)) < 0.0127).astype(np.float32)
+    x = x / np.maximum(x.sum(1, keepdims=True), 1.0)
+    torch.manual_seed(0)
+    l1, l2 = kg.GCNConv(16), kg.GCNConv(7)
+    xg = cuda(x).requires_grad_(True)
+    launches0 = _lib.load().kgb_launch_count()
+    out = l2([torch.relu(l1([xg, ei])), ei])
+    assert _lib.load().kgb_launch_count() - launches0 >= 8   # 2 x (split + GEMM + gather) + CSR build
+    with torch.no_grad():   # non-zero biases so their gradients and the epilogue are exercised
+        l1.bias.copy_(cuda(rng.standard_normal(16).astype(np.float32) * 0.1))
+        l2.bias.copy_(cuda(rng.standard_normal(7).astype(np.float32) * 0.1))
+    out = l2([torch.relu(l1([xg, ei])), ei])
+    pg = [xg, l1.kernel, l1.bias, l2.kernel, l2.bias]
+    xo = torch.from_numpy(x).requires_grad_(True)
+    pc = [xo] + [cpu_param(p) for p in pg[1:]]
+    eio = torch.from_numpy(ei)
+    want = ref.gcn_conv(torch.relu(ref.gcn_conv(xo, eio, pc[1], pc[2])), eio, pc[3], pc[4])
+    R = rng.standard_normal((n, 7)).astype(np.float32)
+    check_all(out, want, pg, pc, ["x", "kernel1", "bias1", "kernel2", "bias2"], R, "C1")
+
+
+def test_c2_pubmed_shaped_two_layer_gatv2():
+    """C2: 19,717 nodes, 88,648 directed edges, 500 features, GATv2Conv(8, heads=8) -> ELU -> GATv2Conv(3, heads=1)."""
+    import keras_geometric_b200 as kg
+    rng = np.random.default_rng(0)
+    n, e, fin = 19717, 88648, 500
+    ei = sym_graph(rng, n, e)
+    x = rng.standard_normal((n, fin)).astype(np.float32)
+    torch.manual_seed(0)
+    g1, g2 = kg.GATv2Conv(8, heads=8), kg.GATv2Conv(3, heads=1)
+    xg = cuda(x).requires_grad_(True)
+    g2([torch.nn.functional.elu(g1([xg, ei])), ei])   # builds the weights
+    with torch.no_grad():
+        g1.bias.copy_(cuda(rng.standard_normal(64).astype(np.float32) * 0.1))
+        g2.bias.copy_(cuda(rng.standard_normal(3).astype(np.float32) * 0.1))
+    out = g2([torch.nn.functional.elu(g1([xg, ei])), ei])
+    pg = [xg, g1.linear_transform.kernel, g1.att, g1.bias, g2.linear_transform.kernel, g2.att, g2.bias]
+    xo = torch.from_numpy(x).requires_grad_(True)
+    pc = [xo] + [cpu_param(p) for p in pg[1:]]
+    eio = torch.from_numpy(ei)
+    h = torch.nn.functional.elu(ref.gatv2_conv(xo, eio, pc[1], pc[2], pc[3], heads=8))
+    want = ref.gatv2_conv(h, eio, pc[4], pc[5], pc[6], heads=1)
+    R = rng.standard_normal((n, 3)).astype(np.float32)
+    check_all(out, want, pg, pc, ["x", "W1", "att1", "bias1", "W2", "att2", "bias2"], R, "C2")
+
+
+def molecule_batch(rng, n_graphs=4096, feats=32):
+    """nodes/graph ~ clip(round(N(25, 5^2)), 5, 60); random spanning tree + extra edges up to ~27
+    undirected (54 directed) edges per graph; node features N(0, 1)."""
+    sizes = np.clip(np.round(rng.normal(25, 5, n_graphs)), 5, 60).astype(np.int64)
+    xs, eis = [], []
+    for s in sizes:
+        par = rng.integers(0, np.arange(1, s))
+        a, b = np.arange(1, s), par
+        extra = max(0, 27 - (s - 1))
+        ea, eb = rng.integers(0, s, extra), rng.integers(0, s, extra)
+        eis.append(np.stack([np.concatenate([a, b, ea, eb]), np.concatenate([b, a, eb, ea])]).astype(np.int32))
+        xs.append(rng.standard_normal((s, feats)).astype(np.float32))
+    return xs, eis
+
+
+def test_c3_molecule_batch_three_layer_gin_readout():
+    """C3: 4,096 molecule-shaped graphs through batch_graphs (device-side disjoint union), 3 x GINConv(64,
+    mlp_hidden=[64], sum) -> BatchGlobalPooling(sum) -> Dense(2)."""
+    import keras_geometric_b200 as kg
+    from keras_geometric_b200._compat import Dense
+    rng = np.random.default_rng(0)
+    xs, eis = molecule_batch(rng)
+    batch = kg.batch_graphs([kg.GraphData(x=x, edge_index=ei) for x, ei in zip(xs, eis)])
+    bx, bei, bb = ref.batch_graphs(xs, eis)
+    np.testing.assert_array_equal(batch.x.cpu().numpy(), bx)                     # bit-exact union
+    np.testing.assert_array_equal(batch.edge_index.cpu().numpy(), bei)
+    np.testing.assert_array_equal(batch.batch.cpu().numpy(), bb)
+    n, e = bx.shape[0], bei.shape[1]
+    assert 95_000 < n < 110_000 and 215_000 < e < 230_000
+    torch.manual_seed(0)
+    gins = [kg.GINConv(64, mlp_hidden=[64], aggregator="sum") for _ in range(3)]
+    pool, head = kg.BatchGlobalPooling(pooling="sum"), Dense(2)
+    xg = batch.x.clone().requires_grad_(True)
+
+    def model(x0):
+        h = x0
+        for lyr in gins:
+            h = lyr([h, batch.edge_index])
+        return head(pool([h, batch.batch]))
+
+    model(xg)   # builds the weights
+    weights, names = [], []
+    for i, lyr in enumerate(gins):
+        for d in lyr.mlp.layers:
+            with torch.no_grad():
+                d.bias.copy_(cuda(rng.standard_normal(int(d.bias.shape[0])).astype(np.float32) * 0.1))
+            weights += [d.kernel, d.bias]
+            names += [f"gin{i}.{d.name}.kernel", f"gin{i}.{d.name}.bias"]
+    weights += [head.kernel, head.bias]
+    names += ["head.kernel", "head.bias"]
+    out = model(xg)
+    assert tuple(out.shape) == (4096, 2)
+    pg = [xg] + weights
+    xo = torch.from_numpy(bx).requires_grad_(True)
+    pc = [xo] + [cpu_param(p) for p in weights]
+    eio, bo = torch.from_numpy(bei), torch.from_numpy(bb)
+    h, k = xo, 1
+    for _ in range(3):
+        w1, b1, w2, b2 = pc[k:k + 4]
+        k += 4
+        h = ref.gin_conv(h, eio, lambda t, w1=w1, b1=b1, w2=w2, b2=b2: torch.relu(t @ w1 + b1) @ w2 + b2, 0.0, "sum")
+    want = ref.batch_global_pooling(h, bo, "sum") @ pc[k] + pc[k + 1]
+    R = rng.standard_normal((4096, 2)).astype(np.float32)
+    check_all(out, want, pg, pc, ["x"] + names, R, "C3")
