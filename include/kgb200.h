@@ -206,6 +206,35 @@ int kgb_gather_rows(int device, const float* src, int64_t lds, const int32_t* id
                     int32_t F, float scale, float* out, int64_t ldo, kgb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K7  halo exchange over peer memory (NVLink / NVSwitch), one process per GPU.
+ * The reference is single-process (no counterpart); this is the exchange step the north star's partitioned path
+ * needs before each layer's aggregation.  Every rank owns a WINDOW (plain cudaMalloc memory, exportable with CUDA
+ * IPC); peers map it once (kgb_ipc_open) and kgb_halo_push then packs the requested feature rows and stores them
+ * STRAIGHT INTO THE RECEIVERS' WINDOWS with 128-bit stores over NVLink - no staging buffer, no send/recv protocol.
+ * Ordering between ranks (window free before the push / all pushes landed before the read) is the caller's
+ * business (one tiny torch.distributed all-reduce on the same stream before and after).
+ * ------------------------------------------------------------------------------------- */
+#define KGB_MAX_PEERS 16
+int kgb_window_alloc(int device, size_t bytes, void** ptr);                 /* cudaMalloc on `device`          */
+int kgb_window_free(int device, void* ptr);
+int kgb_ipc_export(int device, const void* ptr, unsigned char handle[64]);  /* cudaIpcGetMemHandle             */
+int kgb_ipc_open(int device, const unsigned char handle[64], void** ptr);   /* map a peer's window, enables
+                                                                                peer access from `device`       */
+int kgb_ipc_close(int device, void* ptr);
+typedef struct kgb_halo_push_args {
+  const float* src;        /* [*, F] rows of this rank, leading dimension lds                              */
+  int64_t lds;
+  const int32_t* idx;      /* optional [n_slots]: slot s sends row idx[s]; NULL: slot s sends row s        */
+  int32_t F;
+  int32_t n_peers;         /* world size (<= KGB_MAX_PEERS)                                                 */
+  int64_t slot_begin[KGB_MAX_PEERS + 1]; /* slots [slot_begin[p], slot_begin[p+1]) go to peer p            */
+  float* dst[KGB_MAX_PEERS];             /* peer p's window region (device pointer valid on this device)   */
+  int64_t dst_row0[KGB_MAX_PEERS];       /* first row of this rank's block inside peer p's region          */
+  int64_t ldd;             /* leading dimension of the window rows (floats)                                 */
+} kgb_halo_push_args;
+int kgb_halo_push(int device, const kgb_halo_push_args* a, kgb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * K6  fused GATv2 edge kernel.  Replaces layers/gatv2_conv.py:241-264 (_gatv2_propagate edge
  * part), :268-289 (_compute_attention), :291-311 (_softmax_by_target), :313-335
  * (_aggregate_messages) and the bias add of :337-352.

@@ -39,6 +39,17 @@ class GatherReduceArgs(Structure):
     ]
 
 
+MAX_PEERS = 16
+
+
+class HaloPushArgs(Structure):
+    """Mirror of ``struct kgb_halo_push_args`` (include/kgb200.h)."""
+
+    _fields_ = [("src", c_void_p), ("lds", c_int64), ("idx", c_void_p), ("F", c_int32), ("n_peers", c_int32),
+                ("slot_begin", c_int64 * (MAX_PEERS + 1)), ("dst", c_void_p * MAX_PEERS),
+                ("dst_row0", c_int64 * MAX_PEERS), ("ldd", c_int64)]
+
+
 class HubTable(Structure):
     """Mirror of ``struct kgb_hub_table`` (include/kgb200.h)."""
 
@@ -78,6 +89,12 @@ SIGNATURES = {
     "kgb_gather_max_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "kgb_gather_rows": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_float, c_void_p, c_int64,
                                 c_void_p]),
+    "kgb_window_alloc": (c_int, [c_int, c_size_t, POINTER(c_void_p)]),
+    "kgb_window_free": (c_int, [c_int, c_void_p]),
+    "kgb_ipc_export": (c_int, [c_int, c_void_p, ctypes.c_char_p]),
+    "kgb_ipc_open": (c_int, [c_int, ctypes.c_char_p, POINTER(c_void_p)]),
+    "kgb_ipc_close": (c_int, [c_int, c_void_p]),
+    "kgb_halo_push": (c_int, [c_int, POINTER(HaloPushArgs), c_void_p]),
     "kgb_gatv2_partial_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "kgb_gatv2_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_float,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(HubTable),

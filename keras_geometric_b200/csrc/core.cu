@@ -59,6 +59,44 @@ const char* kgb_last_error(void) { return kgb::g_err; }
 
 int64_t kgb_launch_count(void) { return (int64_t)__atomic_load_n(&kgb::g_launches, __ATOMIC_RELAXED); }
 
+int kgb_window_alloc(int device, size_t bytes, void** ptr) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(ptr != nullptr && bytes > 0, "bad arguments");
+  KGB_CHECK_CUDA(cudaMalloc(ptr, bytes));   // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+  return KGB_OK;
+}
+
+int kgb_window_free(int device, void* ptr) {
+  KGB_USE_DEVICE(device);
+  if (ptr) KGB_CHECK_CUDA(cudaFree(ptr));
+  return KGB_OK;
+}
+
+int kgb_ipc_export(int device, const void* ptr, unsigned char handle[64]) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(ptr != nullptr && handle != nullptr, "NULL pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  cudaIpcMemHandle_t h;
+  KGB_CHECK_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+  memcpy(handle, &h, 64);
+  return KGB_OK;
+}
+
+int kgb_ipc_open(int device, const unsigned char handle[64], void** ptr) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(ptr != nullptr && handle != nullptr, "NULL pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  KGB_CHECK_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return KGB_OK;
+}
+
+int kgb_ipc_close(int device, void* ptr) {
+  KGB_USE_DEVICE(device);
+  if (ptr) KGB_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return KGB_OK;
+}
+
 int kgb_device_info(int device, int* sms, int* cc_major, int* cc_minor, int64_t* l2_bytes) {
   KGB_USE_DEVICE(device);
   int v = 0;

@@ -573,9 +573,16 @@ __device__ __forceinline__ void tie_walk(const MaxBwdP& p, int64_t k0, int64_t k
           if (!on[ch]) continue;
 #pragma unroll
           for (int e = 0; e < VEC; ++e) {
-            if (a[ch][e] == -2 && v[u][ch][e] == o[ch][e]) {
+            // special entries: ties between different sources (arg == -2) and non-finite gradients, which the
+            // reference multiplies with a 0/1 mask over ALL edges of the row (0 * inf = NaN reaches every source)
+            const bool nonfin = !(fabsf(gv[ch][e]) <= 3.4028234e38f);
+            const bool special = a[ch][e] == -2 || (a[ch][e] >= 0 && nonfin);
+            if (!special) continue;
+            if (v[u][ch][e] == o[ch][e]) {
               if (PHASE == 0) cnt[ch][e] += 1.f;
               else max_bwd_add(p, shift, (int64_t)c[u], (gl + ch * G) * VEC + e, __fdiv_rn(gv[ch][e], cnt[ch][e]));
+            } else if (PHASE == 1 && nonfin) {
+              max_bwd_add(p, shift, (int64_t)c[u], (gl + ch * G) * VEC + e, __fmul_rn(gv[ch][e], 0.f));
             }
           }
         }
@@ -598,8 +605,9 @@ __device__ __forceinline__ bool max_bwd_load_row(const MaxBwdP& p, int shift, in
     ld_vec_i<VEC>(p.arg + r * p.ldo + f0, a[ch]);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      if (a[ch][e] >= 0) max_bwd_add(p, shift, (int64_t)a[ch][e], f0 + e, gv[ch][e]);
-      tie |= (a[ch][e] == -2);
+      const bool nonfin = !(fabsf(gv[ch][e]) <= 3.4028234e38f);
+      if (a[ch][e] >= 0 && !nonfin) max_bwd_add(p, shift, (int64_t)a[ch][e], f0 + e, gv[ch][e]);
+      tie |= (a[ch][e] == -2) || (a[ch][e] >= 0 && nonfin);   // both re-walk the row
     }
   }
   return (__ballot_sync(gmask, tie) & gmask) != 0;
@@ -767,6 +775,44 @@ gather_rows_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __
         for (int e = 0; e < VEC; ++e) v[e] = __fmul_rn(v[e], scale);
       }
       st_vec<VEC>(out + r * ldo + f0, v);
+    }
+  }
+}
+
+// K7: pack + push.  Slot s (grouped by destination peer) reads one feature row of this rank and stores it into the
+// destination rank's window over NVLink (peer memory mapped with CUDA IPC).
+struct PushTab {
+  int n_peers;
+  int64_t slot_begin[KGB_MAX_PEERS + 1];
+  float* dst[KGB_MAX_PEERS];
+  int64_t dst_row0[KGB_MAX_PEERS];
+};
+
+template <int VEC, int G, int NCH>
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __restrict__ idx, int F, int64_t ldd,
+                 const PushTab tab) {
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int gw = lane / G;
+  const int nv = F / VEC;
+  const int64_t n_slots = tab.slot_begin[tab.n_peers];
+  const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
+  for (int64_t s = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; s < n_slots;
+       s += (int64_t)gridDim.x * gpb) {
+    int p = 0;
+#pragma unroll
+    for (int q = 1; q < KGB_MAX_PEERS; ++q) p += (q < tab.n_peers && s >= tab.slot_begin[q]) ? 1 : 0;
+    const int64_t r = idx ? (int64_t)__ldg(idx + s) : s;
+    float* drow = tab.dst[p] + (tab.dst_row0[p] + (s - tab.slot_begin[p])) * ldd;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if ((gl + ch * G) >= nv) continue;
+      const int f0 = (gl + ch * G) * VEC;
+      float v[VEC];
+      ld_vec<VEC>(src + r * lds + f0, v);
+      st_vec<VEC>(drow + f0, v);
     }
   }
 }
@@ -1069,6 +1115,45 @@ int kgb_gather_rows(int device, const float* src, int64_t lds, const int32_t* id
     const int grid = grid_for(device, n_out, s.g);
     KGB_DISPATCH_SHAPE(s, (gather_rows_kernel<V, G_, N_><<<grid, 256, 0, st>>>(src + f0, lds, idx, n_out, Fs,
                                                                                scale, out + f0, ldo)));
+    KGB_CHECK_LAUNCH();
+  }
+  return KGB_OK;
+}
+
+int kgb_halo_push(int device, const kgb_halo_push_args* a, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(a != nullptr, "args is NULL");
+  KGB_REQUIRE(a->F > 0 && a->n_peers >= 1 && a->n_peers <= KGB_MAX_PEERS, "bad F / n_peers");
+  KGB_REQUIRE(a->lds >= a->F && a->ldd >= a->F, "leading dimension smaller than F");
+  PushTab tab;
+  tab.n_peers = a->n_peers;
+  bool can4 = aligned16(a->src) && a->lds % 4 == 0 && a->ldd % 4 == 0;
+  for (int p = 0; p <= a->n_peers; ++p) {
+    tab.slot_begin[p] = a->slot_begin[p];
+    KGB_REQUIRE(p == 0 ? a->slot_begin[0] == 0 : a->slot_begin[p] >= a->slot_begin[p - 1], "slot_begin must be a prefix sum");
+  }
+  for (int p = 0; p < KGB_MAX_PEERS; ++p) {
+    tab.dst[p] = p < a->n_peers ? a->dst[p] : nullptr;
+    tab.dst_row0[p] = p < a->n_peers ? a->dst_row0[p] : 0;
+    if (p < a->n_peers && a->slot_begin[p + 1] > a->slot_begin[p]) {
+      KGB_REQUIRE(a->dst[p] != nullptr && a->dst_row0[p] >= 0, "peer %d has slots but no window", p);
+      can4 = can4 && aligned16(a->dst[p]);
+    }
+  }
+  for (int p = a->n_peers + 1; p <= KGB_MAX_PEERS; ++p) tab.slot_begin[p] = a->slot_begin[a->n_peers];
+  const int64_t n_slots = a->slot_begin[a->n_peers];
+  if (n_slots == 0) return KGB_OK;
+  KGB_REQUIRE(a->src != nullptr, "src is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vec = (can4 && a->F % 4 == 0) ? 4 : 1;
+  const int slab = 32 * 4 * vec;
+  for (int f0 = 0; f0 < a->F; f0 += slab) {
+    const int Fs = (a->F - f0 < slab) ? (a->F - f0) : slab;
+    PushTab t2 = tab;
+    for (int p = 0; p < a->n_peers; ++p) if (t2.dst[p]) t2.dst[p] += f0;
+    Shape s = pick_shape(Fs, vec == 4);
+    const int grid = grid_for(device, n_slots, s.g);
+    KGB_DISPATCH_SHAPE(s, (halo_push_kernel<V, G_, N_><<<grid, 256, 0, st>>>(a->src + f0, a->lds, a->idx, Fs, a->ldd, t2)));
     KGB_CHECK_LAUNCH();
   }
   return KGB_OK;

@@ -14,10 +14,17 @@ rows by a deterministic segmented sum (kgb_gather_reduce over the CSR of send_id
 atomics.  Degrees (mean / GCN normalisation) need no communication: every in-edge of an owned
 target is local.  The conv layers accept a ``PartitionedGraph`` in place of ``edge_index``.
 
-Works with any torch.distributed backend (tests use gloo on the CPU for the plan logic; the
-exchange of CUDA tensors needs NCCL).
+Transport.  With CUDA tensors and more than one rank the halo rows do not go through NCCL send/recv: every rank
+owns a WINDOW of device memory that its peers map with CUDA IPC (``PeerWindow``), and the pack kernel
+(kgb_halo_push) stores each requested row straight into the receiver's window over NVLink.  Two tiny all-reduces on
+the communication stream order the ranks (window free / all rows landed).  ``KGB200_HALO=nccl`` (or a failed IPC
+mapping) selects ``all_to_all_single`` instead; the CPU tests use gloo for the plan logic.
 """
 from __future__ import annotations
+
+import ctypes
+import os
+import warnings
 
 import torch
 import torch.distributed as dist
@@ -30,6 +37,31 @@ def partition_bounds(n_global: int, world: int) -> list:
     b = [0]
     for r in range(world):
         b.append(b[-1] + base + (1 if r < extra else 0))
+    return b
+
+
+def check_bounds(bounds, n_global: int, world: int) -> list:
+    """Validate user-supplied contiguous ranges: world + 1 non-decreasing cuts from 0 to n_global."""
+    b = [int(v) for v in bounds]
+    if len(b) != world + 1 or b[0] != 0 or b[-1] != int(n_global) or any(b[i] > b[i + 1] for i in range(world)):
+        raise ValueError(f"bounds must be {world + 1} non-decreasing cuts from 0 to {n_global}, got {b}")
+    return b
+
+
+def cost_balanced_bounds(dst_global: torch.Tensor, n_global: int, world: int, node_weight: float = 28.0) -> list:
+    """Contiguous node ranges of ~equal cost = in-edges + node_weight * nodes.  Power-law graphs with skewed ids
+    (RMAT) give one rank most of the edges under equal node counts and most of the dense-transform rows under equal
+    edge counts; ``node_weight`` is the cost of one node's dense transforms in units of one gathered edge
+    (28 for the 256-wide SAGE step on a B200).  Every rank must pass the SAME ``dst_global`` (all edges)."""
+    deg = torch.bincount(dst_global.long(), minlength=n_global).to(torch.float64) + float(node_weight)
+    cum = torch.cumsum(deg, 0)
+    total = float(cum[-1]) if n_global else 0.0
+    targets = torch.tensor([total * r / world for r in range(1, world)], device=dst_global.device,
+                           dtype=torch.float64)
+    cuts = (torch.searchsorted(cum, targets) + 1).tolist() if world > 1 and n_global else [0] * (world - 1)
+    b = [0] + [min(int(c), n_global) for c in cuts] + [n_global]
+    for i in range(1, len(b)):
+        b[i] = max(b[i], b[i - 1])
     return b
 
 
@@ -47,9 +79,14 @@ class HaloPlan:
     """
 
     def __init__(self, src_global: torch.Tensor, dst_global: torch.Tensor, n_global: int, rank: int, world: int,
-                 group=None):
+                 group=None, bounds=None):
         self.rank, self.world, self.group = rank, world, group
-        self.bounds = partition_bounds(n_global, world)
+        self.bounds = partition_bounds(n_global, world) if bounds is None else check_bounds(bounds, n_global, world)
+        if bounds is not None and world > 1:   # every rank must cut the node range at the same places
+            theirs = [None] * world
+            dist.all_gather_object(theirs, self.bounds, group=group)
+            if any(t != self.bounds for t in theirs):
+                raise ValueError(f"rank {rank}: partition bounds differ between ranks: {theirs}")
         lo, hi = self.bounds[rank], self.bounds[rank + 1]
         self.lo, self.hi = lo, hi
         self.n_local = hi - lo
@@ -87,6 +124,33 @@ class HaloPlan:
         if want.numel() and (int(self.send_idx.min()) < 0 or int(self.send_idx.max()) >= self.n_local):
             raise RuntimeError("halo plan: a peer requested a row this rank does not own")
         self.n_send = int(self.send_idx.numel())
+        # recv_matrix[p][q] = rows rank p receives from rank q (== rows q sends to p): every rank knows where its
+        # block starts inside each peer's halo buffer (forward push) and inside each owner's send list (backward push)
+        if world > 1:
+            rm = [None] * world
+            dist.all_gather_object(rm, [int(c) for c in self.recv_counts], group=group)
+            self.recv_matrix = rm
+        else:
+            self.recv_matrix = [[0]]
+        self.any_halo = any(sum(row) > 0 for row in self.recv_matrix)   # rank-uniform: some rank needs remote rows
+
+    def push_tables(self):
+        """Index arithmetic of the peer-memory exchange (pure host logic, tested on the CPU).
+        forward  (rows of mine -> peers' halo buffers):  slots grouped by destination peer p,
+                 slot_begin = prefix(send_counts), my block starts at row sum_{q < me} recv_matrix[p][q] of p's halo;
+        backward (gradients of my halo rows -> their owners' send lists): slots grouped by owner q,
+                 slot_begin = prefix(recv_counts), my block starts at row sum_{p < me} recv_matrix[p][q] of q's list."""
+        me, W, rm = self.rank, self.world, self.recv_matrix
+        fwd_begin, bwd_begin = [0], [0]
+        for p in range(W):
+            fwd_begin.append(fwd_begin[-1] + int(self.send_counts[p]))
+            bwd_begin.append(bwd_begin[-1] + int(self.recv_counts[p]))
+        fwd_row0 = [sum(rm[p][:me]) for p in range(W)]
+        bwd_row0 = [sum(rm[p][q] for p in range(me)) for q in range(W)]
+        n_halo_all = [sum(rm[p]) for p in range(W)]
+        n_send_all = [sum(rm[p][q] for p in range(W)) for q in range(W)]
+        return {"fwd_begin": fwd_begin, "fwd_row0": fwd_row0, "bwd_begin": bwd_begin, "bwd_row0": bwd_row0,
+                "n_halo_all": n_halo_all, "n_send_all": n_send_all}
 
     def edge_index_local(self) -> torch.Tensor:
         return torch.stack([self.col_local, self.dst_local]).contiguous()
@@ -102,18 +166,127 @@ class HaloPlan:
         return ei_l, ei_h.contiguous()
 
 
+class _DeviceBytes:
+    """``__cuda_array_interface__`` view of raw device memory (the window is not torch-allocated)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PeerWindow:
+    """One symmetric window per rank: ``[halo region | back region]``, each ``rows x f_cap`` floats, allocated with
+    cudaMalloc by libkgb200 and mapped into every peer with CUDA IPC.  ``ptr[r]`` is rank r's window as seen from
+    THIS device (NVLink peer memory for r != rank)."""
+
+    def __init__(self, plan: HaloPlan, f_cap: int, device, group=None):
+        """Collective.  Every stage that can fail locally is followed by a collective that all ranks reach, so a
+        failure on one rank turns into ``self.ok == False`` on all of them instead of a hang."""
+        from . import _lib
+        lib = _lib.load()
+        self.lib, self.device, self.group, self.f_cap = lib, device, group, int(f_cap)
+        self.rank, self.world = plan.rank, plan.world
+        t = plan.push_tables()
+        self.tables = t
+        row_bytes = 4 * self.f_cap
+        self.back_off = [((t["n_halo_all"][r] * row_bytes + 255) // 256) * 256 for r in range(self.world)]
+        nbytes = self.back_off[self.rank] + max(t["n_send_all"][self.rank], 1) * row_bytes + 256
+        self.nbytes = nbytes
+        self.base, self.ptr, self._opened, self.error = None, [], [], None
+        raw = None
+        try:   # stage 1 (local): allocate + export
+            base = ctypes.c_void_p()
+            _lib.check(lib.kgb_window_alloc(device.index, nbytes, ctypes.byref(base)), "kgb_window_alloc")
+            self.base = base.value
+            handle = ctypes.create_string_buffer(64)
+            _lib.check(lib.kgb_ipc_export(device.index, self.base, handle), "kgb_ipc_export")
+            raw = bytes(handle.raw)
+        except Exception as e:  # noqa: BLE001
+            self.error = e
+        handles = [None] * self.world
+        dist.all_gather_object(handles, raw, group=group)
+        if self.error is None and all(h is not None for h in handles):
+            try:   # stage 2 (local): map the peers
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        self.ptr.append(self.base)
+                        continue
+                    p = ctypes.c_void_p()
+                    _lib.check(lib.kgb_ipc_open(device.index, h, ctypes.byref(p)), "kgb_ipc_open")
+                    self.ptr.append(p.value)
+                    self._opened.append(p.value)
+                self.local = torch.as_tensor(_DeviceBytes(self.base, nbytes), device=device)
+            except Exception as e:  # noqa: BLE001
+                self.error = e
+        elif self.error is None:
+            self.error = RuntimeError("a peer could not allocate / export its window")
+        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        ok = torch.tensor([1 if self.error is None else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        self.ok = bool(int(ok))
+
+    def barrier(self) -> None:
+        """Orders the ranks on the CURRENT stream (a one-element all-reduce; stream-ordered like every collective)."""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def halo_view(self, n_rows: int, F: int) -> torch.Tensor:
+        return self.local[:max(n_rows, 1) * F * 4].view(torch.float32).view(max(n_rows, 1), F)
+
+    def back_view(self, n_rows: int, F: int) -> torch.Tensor:
+        o = self.back_off[self.rank]
+        return self.local[o:o + max(n_rows, 1) * F * 4].view(torch.float32).view(max(n_rows, 1), F)
+
+    def push(self, src: torch.Tensor, idx, F: int, forward: bool) -> None:
+        """kgb_halo_push on the CURRENT stream: forward = my rows -> peers' halo regions, else my halo-row gradients
+        -> their owners' back regions.  Rows in the window are dense (leading dimension F)."""
+        from . import _lib
+        from .graph import _stream
+        t = self.tables
+        a = _lib.HaloPushArgs()
+        a.src, a.lds, a.idx, a.F, a.n_peers = src.data_ptr(), src.stride(0), (idx.data_ptr() if idx is not None else None), F, self.world
+        begin = t["fwd_begin"] if forward else t["bwd_begin"]
+        row0 = t["fwd_row0"] if forward else t["bwd_row0"]
+        for p in range(self.world + 1):
+            a.slot_begin[p] = begin[p]
+        for p in range(self.world):
+            a.dst[p] = self.ptr[p] + (0 if forward else self.back_off[p])
+            a.dst_row0[p] = row0[p]
+        a.ldd = F
+        _lib.check(self.lib.kgb_halo_push(self.device.index, ctypes.byref(a), _stream(self.device)), "kgb_halo_push")
+
+    def close(self) -> None:
+        from . import _lib
+        torch.cuda.synchronize(self.device)
+        for p in self._opened:
+            self.lib.kgb_ipc_close(self.device.index, p)
+        self._opened = []
+        if dist.is_initialized():
+            try:
+                dist.barrier(group=self.group)   # nobody unmaps-after-free: peers closed their mappings first
+            except Exception:  # noqa: BLE001
+                pass
+        if self.base is not None:
+            _lib.check(self.lib.kgb_window_free(self.device.index, self.base), "kgb_window_free")
+        self.base = None
+
+
 class PartitionedGraph:
     """Halo plan + device structures of one rank.  Pass it to SAGEConv / GCNConv instead of
     ``edge_index``; ``x`` is then this rank's [n_local, F] slice of the node features."""
 
     def __init__(self, src_global, dst_global, n_global: int, rank: int | None = None, world: int | None = None,
-                 group=None, n_loops_local: bool = False):
+                 group=None, n_loops_local: bool = False, bounds=None):
+        """``bounds``: optional world + 1 cuts of the node range (e.g. ``cost_balanced_bounds``), identical on every
+        rank; default: equal node counts (``partition_bounds``)."""
         from .graph import GraphStructure, build_csr
         if rank is None:
             rank = dist.get_rank(group) if dist.is_initialized() else 0
         if world is None:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.plan = HaloPlan(src_global, dst_global, n_global, rank, world, group)
+        self.plan = HaloPlan(src_global, dst_global, n_global, rank, world, group, bounds=bounds)
+        self.any_halo = self.plan.any_halo
+        self._window = None
+        self._p2p_failed = False
         p = self.plan
         self.n_local, self.n_halo, self.n_ext = p.n_local, p.n_halo, p.n_local + p.n_halo
         self.group, self.world, self.rank = group, world, rank
@@ -147,7 +320,7 @@ class PartitionedGraph:
         if self._split is None:
             from .graph import GraphStructure
             ei_l, ei_h = self.plan.split_edges()
-            g_l = GraphStructure(ei_l, self.n_local, self.n_local, 0)
+            g_l = GraphStructure(ei_l, self.n_local, self.n_local, self._n_loops)   # self-loops are local edges
             g_h = GraphStructure(ei_h, self.n_local, max(self.n_halo, 1), 0)
             deg = (g_l.csr.deg + g_h.csr.deg).to(torch.float32)
             self._split = (g_l, g_h, 1.0 / torch.clamp(deg, min=1e-8))
@@ -205,11 +378,42 @@ class PartitionedGraph:
     halo_finish = exchange_finish
 
     # ---- raw (no autograd) halves of the exchange, for nodes that schedule the overlap themselves ----
+    # ---- transport -----------------------------------------------------------------------------------------
+    def _p2p_window(self, F: int):
+        """The peer-memory window (created collectively on first use, re-created when a wider row arrives), or None
+        when the transport is NCCL (KGB200_HALO=nccl, CPU tensors, or the IPC mapping failed)."""
+        if (self.world <= 1 or self.device.type != "cuda" or self._p2p_failed
+                or os.environ.get("KGB200_HALO", "p2p").lower() == "nccl" or dist.get_backend(self.group) != "nccl"):
+            return None
+        w = self._window
+        if w is not None and F <= w.f_cap:
+            return w
+        if w is not None:
+            w.close()
+            self._window = None
+        f_cap = max(256, (int(F) + 63) // 64 * 64)
+        w = PeerWindow(self.plan, f_cap, self.device, self.group)
+        if not w.ok:   # decided collectively: all ranks fall back to the same transport
+            warnings.warn(f"keras_geometric_b200.dist: peer-memory halo window unavailable ({w.error}); "
+                          "using NCCL all_to_all")
+            w.close()
+            self._p2p_failed = True
+            return None
+        self._window = w
+        return w
+
     def halo_rows_raw(self, x_local: torch.Tensor) -> torch.Tensor:
-        """pack + all-to-all on the CURRENT stream: [n_local, F] -> [n_halo, F]."""
+        """pack + exchange on the CURRENT stream: [n_local, F] -> [n_halo, F].  With the peer-memory transport the
+        result is a view of this rank's window: valid until the next forward exchange on this graph."""
         from . import ops
         p = self.plan
         F = int(x_local.shape[1])
+        win = self._p2p_window(F)
+        if win is not None:
+            win.barrier()                                   # every rank has consumed its previous halo rows
+            win.push(x_local, p.send_idx if p.n_send else None, F, forward=True)
+            win.barrier()                                   # every rank's rows have landed
+            return win.halo_view(self.n_halo, F)
         halo = torch.empty((max(self.n_halo, 1), F), dtype=x_local.dtype, device=x_local.device)
         send = ops.gather_rows(x_local, p.send_idx) if p.n_send else x_local.new_empty((0, F))
         dist.all_to_all_single(halo[:self.n_halo], send, output_split_sizes=p.recv_counts,
@@ -217,18 +421,47 @@ class PartitionedGraph:
         return halo
 
     def halo_grad_raw(self, g_halo: torch.Tensor) -> torch.Tensor:
-        """reverse all-to-all on the CURRENT stream: [n_halo, F] gradient rows -> [n_send, F] rows at their owners
-        (to be summed per owner row with ``send_csr``)."""
+        """reverse exchange on the CURRENT stream: [n_halo, F] gradient rows -> [n_send, F] rows at their owners
+        (to be summed per owner row with ``send_csr``).  Peer-memory transport: a view of this rank's window, valid
+        until the next backward exchange on this graph."""
         p = self.plan
         F = int(g_halo.shape[1])
+        win = self._p2p_window(F)
+        if win is not None:
+            win.barrier()
+            win.push(g_halo, None, F, forward=False)
+            win.barrier()
+            return win.back_view(p.n_send, F)
         back = torch.empty((max(p.n_send, 1), F), dtype=g_halo.dtype, device=g_halo.device)
         dist.all_to_all_single(back[:p.n_send], g_halo[:self.n_halo], output_split_sizes=p.send_counts,
                                input_split_sizes=p.recv_counts, group=self.group)
         return back
 
+    def close(self) -> None:
+        """Release the peer-memory window (collective: every rank must call it)."""
+        if self._window is not None:
+            self._window.close()
+            self._window = None
+
     def exchange_vector(self, v_local: torch.Tensor) -> torch.Tensor:
         """Per-node scalar (e.g. GCN dis) -> [n_ext]; no autograd."""
         return _exchange_fwd(v_local.reshape(-1, 1).contiguous(), self).reshape(-1)
+
+    def gcn_dis_split(self):
+        """(dis [n_local], dis_halo [n_halo]): deg^-1/2 of the TOTAL in-degree (local + halo sources + self-loops) for
+        the owned rows, and the same values of the halo rows (fetched once per graph) - for the split structures."""
+        if getattr(self, "_dis_split", None) is None:
+            from . import _lib
+            from .graph import _stream
+            lib = _lib.load()
+            g_l, g_h, _ = self.split
+            deg = (g_l.csr.deg + g_h.csr.deg).contiguous()
+            dis = torch.empty(self.n_local, dtype=torch.float32, device=self.device)
+            _lib.check(lib.kgb_gcn_norm(self.device.index, deg.data_ptr(), self.n_local, None, 0, 0, dis.data_ptr(),
+                                        None, _stream(self.device)), "kgb_gcn_norm")
+            halo = self.halo_rows_raw(dis.reshape(-1, 1).contiguous())[:max(self.n_halo, 1)].reshape(-1).clone()
+            self._dis_split = (dis, halo)
+        return self._dis_split
 
     def gcn_dis_ext(self) -> torch.Tensor:
         """deg^-1/2 for local rows followed by the halo rows' values (fetched once per graph)."""
@@ -244,16 +477,23 @@ class PartitionedGraph:
 
 
 def _exchange_fwd(x_local: torch.Tensor, pg: PartitionedGraph) -> torch.Tensor:
-    from . import ops
-    p = pg.plan
     F = int(x_local.shape[1])
     x_ext = torch.empty((pg.n_ext, F), dtype=x_local.dtype, device=x_local.device)
     if pg.world > 1:
-        send = ops.gather_rows(x_local, p.send_idx) if p.n_send else x_local.new_empty((0, F))
-        dist.all_to_all_single(x_ext[pg.n_local:], send, output_split_sizes=p.recv_counts,
-                               input_split_sizes=p.send_counts, group=pg.group)
+        halo = pg.halo_rows_raw(x_local)
+        if pg.n_halo:
+            x_ext[pg.n_local:].copy_(halo[:pg.n_halo])   # out of the window: x_ext may be saved for a backward
     x_ext[:pg.n_local].copy_(x_local)
     return x_ext
+
+
+def _land(back: torch.Tensor, pg: PartitionedGraph, F: int, device, dtype) -> torch.Tensor:
+    """Deterministic per-owner sum of the returned gradient rows (CSR of the send list)."""
+    from . import _lib, ops
+    if pg.plan.n_send and pg.send_csr is not None:
+        g_local, _ = ops.gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm)
+        return g_local
+    return torch.zeros((pg.n_local, F), dtype=dtype, device=device)
 
 
 class _HaloExchange(torch.autograd.Function):
@@ -265,60 +505,45 @@ class _HaloExchange(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, g_ext):
-        from . import _lib, ops
         pg = ctx.pg
-        p = pg.plan
         g_ext = g_ext.contiguous()
         g_ext.record_stream(torch.cuda.current_stream(g_ext.device))  # produced on the compute stream
         g_local = g_ext[:pg.n_local].clone()
         if pg.world > 1:
             F = int(g_ext.shape[1])
-            back = torch.empty((p.n_send, F), dtype=g_ext.dtype, device=g_ext.device)
-            dist.all_to_all_single(back, g_ext[pg.n_local:].contiguous(), output_split_sizes=p.send_counts,
-                                   input_split_sizes=p.recv_counts, group=pg.group)
-            if p.n_send:
-                add, _ = ops.gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm)
-                g_local += add
+            back = pg.halo_grad_raw(g_ext[pg.n_local:])
+            if pg.plan.n_send:
+                g_local += _land(back, pg, F, g_ext.device, g_ext.dtype)
         return g_local, None
 
 
 class _HaloRows(torch.autograd.Function):
-    """x_local [n_local, F] -> halo [n_halo, F]: pack + all-to-all; backward = reverse all-to-all + the deterministic
+    """x_local [n_local, F] -> halo [n_halo, F]: pack + exchange; backward = reverse exchange + the deterministic
     segmented sum of the returned gradient rows into their owners (zero for rows nobody asked for)."""
 
     @staticmethod
     def forward(ctx, x_local, pg: PartitionedGraph):
-        from . import ops
         ctx.pg = pg
-        p = pg.plan
         x_local = x_local.contiguous()
         F = int(x_local.shape[1])
-        halo = torch.empty((max(pg.n_halo, 1), F), dtype=x_local.dtype, device=x_local.device)
+        if pg.world > 1:
+            halo = pg.halo_rows_raw(x_local)
+            if pg._window is not None:
+                halo = halo.clone()    # autograd-visible result must not alias the (reused) window
+        else:
+            halo = torch.zeros((max(pg.n_halo, 1), F), dtype=x_local.dtype, device=x_local.device)
         if pg.n_halo == 0:
             halo.zero_()
-        if pg.world > 1:
-            send = ops.gather_rows(x_local, p.send_idx) if p.n_send else x_local.new_empty((0, F))
-            dist.all_to_all_single(halo[:pg.n_halo], send, output_split_sizes=p.recv_counts,
-                                   input_split_sizes=p.send_counts, group=pg.group)
         return halo
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g_halo):
-        from . import _lib, ops
         pg = ctx.pg
-        p = pg.plan
         g_halo = g_halo.contiguous()
         g_halo.record_stream(torch.cuda.current_stream(g_halo.device))  # produced on the compute stream
         F = int(g_halo.shape[1])
-        if pg.world > 1 and p.n_send:
-            back = torch.empty((p.n_send, F), dtype=g_halo.dtype, device=g_halo.device)
-            dist.all_to_all_single(back, g_halo[:pg.n_halo], output_split_sizes=p.send_counts,
-                                   input_split_sizes=p.recv_counts, group=pg.group)
-            g_local, _ = ops.gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm)
-        else:
-            if pg.world > 1:
-                dist.all_to_all_single(g_halo.new_empty((0, F)), g_halo[:pg.n_halo], output_split_sizes=p.send_counts,
-                                       input_split_sizes=p.recv_counts, group=pg.group)
-            g_local = torch.zeros((pg.n_local, F), dtype=g_halo.dtype, device=g_halo.device)
-        return g_local, None
+        if pg.world > 1:
+            back = pg.halo_grad_raw(g_halo)
+            return _land(back, pg, F, g_halo.device, g_halo.dtype), None
+        return torch.zeros((pg.n_local, F), dtype=g_halo.dtype, device=g_halo.device), None

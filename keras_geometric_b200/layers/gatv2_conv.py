@@ -86,7 +86,7 @@ class GATv2Conv(MessagePassing):
         x = to_device_tensor(x, what="x")
         if x.dtype != torch.float32:
             x = x.to(torch.float32)
-        if bool(pg.graph.n_loops) != bool(self.add_self_loops_flag):
+        if bool(pg._n_loops) != bool(self.add_self_loops_flag):
             raise ValueError("PartitionedGraph(n_loops_local=...) must match GATv2Conv(add_self_loops=...)")
         if self.dropout_layer is not None and training:
             raise NotImplementedError("partitioned GATv2Conv does not support attention dropout")

@@ -154,10 +154,14 @@ class GCNConv(MessagePassing):
         ``pg`` must have been built with ``n_loops_local=self.add_self_loops``."""
         if self.dropout_rate > 0 and training:
             raise NotImplementedError("partitioned GCNConv does not support message dropout")
-        if bool(pg.graph.n_loops) != bool(self.add_self_loops):
+        if bool(pg._n_loops) != bool(self.add_self_loops):
             raise ValueError("PartitionedGraph(n_loops_local=...) must match GCNConv(add_self_loops=...)")
         kernel, bias = value_of(self.kernel), value_of(self.bias) if self.use_bias else None
-        h_ext = pg.exchange(ops.linear(x, kernel))
+        h = ops.linear(x, kernel)
+        if pg.world > 1 and pg.any_halo:
+            # local-source edges (and the self-loops) are reduced while the transformed halo rows are in flight
+            return ops.aggregate_partitioned(h, pg, "gcn" if self.normalize else "sum", bias=bias)
+        h_ext = pg.exchange(h)
         weight = None
         if self.normalize:
             dis_local, dis_ext = pg.gcn_dis_ext()

@@ -121,7 +121,7 @@ class GINConv(MessagePassing):
                 and self._uses_default("pre_aggregate", "aggregate", "post_update")):
             raise NotImplementedError("partitioned GINConv supports the default message/aggregate/update hooks")
         eps = value_of(self.eps) if self.train_eps else float(self.eps_init)
-        if self.aggregator in ("sum", "mean") and pg.world > 1 and pg.n_halo > 0 and int(x.shape[0]) > 0:
+        if self.aggregator in ("sum", "mean") and pg.world > 1 and pg.any_halo:   # rank-uniform choice of the path
             g_local, g_halo, inv_deg = pg.split
             scale = (None, inv_deg) if self.aggregator == "mean" else None
             halo = pg.halo_start(x)

@@ -229,7 +229,7 @@ class SAGEConv(MessagePassing):
         act_is_none = self._activation_id in (None, "linear")
         linear_agg = self.actual_aggregator in ("mean", "sum")
         fuse_act = act_is_relu or act_is_none
-        if linear_agg and pg.world > 1 and pg.n_halo > 0 and int(x.shape[0]) > 0:
+        if linear_agg and pg.world > 1 and pg.any_halo:   # rank-uniform choice of the path (collectives stay matched)
             # local-source edges are reduced while the halo rows are in flight; the halo part is added on top
             g_local, g_halo, inv_deg = pg.split
             scale = (None, inv_deg) if self.actual_aggregator == "mean" else None

@@ -651,7 +651,7 @@ def linear(x, w, addend=None, bias=None, act=None) -> torch.Tensor:
 def sage_layer_ok(x: torch.Tensor, w_neigh: torch.Tensor, w_self: torch.Tensor) -> bool:
     """Shapes the one-node SAGE layer (``sage_layer``) covers: everything on the hand-written tcgen05 kernels."""
     M, K, N = int(x.shape[0]), int(x.shape[1]), int(w_neigh.shape[1])
-    return (_gemm_ok(x, w_neigh, w_self) and M >= 1 and K <= _TC_SLAB and N <= _TC_SLAB
+    return (_gemm_ok(x, w_neigh, w_self) and M >= 0 and K <= _TC_SLAB and N <= _TC_SLAB
             and tuple(w_self.shape) == tuple(w_neigh.shape))
 
 
@@ -867,6 +867,80 @@ class _SagePartitioned(torch.autograd.Function):
             gx = linear_tc(g, hi, lo, K, c=gx)
             gx = land(back, gx)
         return gx, g_wn, g_ws, g_bias, None, None, None, None
+
+
+class _AggregatePartitioned(torch.autograd.Function):
+    """out = act(out_scale * sum_j src_scale_j * x_j + bias) over a 1-D node partition as ONE autograd node: a linear
+    aggregation (sum / mean / GCN-normalised sum) whose halo rows travel on the communication stream while the
+    local-source edges are reduced; in the backward the halo gradients are produced first and travel back while the
+    local transposed gather runs.  ``scales`` = (src_local [n_local] | None, src_halo [n_halo] | None,
+    dst [n_local] | None)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, pg, scales, relu: bool):
+        x = _f32c(x, "x")
+        g_l, g_h, _ = pg.split
+        s_loc, s_halo, s_dst = scales
+        bias_c = _f32c(bias, "bias").contiguous() if bias is not None else None
+        dev = x.device
+        cur, cs = torch.cuda.current_stream(dev), pg._comm_stream()
+        cs.wait_stream(cur)
+        with torch.cuda.stream(cs):
+            halo = pg.halo_rows_raw(x)
+        x.record_stream(cs)
+        part, _ = gather_reduce_raw(x, g_l.csr, _lib.OP_SUM, src_scale=s_loc, out_scale=s_dst)
+        cur.wait_stream(cs)
+        halo.record_stream(cur)
+        out, _ = gather_reduce_raw(halo, g_h.csr, _lib.OP_SUM, src_scale=s_halo, out_scale=s_dst, addend=part,
+                                   bias=bias_c, act=_lib.ACT_RELU if relu else _lib.ACT_NONE)
+        ctx.pg, ctx.scales, ctx.relu, ctx.has_bias = pg, scales, relu, bias is not None
+        ctx.save_for_backward(*([out] if relu else []))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        pg = ctx.pg
+        g_l, g_h, _ = pg.split
+        s_loc, s_halo, s_dst = ctx.scales
+        g = _f32c(g, "grad")
+        out = ctx.saved_tensors[0] if ctx.relu else None
+        g_bias = None
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            g, g_bias = relu_bwd_colsum(g, out)
+        elif ctx.relu:
+            g = relu_bwd(g, out)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            dev = g.device
+            cur, cs = torch.cuda.current_stream(dev), pg._comm_stream()
+            # transposed: the targets' rows are gathered (scaled by the per-target factor), the sources' rows written
+            g_halo, _ = gather_reduce_raw(g, g_h.csc, _lib.OP_SUM, src_scale=s_dst, out_scale=s_halo)
+            cs.wait_stream(cur)
+            with torch.cuda.stream(cs):
+                back = pg.halo_grad_raw(g_halo)
+            g_halo.record_stream(cs)
+            gx, _ = gather_reduce_raw(g, g_l.csc, _lib.OP_SUM, src_scale=s_dst, out_scale=s_loc)
+            cur.wait_stream(cs)
+            back.record_stream(cur)
+            if pg.send_csr is not None:
+                gx, _ = gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm, addend=gx)
+        return gx, g_bias, None, None, None
+
+
+def aggregate_partitioned(x, pg, op: str = "sum", bias=None, relu: bool = False) -> torch.Tensor:
+    """Linear neighbourhood aggregation of this rank's rows on a partitioned graph (``keras_geometric_b200.dist``):
+    ``op`` in "sum", "mean", "gcn" (symmetric normalisation with the total in-degree, utils/main.py:20-33)."""
+    if op == "sum":
+        scales = (None, None, None)
+    elif op == "mean":
+        scales = (None, None, pg.split[2])
+    elif op == "gcn":
+        dis, dis_halo = pg.gcn_dis_split()
+        scales = (dis, dis_halo, dis)
+    else:
+        raise ValueError(f"aggregate_partitioned: unsupported aggregation {op!r}")
+    return _AggregatePartitioned.apply(x, bias, pg, scales, relu)
 
 
 def sage_partitioned(x, w_neigh, w_self, bias, pg, op: str, relu: bool, reorder: bool) -> torch.Tensor:

@@ -76,6 +76,35 @@ def _worker(rank, world, port, n, e, F, seed, q):
         for i_, g_ in zip(all_ids, all_g):
             np.add.at(tot, i_, g_)
         np.testing.assert_allclose(g_local.numpy(), tot[lo:hi], rtol=1e-5, atol=1e-5)
+        # peer-memory transport: the push tables place every rank's block at the right rows of the receiver's window
+        # (host emulation: each rank publishes what kgb_halo_push would store where, the receiver assembles it)
+        t = plan.push_tables()
+        assert t["fwd_begin"][-1] == plan.n_send and t["bwd_begin"][-1] == plan.n_halo
+        assert t["n_halo_all"][rank] == plan.n_halo and t["n_send_all"][rank] == plan.n_send
+        sends = [(p, t["fwd_row0"][p], x_local[plan.send_idx[t["fwd_begin"][p]:t["fwd_begin"][p + 1]].long()].numpy())
+                 for p in range(world)]
+        g_halo = g_ext[plan.n_local:]
+        backs = [(o, t["bwd_row0"][o], g_halo[t["bwd_begin"][o]:t["bwd_begin"][o + 1]].numpy()) for o in range(world)]
+        all_sends, all_backs = [None] * world, [None] * world
+        dist.all_gather_object(all_sends, sends)
+        dist.all_gather_object(all_backs, backs)
+        win_halo = np.full((plan.n_halo, F), np.nan, np.float32)
+        win_back = np.full((plan.n_send, F), np.nan, np.float32)
+        for blocks in all_sends:
+            dest, row0, rows = blocks[rank]
+            win_halo[row0:row0 + len(rows)] = rows
+        for blocks in all_backs:
+            dest, row0, rows = blocks[rank]
+            win_back[row0:row0 + len(rows)] = rows
+        np.testing.assert_array_equal(win_halo, recv.numpy())    # same rows, same order as the all_to_all
+        np.testing.assert_array_equal(win_back, back.numpy())
+        # user-supplied ranges: validated, identical on all ranks, and the plan follows them
+        from keras_geometric_b200.dist import check_bounds, cost_balanced_bounds
+        cb = cost_balanced_bounds(torch.from_numpy(ei[1]), n, world, node_weight=2.0)
+        assert check_bounds(cb, n, world) == cb
+        mine2 = (ei[1] >= cb[rank]) & (ei[1] < cb[rank + 1])
+        plan2 = HaloPlan(torch.from_numpy(ei[0][mine2]), torch.from_numpy(ei[1][mine2]), n, rank, world, bounds=cb)
+        assert plan2.n_local == cb[rank + 1] - cb[rank]
         q.put((rank, "ok"))
     except Exception as ex:  # noqa: BLE001
         import traceback
@@ -97,6 +126,18 @@ def test_halo_plan_gloo(world, n, e):
         p.join(timeout=60)
     for rank, msg in res:
         assert msg == "ok", f"rank {rank}: {msg}"
+
+
+def test_bounds_validation():
+    from keras_geometric_b200.dist import check_bounds, cost_balanced_bounds
+    assert check_bounds([0, 3, 10], 10, 2) == [0, 3, 10]
+    for bad in ([0, 11, 10], [1, 3, 10], [0, 3, 9], [0, 10]):
+        with pytest.raises(ValueError, match="bounds must be"):
+            check_bounds(bad, 10, 2)
+    dst = torch.tensor([0] * 50 + list(range(1, 11)))          # node 0 is a hub
+    b = cost_balanced_bounds(dst, 11, 2, node_weight=1.0)
+    assert b[0] == 0 and b[-1] == 11 and b[1] <= 2              # the hub's range is short
+    assert cost_balanced_bounds(dst, 11, 1) == [0, 11]
 
 
 def test_partition_bounds():
