@@ -1,10 +1,16 @@
 """Multi-GPU arm of bench.py: the C4 model on a graph `world` times larger (weak scaling), 1-D
 node-partitioned with a halo exchange before every aggregation (keras_geometric_b200.dist).
-One process per GPU (torchrun); NCCL over NVLink; timing = max over ranks of CUDA-event time."""
+One process per GPU (torchrun); halo rows travel through peer-memory windows over NVLink (kgb_halo_push), NCCL
+carries the barriers and the weight-gradient all-reduce; timing = max over ranks of CUDA-event time.
+
+Before anything is timed every rank runs the partitioned layers on a small RMAT graph and rank 0 compares outputs
+and gradients with the CPU oracle (`parity_check`); the run exits non-zero if that fails.  After the timed steps the
+line gets a `c5_strong` block: BASELINE configs[4] (100 M nodes / 1 B edges, F = 64) strong-scaled over the ranks."""
 from __future__ import annotations
 
 import json
 import os
+import sys
 
 import torch
 import torch.distributed as dist
@@ -13,41 +19,37 @@ import torch.distributed as dist
 NODE_WEIGHT = 28  # cost of one node (dense transforms) in units of one edge (gather), measured on C4
 
 
-def edge_balanced_bounds(dst: torch.Tensor, n_global: int, world: int) -> list:
-    """Contiguous node ranges of ~equal cost = in-edges + NODE_WEIGHT * nodes (RMAT ids are heavily skewed,
-    so equal node counts would give one rank most of the edges and equal edge counts most of the GEMM rows)."""
-    deg = torch.bincount(dst.long(), minlength=n_global) + NODE_WEIGHT
-    cum = torch.cumsum(deg, 0)
-    total = int(cum[-1])
-    targets = torch.tensor([total * r // world for r in range(1, world)], device=dst.device)
-    cuts = (torch.searchsorted(cum, targets) + 1).tolist() if world > 1 else []
-    return [0] + [min(int(c), n_global) for c in cuts] + [n_global]
-
-
 def run(args, world, rank, local_rank):
     from bench import C4, RMAT, ClockSampler, build_model, cross_entropy, rmat_edge_index
+    import bench_extra
     from keras_geometric_b200 import _lib, ops
-    from keras_geometric_b200.dist import PartitionedGraph
+    from keras_geometric_b200.dist import PartitionedGraph, cost_balanced_bounds
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+
+    parity = bench_extra.parity_check(world, rank, dev)      # partitioned layers vs the CPU oracle (rank 0's host)
+    if not parity["ok"]:
+        if rank == 0:
+            print(json.dumps({"error": "partitioned path failed the oracle parity check", "parity_check": parity}))
+        dist.destroy_process_group()
+        sys.exit(1)
+
     cfg = dict(C4)
     div = max(1, args.scale_div)
     n_global = cfg["nodes"] // div * world
     e_global = cfg["edges"] // div * world // 2 * 2
     scale = cfg["rmat_scale"] - (div.bit_length() - 1) + (world - 1).bit_length()
     ei = rmat_edge_index(n_global, e_global, scale, 0, dev)   # every rank generates the same global list
-    bounds = edge_balanced_bounds(ei[1], n_global, world)
+    bounds = cost_balanced_bounds(ei[1], n_global, world, NODE_WEIGHT)
     lo, hi = bounds[rank], bounds[rank + 1]
     mine = (ei[1] >= lo) & (ei[1] < hi)
     src, dst = ei[0][mine].clone(), ei[1][mine].clone()
     del ei, mine
     torch.cuda.empty_cache()
-    import keras_geometric_b200.dist as kd
-    kd.partition_bounds = lambda n, w, _b=bounds: _b   # edge-balanced ranges instead of equal node counts
-    pg = PartitionedGraph(src, dst, n_global, rank, world)
+    pg = PartitionedGraph(src, dst, n_global, rank, world, bounds=bounds)
     e_local = int(src.numel())
     del src, dst
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -80,26 +82,37 @@ def run(args, world, rank, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = lib.kgb_launch_count()
+    retries0 = torch.cuda.memory_stats(dev).get("num_alloc_retries", 0)
     ops.PROFILE = []
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     torch.cuda.synchronize()
-    t0.record()
-    for _ in range(args.steps):
+    marks[0].record()
+    for i in range(args.steps):
         loss = step()
-    t1.record()
+        marks[i + 1].record()
     torch.cuda.synchronize()
     dist.barrier()
     launches = lib.kgb_launch_count() - l0
     prof, ops.PROFILE = ops.PROFILE, None
     clocks = sampler.stop()
-    ms = torch.tensor([t0.elapsed_time(t1) / args.steps], device=dev)
+    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
+    ms = torch.tensor([marks[0].elapsed_time(marks[-1]) / args.steps], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms)
-    stats = torch.tensor([pg.n_local, pg.n_halo, e_local, pg.plan.n_send], device=dev, dtype=torch.float64)
+    stats = torch.tensor([pg.n_local, pg.n_halo, e_local, pg.plan.n_send,
+                          torch.cuda.memory_stats(dev).get("num_alloc_retries", 0) - retries0,
+                          torch.cuda.max_memory_allocated(dev) / 2 ** 30, min(per_step), max(per_step)],
+                         device=dev, dtype=torch.float64)
     allstats = [torch.zeros_like(stats) for _ in range(world)]
     dist.all_gather(allstats, stats)
     n_layers = len(layers)
     value = n_layers * e_global / (ms_step * 1e-3) / 1e9
+    transport = "peer-memory windows (CUDA IPC + kgb_halo_push over NVLink)" if pg._window is not None else \
+        "NCCL all_to_all_single"
+    pg.close()
+    del pg, x, y, layers, params, opt
+    torch.cuda.empty_cache()
+    c5 = bench_extra.c5_strong(world, rank, dev) if not args.no_c5 else None
     if rank == 0:
         g = {}
         for rec in prof:
@@ -113,25 +126,37 @@ def run(args, world, rank, local_rank):
                        "frac": v[1] / v[0] / 1e6 / peak} for k, v in g.items()}
         dom = max(g, key=lambda k: g[k][0]) if g else None
         halo_rows = [int(s[1]) for s in allstats]
+        send_rows = [int(s[3]) for s in allstats]
         # bytes a rank receives per step: layer widths 100 / 256 / 48 forward, 256 / 48 backward (reverse direction)
         widths_fwd, widths_bwd = [100, 256, 48], [256, 48]
-        halo_bytes = max(halo_rows) * 4 * (sum(widths_fwd) + sum(widths_bwd))
+        recv_b = [4 * (h * sum(widths_fwd) + s * sum(widths_bwd)) for h, s in zip(halo_rows, send_rows)]
+        send_b = [4 * (s * sum(widths_fwd) + h * sum(widths_bwd)) for h, s in zip(halo_rows, send_rows)]
+        link_bytes = max(max(recv_b), max(send_b))
         print(json.dumps({
             "metric": "aggregated edges/sec per layer fwd+bwd", "value": value, "unit": "GTEPS", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C4 x {world}: 3-layer SAGEConv(mean) 100->256->256->47, RMAT graph 1-D "
-                                   "node-partitioned (cost-balanced ranges), NCCL all_to_all halo exchange per layer overlapped "
-                                   "with the local-source part of the aggregation and the weight-gradient GEMMs",
+                                   "node-partitioned (cost-balanced ranges), halo rows pushed into the receivers' "
+                                   "windows before every aggregation, overlapped with the local-source part of the "
+                                   "aggregation and the weight-gradient GEMMs",
                        "nodes": n_global, "edges": e_global, "layers": n_layers, "rmat": list(RMAT), "seed": 0,
+                       "halo_transport": transport,
                        "per_rank": {"n_local": [int(s[0]) for s in allstats], "n_halo": halo_rows,
-                                    "edges": [int(s[2]) for s in allstats], "n_send": [int(s[3]) for s in allstats]},
+                                    "edges": [int(s[2]) for s in allstats], "n_send": send_rows,
+                                    "alloc_retries_in_timed_region": [int(s[4]) for s in allstats],
+                                    "peak_mem_GiB": [round(float(s[5]), 1) for s in allstats],
+                                    "step_ms_min": [round(float(s[6]), 2) for s in allstats],
+                                    "step_ms_max": [round(float(s[7]), 2) for s in allstats]},
                        "l2": "per-rank inputs exceed the 126 MB L2"},
+            "parity_check": parity,
             "roofline": ({"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak,
-                          "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None} if dom else None),
+                          "unit": "GB/s", "frac": kernels[dom]["frac"], "alg_frac": kernels[dom]["frac"],
+                          "traffic": None} if dom else None),
             "kernels": kernels, "gpu_launches": int(launches), "clocks": clocks,
-            "halo": {"max_rows_per_rank": max(halo_rows), "bytes_received_per_step_max_rank": halo_bytes,
-                     "nvlink_floor_ms_at_770GBps": halo_bytes / 770e9 * 1e3},
+            "halo": {"max_rows_per_rank": max(halo_rows), "bytes_per_step_busiest_direction": link_bytes,
+                     "nvlink_floor_ms_at_770GBps": link_bytes / 770e9 * 1e3},
+            "c5_strong": c5,
             "e2e": {"value": value, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "note": "multi-GPU arm keeps the partitioned inputs resident; the host-buffer e2e figure is "
                             "reported by the 1-GPU run"},

@@ -270,19 +270,20 @@ int kgb_gatv2_fwd(int device, const float* hsrc, const float* hdst, int64_t n_sr
 /* Backward, pass 1 over the forward CSR (per target): g_hdst[i] (written), r[i,h] =
  * sum_c g[i,h,c] * agg[i,h,c] (written, workspace [n_dst,H]) and the attention-vector
  * gradient partials g_att_part [n_parts, H*C] (n_parts from kgb_gatv2_bwd_parts()).
- * `agg` is the forward output WITHOUT bias. */
+ * `agg` is the forward output; `bias` (optional) is the vector the forward fused into it (subtracted again). */
 int kgb_gatv2_bwd_parts(int device, int64_t n_dst, int32_t H, int32_t C);
 int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float* hsrc,
                       const float* hdst, int64_t n_src, int64_t n_dst, int32_t H, int32_t C,
                       const float* att, float slope, const int64_t* rowptr, const int32_t* col,
-                      const float* rowmax, const float* rowden,
+                      const float* rowmax, const float* rowden, const float* bias,
                       float* g_hdst, float* r, float* g_att_part, int32_t n_parts,
                       const kgb_hub_table* hubs, kgb_stream_t stream);
-/* Backward, pass 2 over the transposed structure (per source): g_hsrc[j] (written). */
+/* Backward, pass 2 over the transposed structure (per source): g_hsrc[j] (written) = per-source gradient
+ * (+ addend[j], optional [n_src, H*C]: on a square graph the per-target part g_hdst, saving a pass). */
 int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float* hdst,
                       int64_t n_src, int64_t n_dst, int32_t H, int32_t C, const float* att,
                       float slope, const int64_t* colptr, const int32_t* row,
-                      const float* rowmax, const float* rowden, const float* r,
+                      const float* rowmax, const float* rowden, const float* r, const float* addend,
                       float* g_hsrc, const kgb_hub_table* hubs, kgb_stream_t stream);
 /* out[f] = sum_p part[p,f]  in fixed order (deterministic reduction of partials). */
 int kgb_reduce_parts(int device, const float* part, int32_t n_parts, int32_t F, float* out,

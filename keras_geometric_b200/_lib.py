@@ -102,10 +102,10 @@ SIGNATURES = {
     "kgb_gatv2_bwd_parts": (c_int, [c_int, c_int64, c_int32, c_int32]),
     "kgb_gatv2_bwd_dst": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
                                   c_int32, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_int32, POINTER(HubTable), c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_int32, POINTER(HubTable), c_void_p]),
     "kgb_gatv2_bwd_src": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
                                   c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  POINTER(HubTable), c_void_p]),
+                                  c_void_p, POINTER(HubTable), c_void_p]),
     "kgb_reduce_parts": (c_int, [c_int, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "kgb_linear_tc_rows": (c_int32, [c_int32]),
     "kgb_split_tf32": (c_int, [c_int, c_void_p, c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),

@@ -33,7 +33,7 @@ struct GatP {
   const float* bias;
   float* out; float* rowmax; float* rowden;
   // backward
-  const float* g; const float* agg; const float* r_in;
+  const float* g; const float* agg; const float* r_in; const float* addend;
   float* g_hdst; float* r_out; float* g_att_part; float* g_hsrc;
   // hub table of the structure being walked + workspaces
   const int32_t* hub_row; const int32_t* hub_chunk_base; const int32_t* hub_nchunks; const int32_t* chunk_hub;
@@ -325,7 +325,11 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
                                                    int64_t k0, int64_t k1, float (&ghi)[CC][VEC],
                                                    float (&ga)[CC][VEC]) {
   constexpr int G = LPH * HPG;
-  constexpr int U = (G < 4) ? G : 4;
+#ifndef KGB_GAT_U_DST
+#define KGB_GAT_U_DST 4
+#endif
+  constexpr int UMAX = (KGB_GAT_U_DST / CC) < 1 ? 1 : (KGB_GAT_U_DST / CC);
+  constexpr int U = (G < UMAX) ? G : UMAX;
   const int HC = p.H * p.C;
   float hi[CC][VEC], gi[CC][VEC];
   float rpart = 0.f;
@@ -335,6 +339,12 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
     ld_vec<VEC>(p.hdst + row * HC + L.off[cc], hi[cc]);
     ld_vec<VEC>(p.g + row * HC + L.off[cc], gi[cc]);
     ld_vec<VEC>(p.agg + row * HC + L.off[cc], ag);
+    if (p.bias) {  // `agg` is the forward output: take the fused bias off again
+      float b[VEC];
+      ld_vec<VEC>(p.bias + L.off[cc], b);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) ag[e] -= b[e];
+    }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       if (!L.on[cc]) gi[cc][e] = 0.f;
@@ -397,8 +407,14 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
   return r;
 }
 
+#ifndef KGB_GAT_MINB_DST
+#define KGB_GAT_MINB_DST 2
+#endif
+#ifndef KGB_GAT_MINB_SRC
+#define KGB_GAT_MINB_SRC 2
+#endif
 template <int VEC, int LPH, int CC, int HPG>
-__global__ void __launch_bounds__(256, 2) gatv2_bwd_dst_kernel(const GatP p) {
+__global__ void __launch_bounds__(256, KGB_GAT_MINB_DST) gatv2_bwd_dst_kernel(const GatP p) {
   using Ctx = LaneCtx<VEC, LPH, CC, HPG>;
   constexpr int G = Ctx::G;
   constexpr int SLOTS = G * CC * VEC;  // floats of the att gradient one group covers
@@ -466,7 +482,11 @@ template <int VEC, int LPH, int CC, int HPG>
 __device__ __forceinline__ void gat_bwd_src_range(const GatP& p, const LaneCtx<VEC, LPH, CC, HPG>& L, int64_t row,
                                                   int64_t k0, int64_t k1, float (&ghj)[CC][VEC]) {
   constexpr int G = LPH * HPG;
-  constexpr int U = (G < 2) ? G : 2;
+#ifndef KGB_GAT_U_SRC
+#define KGB_GAT_U_SRC 2
+#endif
+  constexpr int UMAX = (KGB_GAT_U_SRC / CC) < 1 ? 1 : (KGB_GAT_U_SRC / CC);
+  constexpr int U = (G < UMAX) ? G : UMAX;
   const int HC = p.H * p.C;
   float hj[CC][VEC];
 #pragma unroll
@@ -531,7 +551,7 @@ __device__ __forceinline__ void gat_bwd_src_range(const GatP& p, const LaneCtx<V
 }
 
 template <int VEC, int LPH, int CC, int HPG>
-__global__ void __launch_bounds__(256, 2) gatv2_bwd_src_kernel(const GatP p) {
+__global__ void __launch_bounds__(256, KGB_GAT_MINB_SRC) gatv2_bwd_src_kernel(const GatP p) {
   using Ctx = LaneCtx<VEC, LPH, CC, HPG>;
   constexpr int G = Ctx::G;
   Ctx L;
@@ -550,8 +570,16 @@ __global__ void __launch_bounds__(256, 2) gatv2_bwd_src_kernel(const GatP p) {
         float ghj[CC][VEC];
         gat_bwd_src_range<VEC, LPH, CC, HPG>(p, L, row, rs, re, ghj);
 #pragma unroll
-        for (int cc = 0; cc < CC; ++cc)
-          if (L.on[cc]) st_vec<VEC>(p.g_hsrc + row * HC + L.off[cc], ghj[cc]);
+        for (int cc = 0; cc < CC; ++cc) {
+          if (!L.on[cc]) continue;
+          if (p.addend) {  // square graph: + the per-target part of the same node's gradient (one pass less)
+            float ad[VEC];
+            ld_vec<VEC>(p.addend + row * HC + L.off[cc], ad);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) ghj[cc][e] += ad[e];
+          }
+          st_vec<VEC>(p.g_hsrc + row * HC + L.off[cc], ghj[cc]);
+        }
       });
   gat_queue_reset(p);
 }
@@ -566,7 +594,9 @@ __global__ void __launch_bounds__(256) gat_sum_finish_kernel(const GatP p, float
     const int nch = __ldg(p.hub_nchunks + h);
     float s = 0.f;
     for (int c = 0; c < nch; ++c) s += p.partial[(base + c) * HC + f];
-    out[(int64_t)__ldg(p.hub_row + h) * HC + f] = s;
+    const int64_t o = (int64_t)__ldg(p.hub_row + h) * HC + f;
+    if (p.addend) s += p.addend[o];
+    out[o] = s;
   }
 }
 
@@ -721,8 +751,8 @@ int kgb_gatv2_bwd_parts(int device, int64_t n_dst, int32_t H, int32_t C) {
 int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float* hsrc, const float* hdst,
                       int64_t n_src, int64_t n_dst, int32_t H, int32_t C, const float* att, float slope,
                       const int64_t* rowptr, const int32_t* col, const float* rowmax, const float* rowden,
-                      float* g_hdst, float* r, float* g_att_part, int32_t n_parts, const kgb_hub_table* hubs,
-                      kgb_stream_t stream) {
+                      const float* bias, float* g_hdst, float* r, float* g_att_part, int32_t n_parts,
+                      const kgb_hub_table* hubs, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(H > 0 && C > 0 && n_dst >= 0 && n_parts > 0, "bad sizes");
   KGB_REQUIRE(g_att_part, "g_att_part is NULL");
@@ -733,7 +763,7 @@ int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float*
   GatP p = {};
   p.hsrc = hsrc; p.hdst = hdst; p.n_src = n_src; p.n_dst = n_dst; p.H = H; p.C = C; p.att = att; p.slope = slope;
   p.rowptr = rowptr; p.col = col; p.rowmax = const_cast<float*>(rowmax); p.rowden = const_cast<float*>(rowden);
-  p.g = g; p.agg = agg; p.g_hdst = g_hdst; p.r_out = r; p.g_att_part = g_att_part;
+  p.g = g; p.agg = agg; p.bias = bias; p.g_hdst = g_hdst; p.r_out = r; p.g_att_part = g_att_part;
   p.n_rows = n_dst;
   gat_set_hubs(p, hubs);
   return gat_run(device, GAT_BWD_DST, p, st, 4, n_parts, g_hdst);
@@ -742,7 +772,7 @@ int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float*
 int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float* hdst, int64_t n_src,
                       int64_t n_dst, int32_t H, int32_t C, const float* att, float slope, const int64_t* colptr,
                       const int32_t* row, const float* rowmax, const float* rowden, const float* r,
-                      float* g_hsrc, const kgb_hub_table* hubs, kgb_stream_t stream) {
+                      const float* addend, float* g_hsrc, const kgb_hub_table* hubs, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(H > 0 && C > 0 && n_src >= 0, "bad sizes");
   if (n_src == 0) return KGB_OK;
@@ -750,7 +780,7 @@ int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float
   GatP p = {};
   p.hsrc = hsrc; p.hdst = hdst; p.n_src = n_src; p.n_dst = n_dst; p.H = H; p.C = C; p.att = att; p.slope = slope;
   p.rowptr = colptr; p.col = row; p.rowmax = const_cast<float*>(rowmax); p.rowden = const_cast<float*>(rowden);
-  p.g = g; p.r_in = r; p.g_hsrc = g_hsrc;
+  p.g = g; p.r_in = r; p.addend = addend; p.g_hsrc = g_hsrc;
   p.n_rows = n_src;
   gat_set_hubs(p, hubs);
   return gat_run(device, GAT_BWD_SRC, p, (cudaStream_t)stream, 4, 0, g_hsrc);

@@ -391,7 +391,7 @@ class PartitionedGraph:
         if w is not None:
             w.close()
             self._window = None
-        f_cap = max(256, (int(F) + 63) // 64 * 64)
+        f_cap = max(64, (int(F) + 63) // 64 * 64)
         w = PeerWindow(self.plan, f_cap, self.device, self.group)
         if not w.ok:   # decided collectively: all ranks fall back to the same transport
             warnings.warn(f"keras_geometric_b200.dist: peer-memory halo window unavailable ({w.error}); "

@@ -25,6 +25,37 @@ def _algorithmic_bytes(nnz, n_rows, F, per_edge_extra, per_row_extra):
     return nnz * (4 * F + 4 + per_edge_extra) + n_rows * (4 * F + per_row_extra) + (n_rows + 1) * 8
 
 
+class _prof:
+    """``with _prof(label, algorithmic_bytes, device):`` records the launch(es) inside it in PROFILE (CUDA events on
+    the launching stream) when profiling is on; free otherwise."""
+
+    __slots__ = ("rec", "dev")
+
+    def __init__(self, label: str, nbytes: int, dev):
+        self.rec = None
+        if PROFILE is not None:
+            self.rec = {"label": label, "bytes": int(nbytes), "start": torch.cuda.Event(enable_timing=True),
+                        "end": torch.cuda.Event(enable_timing=True)}
+            self.dev = dev
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.rec["start"].record(torch.cuda.current_stream(self.dev))
+        return self
+
+    def __exit__(self, *exc):
+        if self.rec is not None:
+            self.rec["end"].record(torch.cuda.current_stream(self.dev))
+            if exc[0] is None and PROFILE is not None:
+                PROFILE.append(self.rec)
+        return False
+
+
+def gat_bytes(nnz: int, n: int, H: int, C: int) -> int:
+    """B_fwd(gatv2) = E'(4HC + 4) + N*4HC (h_i) + N*4HC (out) + N*H*8 (max, denom) + (N+1)*8."""
+    return nnz * (4 * H * C + 4) + 2 * n * 4 * H * C + n * H * 8 + (n + 1) * 8
+
+
 def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
     require_cuda(t, what)
     if t.dtype != torch.float32:
@@ -100,10 +131,13 @@ def _max_bwd(g, arg, out, x, csr: Csr, col, op: int, n_src_rows: int):
         hubs = csr.hub_table(lib.kgb_gather_max_bwd_workspace_bytes(csr.n_hubs, csr.n_chunks, F), st)
         # fixed-point accumulators of the deterministic scatter (freed right after the call; stream-ordered)
         acc = torch.empty(lib.kgb_gather_max_bwd_acc_bytes(n_src_rows, F), dtype=torch.uint8, device=g.device)
-        _lib.check(lib.kgb_gather_max_bwd(g.device.index, g.data_ptr(), g.stride(0), arg.data_ptr(), out.data_ptr(),
-                                          out.stride(0), x.data_ptr(), x.stride(0), csr.rowptr.data_ptr(),
-                                          col.data_ptr(), None, csr.n_rows, F, op, gx.data_ptr(), gx.stride(0),
-                                          n_src_rows, acc.data_ptr(), ctypes.byref(hubs), st), "kgb_gather_max_bwd")
+        # B_bwd(max) = N*F*(4 g + 4 arg) + N*F*4 (zero-init) + N*F*4 (scattered writes)
+        with _prof(f"gather_max_bwd_F{F}", csr.n_rows * F * 16, g.device):
+            _lib.check(lib.kgb_gather_max_bwd(g.device.index, g.data_ptr(), g.stride(0), arg.data_ptr(),
+                                              out.data_ptr(), out.stride(0), x.data_ptr(), x.stride(0),
+                                              csr.rowptr.data_ptr(), col.data_ptr(), None, csr.n_rows, F, op,
+                                              gx.data_ptr(), gx.stride(0), n_src_rows, acc.data_ptr(),
+                                              ctypes.byref(hubs), st), "kgb_gather_max_bwd")
     return gx
 
 
@@ -387,10 +421,11 @@ class _GatV2(torch.autograd.Function):
         rowmax = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
         rowden = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
         hubs = csr.hub_table(lib.kgb_gatv2_partial_bytes(csr.n_chunks, H, C), _stream(dev), gat=True)
-        _lib.check(lib.kgb_gatv2_fwd(dev.index, h_src.data_ptr(), h_dst.data_ptr(), n_src, n_dst, H, C,
-                                     att_c.data_ptr(), float(slope), csr.rowptr.data_ptr(), csr.col.data_ptr(),
-                                     _ptr(bias_c), out.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(),
-                                     ctypes.byref(hubs), _stream(dev)), "kgb_gatv2_fwd")
+        with _prof(f"gatv2_fwd_H{H}_C{C}", gat_bytes(csr.nnz, n_dst, H, C), dev):
+            _lib.check(lib.kgb_gatv2_fwd(dev.index, h_src.data_ptr(), h_dst.data_ptr(), n_src, n_dst, H, C,
+                                         att_c.data_ptr(), float(slope), csr.rowptr.data_ptr(), csr.col.data_ptr(),
+                                         _ptr(bias_c), out.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(),
+                                         ctypes.byref(hubs), _stream(dev)), "kgb_gatv2_fwd")
         ctx.graph, ctx.H, ctx.C, ctx.slope, ctx.same = graph, H, C, float(slope), same
         ctx.has_bias = bias is not None
         ctx.save_for_backward(h_src, h_dst, att_c, out, rowmax, rowden, *([bias_c] if bias is not None else []))
@@ -406,7 +441,7 @@ class _GatV2(torch.autograd.Function):
         H, C, graph = ctx.H, ctx.C, ctx.graph
         dev = g.device
         n_src, n_dst = int(h_src.shape[0]), int(h_dst.shape[0])
-        agg = out - saved[6] if ctx.has_bias else out
+        bias_c = saved[6] if ctx.has_bias else None
         csr, csc = graph.csr, graph.csc
         st = _stream(dev)
         n_parts = lib.kgb_gatv2_bwd_parts(dev.index, n_dst, H, C)
@@ -415,25 +450,27 @@ class _GatV2(torch.autograd.Function):
         g_hdst = torch.empty_like(h_dst)
         r = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
         part = torch.empty((n_parts, H * C), dtype=torch.float32, device=dev)
-        _lib.check(lib.kgb_gatv2_bwd_dst(dev.index, g.data_ptr(), agg.data_ptr(), h_src.data_ptr(), h_dst.data_ptr(),
-                                         n_src, n_dst, H, C, att_c.data_ptr(), ctx.slope, csr.rowptr.data_ptr(),
-                                         csr.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(),
-                                         g_hdst.data_ptr(), r.data_ptr(), part.data_ptr(), n_parts,
-                                         ctypes.byref(csr.hub_table(lib.kgb_gatv2_partial_bytes(csr.n_chunks, H, C), st, gat=True)),
-                                         st), "kgb_gatv2_bwd_dst")
+        with _prof(f"gatv2_bwd_dst_H{H}_C{C}", gat_bytes(csr.nnz, n_dst, H, C), dev):
+            _lib.check(lib.kgb_gatv2_bwd_dst(dev.index, g.data_ptr(), out.data_ptr(), h_src.data_ptr(), h_dst.data_ptr(),
+                                             n_src, n_dst, H, C, att_c.data_ptr(), ctx.slope, csr.rowptr.data_ptr(),
+                                             csr.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(), _ptr(bias_c),
+                                             g_hdst.data_ptr(), r.data_ptr(), part.data_ptr(), n_parts,
+                                             ctypes.byref(csr.hub_table(lib.kgb_gatv2_partial_bytes(csr.n_chunks, H, C), st, gat=True)),
+                                             st), "kgb_gatv2_bwd_dst")
         g_att = torch.empty(H * C, dtype=torch.float32, device=dev)
         _lib.check(lib.kgb_reduce_parts(dev.index, part.data_ptr(), n_parts, H * C, g_att.data_ptr(), st),
                    "kgb_reduce_parts")
         g_hsrc = torch.empty_like(h_src)
-        _lib.check(lib.kgb_gatv2_bwd_src(dev.index, g.data_ptr(), h_src.data_ptr(), h_dst.data_ptr(), n_src, n_dst,
-                                         H, C, att_c.data_ptr(), ctx.slope, csc.rowptr.data_ptr(),
-                                         csc.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(), r.data_ptr(),
-                                         g_hsrc.data_ptr(),
-                                         ctypes.byref(csc.hub_table(lib.kgb_gatv2_partial_bytes(csc.n_chunks, H, C), st, gat=True)),
-                                         st), "kgb_gatv2_bwd_src")
-        g_bias = g.sum(dim=0) if ctx.has_bias else None
-        if ctx.same:
-            return g_hsrc + g_hdst, None, g_att, g_bias, None, None, None, None
+        with _prof(f"gatv2_bwd_src_H{H}_C{C}", gat_bytes(csc.nnz, n_src, H, C), dev):
+            _lib.check(lib.kgb_gatv2_bwd_src(dev.index, g.data_ptr(), h_src.data_ptr(), h_dst.data_ptr(), n_src, n_dst,
+                                             H, C, att_c.data_ptr(), ctx.slope, csc.rowptr.data_ptr(),
+                                             csc.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(), r.data_ptr(),
+                                             g_hdst.data_ptr() if ctx.same else None, g_hsrc.data_ptr(),
+                                             ctypes.byref(csc.hub_table(lib.kgb_gatv2_partial_bytes(csc.n_chunks, H, C), st, gat=True)),
+                                             st), "kgb_gatv2_bwd_src")
+        g_bias = relu_bwd_colsum(g, None)[1] if ctx.has_bias else None   # column sums in one pass (kgb_relu_bwd_colsum)
+        if ctx.same:   # the per-target part was added in the per-source kernel's epilogue
+            return g_hsrc, None, g_att, g_bias, None, None, None, None
         return g_hsrc, g_hdst, g_att, g_bias, None, None, None, None
 
 
