@@ -231,17 +231,18 @@ def test_scripts_parse_and_partition_bounds():
     import ast
     import glob
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for path in [os.path.join(root, "bench.py"), os.path.join(root, "bench_dist.py"),
+    for path in [os.path.join(root, "bench.py"), os.path.join(root, "bench_dist.py"), os.path.join(root, "bench_extra.py"),
                  os.path.join(root, "__graft_entry__.py")] + glob.glob(os.path.join(root, "tools", "*.py")):
         ast.parse(open(path).read(), filename=path)
     import sys
     sys.path.insert(0, root)
     import bench_dist
+    from keras_geometric_b200.dist import cost_balanced_bounds
     gen = torch.Generator().manual_seed(0)
     n = 1000
     dst = (torch.rand(20000, generator=gen) ** 3 * n).long().clamp_(max=n - 1)   # skewed in-degrees
     for world in (1, 2, 3, 8):
-        b = bench_dist.edge_balanced_bounds(dst, n, world)
+        b = cost_balanced_bounds(dst, n, world, bench_dist.NODE_WEIGHT)
         assert b[0] == 0 and b[-1] == n and len(b) == world + 1
         assert all(b[i] <= b[i + 1] for i in range(world))
         if world > 1:
