@@ -15,6 +15,8 @@ keras_ops.py       restatement of the Keras-3 *torch backend* primitives the ref
                    (keras/src/backend/torch/{numpy,math}.py).
 reference_path.py  line-by-line functional restatement of the reference's layer
                    algorithms, each function citing the reference file:line it follows.
+kink.py            pins the oracle's GEMM outputs to given values (straight-through gradient) so that
+                   LeakyReLU sign patterns coincide in full-size GATv2 gradient comparisons.
 keras_shim/        a minimal stand-in ``keras`` package (built on keras_ops.py) that lets
                    the UNMODIFIED reference sources under /root/reference/src be imported
                    in the build container.  Used by tests/golden/make_golden.py to

@@ -36,38 +36,13 @@ def cpu_param(p):
     return p.detach().cpu().clone().requires_grad_(True)
 
 
-def check_all(out_gpu, out_cpu, params_gpu, params_cpu, names, R, tag, skip_rows=None):
-    """``skip_rows`` (name -> bool mask over rows): rows whose gradient depends on the SIGN of a pre-activation that
-    lies within rounding distance of a derivative discontinuity (see kink_rows); they are excluded from that
-    tensor's comparison and must stay a small fraction."""
+def check_all(out_gpu, out_cpu, params_gpu, params_cpu, names, R, tag):
+    """Forward and every gradient at the north star's tolerance: |got - want| <= 1e-5 * (|want| + max|want|)."""
     close(out_gpu, out_cpu, msg=f"{tag} forward")
     g_gpu = torch.autograd.grad((out_gpu * cuda(R)).sum(), params_gpu)
     g_cpu = torch.autograd.grad((out_cpu * torch.from_numpy(R)).sum(), params_cpu)
     for nm, a, b in zip(names, g_gpu, g_cpu):
-        a = a.reshape(b.shape).detach().cpu()
-        if skip_rows is not None and nm in skip_rows:
-            keep = ~skip_rows[nm]
-            assert keep.float().mean() > 0.97, f"{tag}: {int((~keep).sum())} rows excluded from grad {nm}"
-            scale = float(b.abs().max())
-            np.testing.assert_allclose(a[keep].numpy(), b[keep].numpy(), rtol=1e-5, atol=1e-5 * scale,
-                                       err_msg=f"{tag} grad {nm} ({int((~keep).sum())} kink rows excluded)")
-        else:
-            close(a, b, msg=f"{tag} grad {nm}")
-
-
-def kink_rows(h, ei_loops, n, tau_rel=4e-6):
-    """Rows touched by an edge whose GATv2 pre-activation z = h_i + h_j has a component within ``tau_rel * max|h|`` of
-    zero.  LeakyReLU's derivative jumps from 0.2 to 1 there, h comes out of a GEMM with ~2e-6 relative rounding
-    error (3xTF32 on the GPU, a different summation order on the host), so the SIGN of such a z - and with it a
-    finite share of the gradient of both endpoint rows - is not determined at fp32 precision on either side."""
-    h = h.detach().double()
-    src, dst = ei_loops[0].long(), ei_loops[1].long()
-    z = h[dst] + h[src]
-    bad = (z.abs() < tau_rel * float(h.abs().max())).any(dim=1)
-    rows = torch.zeros(n, dtype=torch.bool)
-    rows[src[bad]] = True
-    rows[dst[bad]] = True
-    return rows
+        close(a.reshape(b.shape), b, msg=f"{tag} grad {nm}")
 
 
 def test_c1_cora_shaped_two_layer_gcn():
@@ -119,21 +94,23 @@ def test_c2_pubmed_shaped_two_layer_gatv2():
     xo = torch.from_numpy(x).requires_grad_(True)
     pc = [xo] + [cpu_param(p) for p in pg[1:]]
     eio = torch.from_numpy(ei)
+    # plain oracle: the forward outputs agree at 1e-5
     h = torch.nn.functional.elu(ref.gatv2_conv(xo, eio, pc[1], pc[2], pc[3], heads=8))
-    want = ref.gatv2_conv(h, eio, pc[4], pc[5], pc[6], heads=1)
+    close(out, ref.gatv2_conv(h, eio, pc[4], pc[5], pc[6], heads=1), msg="C2 forward (unpinned oracle)")
+    # gradients: LeakyReLU's derivative jumps at z = h_i + h_j = 0 and a handful of the 7 M pre-activations lie within
+    # GEMM rounding distance of it, so the oracle's two h = xW products are pinned to the values the GPU computed
+    # (oracle/kink.py; the GEMM is checked against float64 separately) - identical sign patterns, plain 1e-5 tolerance
+    from keras_geometric_b200 import ops
+    from oracle.kink import pinned_matmul
+    with torch.no_grad():
+        h1_gpu = ops.linear(xg, g1.linear_transform.kernel)
+        h2_gpu = ops.linear(torch.nn.functional.elu(g1([xg, ei])), g2.linear_transform.kernel)
+    with pinned_matmul([h1_gpu.cpu(), h2_gpu.cpu()]) as pin:
+        h = torch.nn.functional.elu(ref.gatv2_conv(xo, eio, pc[1], pc[2], pc[3], heads=8))
+        want = ref.gatv2_conv(h, eio, pc[4], pc[5], pc[6], heads=1)
+    assert pin["calls"] == 2 and pin["max_rel_dev"] < 1e-5, pin   # the pinned values ARE the oracle's, to rounding
     R = rng.standard_normal((n, 3)).astype(np.float32)
-    # rows whose input gradient hinges on a LeakyReLU sign at rounding distance from the kink: layer-1 kinks touch
-    # the two endpoint rows; a layer-2 kink perturbs g_h2 of its endpoints, which layer 1's backward spreads over
-    # their neighbourhoods
-    loops = torch.arange(n, dtype=torch.int32)
-    ei_l = torch.cat([eio, torch.stack([loops, loops])], dim=1)
-    k1 = kink_rows(xo.detach().double() @ pc[1].detach().double(), ei_l, n)
-    k2 = kink_rows(h.detach().double() @ pc[4].detach().double(), ei_l, n)
-    spread = k2.clone()
-    spread[ei_l[0].long()[k2[ei_l[1].long()]]] = True
-    spread[ei_l[1].long()[k2[ei_l[0].long()]]] = True
-    check_all(out, want, pg, pc, ["x", "W1", "att1", "bias1", "W2", "att2", "bias2"], R, "C2",
-              skip_rows={"x": k1 | spread})
+    check_all(out, want, pg, pc, ["x", "W1", "att1", "bias1", "W2", "att2", "bias2"], R, "C2")
 
 
 def molecule_batch(rng, n_graphs=4096, feats=32):
