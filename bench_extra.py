@@ -154,7 +154,8 @@ def c5_strong(world, rank, dev, div=1, reps=3):
         del g, x
         per_rank = None
     else:
-        bounds = cost_balanced_bounds(ei[1], n, world, node_weight=4.0)
+        # aggregation only: a node costs about as much as 1.5 gathered edges (one output row, its row pointers)
+        bounds = cost_balanced_bounds(ei[1], n, world, node_weight=1.5)
         lo, hi = bounds[rank], bounds[rank + 1]
         mine = (ei[1] >= lo) & (ei[1] < hi)
         src, dst = ei[0][mine].clone(), ei[1][mine].clone()
