@@ -132,11 +132,21 @@ def c5_strong(world, rank, dev, div=1, reps=3):
            "n_gpus": world}
     gen = torch.Generator(device=dev).manual_seed(5 + rank)
 
-    def run(agg_fn, x):
+    phases = {}
+
+    def run(agg_fn, x, tag=""):
         def once():
             o = agg_fn(x)
             torch.autograd.grad(o, x, o.detach())   # seed = the output itself: no extra [N, F] buffer
+        ops.PROFILE = []
         ms = torch.tensor([_time(once, reps=reps, warm=2)], device=dev)
+        prof, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for r in prof[-(len(prof) * reps // (reps + 2)):]:   # the timed repetitions only
+            a = agg.setdefault(r["label"], [0.0, 0, 0])
+            a[0] += r["start"].elapsed_time(r["end"]); a[1] += r["bytes"]; a[2] += 1
+        phases[tag] = {k: {"ms_per_fwd_bwd": v[0] / reps, "GBps": (v[1] / v[0] / 1e6) if v[1] else None}
+                       for k, v in agg.items()}
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
@@ -145,12 +155,12 @@ def c5_strong(world, rank, dev, div=1, reps=3):
         x = torch.randn((n, F), device=dev, generator=gen).requires_grad_(True)
         g = GraphStructure(ei, n, n, 0)
         g.csc  # noqa: B018
-        t_sage = run(lambda t: ops.gather_reduce(t, g, "mean"), x)
+        t_sage = run(lambda t: ops.gather_reduce(t, g, "mean"), x, "sage_mean")
         del g
         torch.cuda.empty_cache()
         g = GraphStructure(ei, n, n, n)
         g.csc  # noqa: B018
-        t_gcn = run(lambda t: ops.gather_reduce(t, g, "sum", weight="gcn"), x)
+        t_gcn = run(lambda t: ops.gather_reduce(t, g, "sum", weight="gcn"), x, "gcn")
         del g, x
         per_rank = None
     else:
@@ -164,14 +174,14 @@ def c5_strong(world, rank, dev, div=1, reps=3):
         e_local = int(src.numel())
         pg = PartitionedGraph(src, dst, n, rank, world, bounds=bounds)
         x = torch.randn((pg.n_local, F), device=dev, generator=gen).requires_grad_(True)
-        t_sage = run(lambda t: ops.aggregate_partitioned(t, pg, "mean"), x)
+        t_sage = run(lambda t: ops.aggregate_partitioned(t, pg, "mean"), x, "sage_mean")
         stats = torch.tensor([pg.n_local, pg.n_halo, e_local, pg.plan.n_send], device=dev, dtype=torch.float64)
         pg.close()
         del pg
         torch.cuda.empty_cache()
         pg = PartitionedGraph(src, dst, n, rank, world, bounds=bounds, n_loops_local=True)
         del src, dst
-        t_gcn = run(lambda t: ops.aggregate_partitioned(t, pg, "gcn"), x)
+        t_gcn = run(lambda t: ops.aggregate_partitioned(t, pg, "gcn"), x, "gcn")
         pg.close()
         del pg, x
         allstats = [torch.zeros_like(stats) for _ in range(world)]
@@ -186,6 +196,12 @@ def c5_strong(world, rank, dev, div=1, reps=3):
     res["sage_mean"] = {"ms_fwd_bwd": t_sage, "GTEPS": e / t_sage / 1e6}
     res["gcn"] = {"ms_fwd_bwd": t_gcn, "GTEPS": (e + n) / t_gcn / 1e6}
     res["per_rank"] = per_rank
+    if world > 1:
+        allph = [None] * world
+        dist.all_gather_object(allph, phases)
+        res["phases_per_rank"] = allph      # CUDA-event time of every launch group inside one fwd+bwd, per rank
+    else:
+        res["phases_per_rank"] = [phases]
     if rank == 0:
         if world == 1 and div == 1:
             try:

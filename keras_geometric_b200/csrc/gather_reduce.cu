@@ -793,26 +793,41 @@ __global__ void __launch_bounds__(256)
 halo_push_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __restrict__ idx, int F, int64_t ldd,
                  const PushTab tab) {
   constexpr int GPW = 32 / G;
+  constexpr int U = NCH >= 4 ? 2 : 4;   // rows in flight per lane group: local HBM reads ahead of the NVLink stores
   const int lane = threadIdx.x & 31;
   const int gl = lane % G;
   const int gw = lane / G;
   const int nv = F / VEC;
   const int64_t n_slots = tab.slot_begin[tab.n_peers];
   const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
-  for (int64_t s = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; s < n_slots;
-       s += (int64_t)gridDim.x * gpb) {
-    int p = 0;
+  const int64_t stride = (int64_t)gridDim.x * gpb;
+  for (int64_t s0 = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; s0 < n_slots;
+       s0 += (int64_t)U * stride) {
+    int64_t r[U];
+    float v[U][NCH][VEC];
 #pragma unroll
-    for (int q = 1; q < KGB_MAX_PEERS; ++q) p += (q < tab.n_peers && s >= tab.slot_begin[q]) ? 1 : 0;
-    const int64_t r = idx ? (int64_t)__ldg(idx + s) : s;
-    float* drow = tab.dst[p] + (tab.dst_row0[p] + (s - tab.slot_begin[p])) * ldd;
+    for (int u = 0; u < U; ++u) {
+      const int64_t s = s0 + (int64_t)u * stride;
+      r[u] = s < n_slots ? (idx ? (int64_t)__ldg(idx + s) : s) : -1;
+    }
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      if ((gl + ch * G) >= nv) continue;
-      const int f0 = (gl + ch * G) * VEC;
-      float v[VEC];
-      ld_vec<VEC>(src + r * lds + f0, v);
-      st_vec<VEC>(drow + f0, v);
+    for (int u = 0; u < U; ++u) {
+      if (r[u] < 0) continue;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+        if ((gl + ch * G) < nv) ld_vec<VEC>(src + r[u] * lds + (gl + ch * G) * VEC, v[u][ch]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (r[u] < 0) continue;
+      const int64_t s = s0 + (int64_t)u * stride;
+      int p = 0;
+#pragma unroll
+      for (int q = 1; q < KGB_MAX_PEERS; ++q) p += (q < tab.n_peers && s >= tab.slot_begin[q]) ? 1 : 0;
+      float* drow = tab.dst[p] + (tab.dst_row0[p] + (s - tab.slot_begin[p])) * ldd;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+        if ((gl + ch * G) < nv) st_vec<VEC>(drow + (gl + ch * G) * VEC, v[u][ch]);
     }
   }
 }

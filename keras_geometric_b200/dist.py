@@ -410,9 +410,12 @@ class PartitionedGraph:
         F = int(x_local.shape[1])
         win = self._p2p_window(F)
         if win is not None:
-            win.barrier()                                   # every rank has consumed its previous halo rows
-            win.push(x_local, p.send_idx if p.n_send else None, F, forward=True)
-            win.barrier()                                   # every rank's rows have landed
+            with ops._prof("halo_wait_pre", 0, self.device):
+                win.barrier()                               # every rank has consumed its previous halo rows
+            with ops._prof(f"halo_push_fwd_F{F}", p.n_send * F * 4, self.device):
+                win.push(x_local, p.send_idx if p.n_send else None, F, forward=True)
+            with ops._prof("halo_wait_post", 0, self.device):
+                win.barrier()                               # every rank's rows have landed
             return win.halo_view(self.n_halo, F)
         halo = torch.empty((max(self.n_halo, 1), F), dtype=x_local.dtype, device=x_local.device)
         send = ops.gather_rows(x_local, p.send_idx) if p.n_send else x_local.new_empty((0, F))
@@ -428,9 +431,13 @@ class PartitionedGraph:
         F = int(g_halo.shape[1])
         win = self._p2p_window(F)
         if win is not None:
-            win.barrier()
-            win.push(g_halo, None, F, forward=False)
-            win.barrier()
+            from . import ops
+            with ops._prof("halo_wait_pre", 0, self.device):
+                win.barrier()
+            with ops._prof(f"halo_push_bwd_F{F}", self.n_halo * F * 4, self.device):
+                win.push(g_halo, None, F, forward=False)
+            with ops._prof("halo_wait_post", 0, self.device):
+                win.barrier()
             return win.back_view(p.n_send, F)
         back = torch.empty((max(p.n_send, 1), F), dtype=g_halo.dtype, device=g_halo.device)
         dist.all_to_all_single(back[:p.n_send], g_halo[:self.n_halo], output_split_sizes=p.send_counts,
