@@ -131,6 +131,7 @@ int kgb_permute_f32(int device, const float* in, const int32_t* perm, int64_t n,
  * hub_* / partial: optional hub table from kgb_csr_hubs plus a float workspace of
  * kgb_gather_reduce_partial_bytes(); when absent every row is reduced by one lane group.
  * ------------------------------------------------------------------------------------- */
+struct kgb_halo_push_args;
 typedef struct kgb_gather_reduce_args {
   const float* x;          /* [n_src_rows, F] gathered matrix                  */
   int64_t ldx;
@@ -169,6 +170,18 @@ typedef struct kgb_gather_reduce_args {
                               ceil(n_rows / kgb_gather_unit_rows()) row units, in the order the queue
                               hands them out.  Heaviest-first (by edge count, hub rows excluded) removes
                               the tail on power-law graphs; the result does not depend on it.   */
+  /* ---- split source / split output (partitioned graphs: [owned rows | halo rows] without a concatenated copy) ---- */
+  const float* x2;         /* optional: column ids >= n_split_src read row (id - n_split_src) of x2             */
+  int64_t ldx2;
+  int64_t n_split_src;     /* ignored when x2 is NULL                                                           */
+  float* out2;             /* optional: output rows >= n_split_out go to row (r - n_split_out) of out2 ...      */
+  int64_t ldo2;
+  int64_t n_split_out;
+  const struct kgb_halo_push_args* out2_push; /* ... or, when given, straight into the peers' windows: row
+                              (r - n_split_out) is slot s of the push table (only slot_begin / dst / dst_row0 /
+                              ldd / n_peers are read).  This is the fused "transposed gather + halo-gradient
+                              exchange" kernel: the rows travel over NVLink while the rest is still being reduced.
+                              Split-output rows take no addend / bias / activation / arg.                        */
 } kgb_gather_reduce_args;
 
 /* rows per task-queue unit of kgb_gather_reduce (unit u covers rows [u*R, (u+1)*R)) */

@@ -36,6 +36,8 @@ class GatherReduceArgs(Structure):
         ("chunk_hub", c_void_p), ("n_hubs", c_int32), ("n_chunks", c_int32),
         ("hub_threshold", c_int32), ("hub_chunk", c_int32), ("partial", c_void_p),
         ("work", c_void_p), ("unit_order", c_void_p),
+        ("x2", c_void_p), ("ldx2", c_int64), ("n_split_src", c_int64),
+        ("out2", c_void_p), ("ldo2", c_int64), ("n_split_out", c_int64), ("out2_push", c_void_p),
     ]
 
 

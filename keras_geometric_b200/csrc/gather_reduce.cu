@@ -24,6 +24,22 @@
 
 namespace kgb {
 
+// Destination table of a halo push (K7): slot s (grouped by destination peer) -> row of that peer's window.
+struct PushTab {
+  int n_peers;
+  int64_t slot_begin[KGB_MAX_PEERS + 1];
+  float* dst[KGB_MAX_PEERS];
+  int64_t dst_row0[KGB_MAX_PEERS];
+  int64_t ldd;
+};
+
+__device__ __forceinline__ float* push_row(const PushTab& tab, int64_t s) {
+  int p = 0;
+#pragma unroll
+  for (int q = 1; q < KGB_MAX_PEERS; ++q) p += (q < tab.n_peers && s >= tab.slot_begin[q]) ? 1 : 0;
+  return tab.dst[p] + (tab.dst_row0[p] + (s - tab.slot_begin[p])) * tab.ldd;
+}
+
 struct GRP {
   const float* x; int64_t ldx;
   int F;
@@ -39,6 +55,10 @@ struct GRP {
   float* partial; int32_t* partial_arg;
   int32_t* work;  // [2] zero on entry: dynamic task queue head + finished-CTA count (self-resetting)
   const int32_t* unit_order;  // optional permutation of the row units (heaviest first)
+  // split source / split output (partitioned graphs)
+  const float* x2; int64_t ldx2; int64_t n_split_src;   // n_split_src = INT64_MAX when x2 is unused
+  float* out2; int64_t ldo2; int64_t n_split_out;       // n_split_out = INT64_MAX when unused
+  int has_push; PushTab tab;                            // fused halo push: split-output rows go to the peers' windows
 };
 
 template <int VEC, int G, int NCH, bool IS_MAX>
@@ -93,7 +113,8 @@ __device__ __forceinline__ void load_batch_full(const GRP& p, int32_t myc, float
     c[u] = __shfl_sync(gmask, myc, j + u, G);
     w[u] = 1.f;
     if constexpr (HAS_W) w[u] = __shfl_sync(gmask, myw, j + u, G);
-    const float* rp = p.x + (int64_t)c[u] * p.ldx;
+    const int64_t cu = c[u];
+    const float* rp = (cu < p.n_split_src) ? p.x + cu * p.ldx : p.x2 + (cu - p.n_split_src) * p.ldx2;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) ld_vec<VEC>(rp + loff[ch], v[u][ch]);
   }
@@ -174,6 +195,25 @@ __device__ __forceinline__ void epilogue(const GRP& p, int64_t slot, int64_t deg
   const int64_t row_out = p.row_ids ? (int64_t)__ldg(p.row_ids + slot) : slot;
   float os = 1.f;
   if (p.out_scale) os = __ldg(p.out_scale + slot);
+  if (row_out >= p.n_split_out) {
+    // second output space: a local buffer, or (fused halo-gradient exchange) the owner's window over NVLink
+    const int64_t r2 = row_out - p.n_split_out;
+    float* drow = p.has_push ? push_row(p.tab, r2) : p.out2 + r2 * p.ldo2;
+    const float den2 = fmaxf((float)deg, 1e-8f);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (!on[ch]) continue;
+      float r[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        r[e] = acc[ch][e];
+        if (p.mean) r[e] = __fdiv_rn(r[e], den2);
+        if (p.out_scale) r[e] = __fmul_rn(r[e], os);
+      }
+      st_vec<VEC>(drow + (gl + ch * G) * VEC, r);
+    }
+    return;
+  }
   // mean: sum / max(count, 1e-8) with a true IEEE division like the reference (aggregators.py:77-81);
   // it runs once per row and element, not per edge
   const float den = fmaxf((float)deg, 1e-8f);
@@ -781,13 +821,6 @@ gather_rows_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __
 
 // K7: pack + push.  Slot s (grouped by destination peer) reads one feature row of this rank and stores it into the
 // destination rank's window over NVLink (peer memory mapped with CUDA IPC).
-struct PushTab {
-  int n_peers;
-  int64_t slot_begin[KGB_MAX_PEERS + 1];
-  float* dst[KGB_MAX_PEERS];
-  int64_t dst_row0[KGB_MAX_PEERS];
-};
-
 template <int VEC, int G, int NCH>
 __global__ void __launch_bounds__(256)
 halo_push_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __restrict__ idx, int F, int64_t ldd,
@@ -820,11 +853,7 @@ halo_push_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __re
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (r[u] < 0) continue;
-      const int64_t s = s0 + (int64_t)u * stride;
-      int p = 0;
-#pragma unroll
-      for (int q = 1; q < KGB_MAX_PEERS; ++q) p += (q < tab.n_peers && s >= tab.slot_begin[q]) ? 1 : 0;
-      float* drow = tab.dst[p] + (tab.dst_row0[p] + (s - tab.slot_begin[p])) * ldd;
+      float* drow = push_row(tab, s0 + (int64_t)u * stride);
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch)
         if ((gl + ch * G) < nv) st_vec<VEC>(drow + (gl + ch * G) * VEC, v[u][ch]);
@@ -987,10 +1016,40 @@ int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t 
   const bool is_max = (a->op == KGB_OP_MAX || a->op == KGB_OP_MIN || a->op == KGB_OP_MAX_RAW);
   cudaStream_t st = (cudaStream_t)stream;
 
-  const bool can4 = aligned16(a->x) && aligned16(a->out) && (a->ldx % 4 == 0) && (a->ldo % 4 == 0) &&
-                    (!a->addend || (aligned16(a->addend) && a->ld_addend % 4 == 0)) &&
-                    (!a->bias || aligned16(a->bias)) && (!a->arg || aligned16(a->arg)) &&
-                    (!hubs || aligned16(a->partial));
+  bool can4 = aligned16(a->x) && aligned16(a->out) && (a->ldx % 4 == 0) && (a->ldo % 4 == 0) &&
+              (!a->addend || (aligned16(a->addend) && a->ld_addend % 4 == 0)) &&
+              (!a->bias || aligned16(a->bias)) && (!a->arg || aligned16(a->arg)) &&
+              (!hubs || aligned16(a->partial));
+  // split source / split output (partitioned graphs)
+  const bool split_out = a->out2 != nullptr || a->out2_push != nullptr;
+  if (a->x2) {
+    KGB_REQUIRE(a->n_split_src >= 0 && a->ldx2 >= a->F, "bad split source");
+    can4 = can4 && aligned16(a->x2) && a->ldx2 % 4 == 0;
+  }
+  PushTab tab = {};
+  if (split_out) {
+    KGB_REQUIRE(!is_max && a->n_split_out >= 0, "a split output needs a linear aggregation");
+    if (a->out2_push) {
+      const kgb_halo_push_args* pa = a->out2_push;
+      KGB_REQUIRE(pa->n_peers >= 1 && pa->n_peers <= KGB_MAX_PEERS && pa->ldd >= a->F, "bad push table");
+      tab.n_peers = pa->n_peers;
+      tab.ldd = pa->ldd;
+      can4 = can4 && pa->ldd % 4 == 0;
+      for (int q = 0; q <= KGB_MAX_PEERS; ++q) tab.slot_begin[q] = pa->slot_begin[q < pa->n_peers ? q : pa->n_peers];
+      for (int q = 0; q < KGB_MAX_PEERS; ++q) {
+        tab.dst[q] = q < pa->n_peers ? pa->dst[q] : nullptr;
+        tab.dst_row0[q] = q < pa->n_peers ? pa->dst_row0[q] : 0;
+        if (q < pa->n_peers && pa->slot_begin[q + 1] > pa->slot_begin[q]) {
+          KGB_REQUIRE(pa->dst[q] != nullptr, "peer %d has rows but no window", q);
+          can4 = can4 && aligned16(pa->dst[q]);
+        }
+      }
+      KGB_REQUIRE(a->n_rows - a->n_split_out <= pa->slot_begin[pa->n_peers], "more split rows than push slots");
+    } else {
+      KGB_REQUIRE(a->ldo2 >= a->F, "bad split output");
+      can4 = can4 && aligned16(a->out2) && a->ldo2 % 4 == 0;
+    }
+  }
   const int vec = (can4 && a->F % 4 == 0) ? 4 : 1;
   const int slab = 32 * 4 * vec;  // widest feature slab of one launch
   for (int f0 = 0; f0 < a->F; f0 += slab) {
@@ -1011,6 +1070,14 @@ int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t 
     p.partial = a->partial;
     p.work = a->work;
     p.unit_order = a->work ? a->unit_order : nullptr;
+    p.x2 = a->x2 ? a->x2 + f0 : nullptr; p.ldx2 = a->ldx2;
+    p.n_split_src = a->x2 ? a->n_split_src : INT64_MAX;
+    p.out2 = a->out2 ? a->out2 + f0 : nullptr; p.ldo2 = a->ldo2;
+    p.n_split_out = split_out ? a->n_split_out : INT64_MAX;
+    p.has_push = a->out2_push ? 1 : 0;
+    p.tab = tab;
+    if (p.has_push)
+      for (int q = 0; q < tab.n_peers; ++q) if (p.tab.dst[q]) p.tab.dst[q] += f0;
     p.partial_arg = nullptr;
     if (hubs && is_max)
       p.partial_arg = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(a->partial) +
@@ -1142,6 +1209,7 @@ int kgb_halo_push(int device, const kgb_halo_push_args* a, kgb_stream_t stream) 
   KGB_REQUIRE(a->lds >= a->F && a->ldd >= a->F, "leading dimension smaller than F");
   PushTab tab;
   tab.n_peers = a->n_peers;
+  tab.ldd = a->ldd;
   bool can4 = aligned16(a->src) && a->lds % 4 == 0 && a->ldd % 4 == 0;
   for (int p = 0; p <= a->n_peers; ++p) {
     tab.slot_begin[p] = a->slot_begin[p];

@@ -236,14 +236,13 @@ class PeerWindow:
         o = self.back_off[self.rank]
         return self.local[o:o + max(n_rows, 1) * F * 4].view(torch.float32).view(max(n_rows, 1), F)
 
-    def push(self, src: torch.Tensor, idx, F: int, forward: bool) -> None:
-        """kgb_halo_push on the CURRENT stream: forward = my rows -> peers' halo regions, else my halo-row gradients
-        -> their owners' back regions.  Rows in the window are dense (leading dimension F)."""
+    def push_args(self, F: int, forward: bool):
+        """Destination table (``kgb_halo_push_args`` without a source): forward = my rows -> peers' halo regions,
+        else my halo-row gradients -> their owners' back regions.  Rows in the window are dense (ld = F)."""
         from . import _lib
-        from .graph import _stream
         t = self.tables
         a = _lib.HaloPushArgs()
-        a.src, a.lds, a.idx, a.F, a.n_peers = src.data_ptr(), src.stride(0), (idx.data_ptr() if idx is not None else None), F, self.world
+        a.F, a.n_peers = F, self.world
         begin = t["fwd_begin"] if forward else t["bwd_begin"]
         row0 = t["fwd_row0"] if forward else t["bwd_row0"]
         for p in range(self.world + 1):
@@ -252,6 +251,14 @@ class PeerWindow:
             a.dst[p] = self.ptr[p] + (0 if forward else self.back_off[p])
             a.dst_row0[p] = row0[p]
         a.ldd = F
+        return a
+
+    def push(self, src: torch.Tensor, idx, F: int, forward: bool) -> None:
+        """kgb_halo_push on the CURRENT stream (pack + store into the peers' windows)."""
+        from . import _lib
+        from .graph import _stream
+        a = self.push_args(F, forward)
+        a.src, a.lds, a.idx = src.data_ptr(), src.stride(0), (idx.data_ptr() if idx is not None else None)
         _lib.check(self.lib.kgb_halo_push(self.device.index, ctypes.byref(a), _stream(self.device)), "kgb_halo_push")
 
     def close(self) -> None:
@@ -444,6 +451,37 @@ class PartitionedGraph:
                                input_split_sizes=p.recv_counts, group=self.group)
         return back
 
+    def halo_grad_fused(self, g: torch.Tensor, tgt_scale=None, halo_scale=None) -> torch.Tensor:
+        """Backward of the halo part on the CURRENT stream, exchange included: the transposed gather over the
+        halo-source structure (one output row per halo row: sum of ``tgt_scale_i * g_i`` over the owned targets i it
+        feeds, times ``halo_scale``) stores every finished row STRAIGHT INTO ITS OWNER'S WINDOW over NVLink
+        (kgb_gather_reduce with a push table) - the rows travel while the rest of the kernel is still reducing, and
+        no [n_halo, F] buffer is written or re-read.  Returns the [n_send, F] rows this rank received (to be summed
+        per owned row with ``send_csr``)."""
+        from . import _lib, ops
+        g_h = self.split[1]
+        F = int(g.shape[1])
+        win = self._p2p_window(F)
+        if win is None:
+            g_halo, _ = ops.gather_reduce_raw(g, g_h.csc, _lib.OP_SUM, src_scale=tgt_scale, out_scale=halo_scale)
+            return self.halo_grad_raw(g_halo)
+        with ops._prof("halo_wait_pre", 0, self.device):
+            win.barrier()                                   # every owner has consumed its previous back rows
+        if self.n_halo:
+            args = win.push_args(F, forward=False)
+            dummy = self._dummy_row(F)
+            ops.gather_reduce_raw(g, g_h.csc, _lib.OP_SUM, src_scale=tgt_scale, out_scale=halo_scale, out=dummy,
+                                  out2_push=args, n_split_out=0, label="halo_grad_push")
+        with ops._prof("halo_wait_post", 0, self.device):
+            win.barrier()                                   # every rank's rows have landed
+        return win.back_view(self.plan.n_send, F)
+
+    def _dummy_row(self, F: int) -> torch.Tensor:
+        d = getattr(self, "_dummy", None)
+        if d is None or d.shape[1] < F:
+            d = self._dummy = torch.empty((1, max(F, 256)), dtype=torch.float32, device=self.device)
+        return d[:, :F]
+
     def close(self) -> None:
         """Release the peer-memory window (collective: every rank must call it)."""
         if self._window is not None:
@@ -455,7 +493,7 @@ class PartitionedGraph:
         return _exchange_fwd(v_local.reshape(-1, 1).contiguous(), self).reshape(-1)
 
     def gcn_dis_split(self):
-        """(dis [n_local], dis_halo [n_halo]): deg^-1/2 of the TOTAL in-degree (local + halo sources + self-loops) for
+        """(dis [n_local], dis_ext [n_local + n_halo]): deg^-1/2 of the TOTAL in-degree (local + halo sources + self-loops) for
         the owned rows, and the same values of the halo rows (fetched once per graph) - for the split structures."""
         if getattr(self, "_dis_split", None) is None:
             from . import _lib
@@ -466,8 +504,8 @@ class PartitionedGraph:
             dis = torch.empty(self.n_local, dtype=torch.float32, device=self.device)
             _lib.check(lib.kgb_gcn_norm(self.device.index, deg.data_ptr(), self.n_local, None, 0, 0, dis.data_ptr(),
                                         None, _stream(self.device)), "kgb_gcn_norm")
-            halo = self.halo_rows_raw(dis.reshape(-1, 1).contiguous())[:max(self.n_halo, 1)].reshape(-1).clone()
-            self._dis_split = (dis, halo)
+            halo = self.halo_rows_raw(dis.reshape(-1, 1).contiguous())[:self.n_halo].reshape(-1)
+            self._dis_split = (dis, torch.cat([dis, halo]))     # (owned rows, [owned | halo] rows)
         return self._dis_split
 
     def gcn_dis_ext(self) -> torch.Tensor:

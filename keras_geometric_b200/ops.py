@@ -74,8 +74,12 @@ def _ptr(t):
 def gather_reduce_raw(x: torch.Tensor, csr: Csr, op: int, *, col: torch.Tensor | None = None,
                       edge_w=None, src_scale=None, out_scale=None, addend=None, addend_scale: float = 1.0,
                       bias=None, act: int = 0, want_arg: bool = False, row_ids=None, out=None,
-                      n_out_rows: int | None = None):
-    """One kgb_gather_reduce launch (no autograd).  Returns ``(out, arg_or_None)``."""
+                      n_out_rows: int | None = None, x2=None, n_split_src: int | None = None, out2=None,
+                      out2_push=None, n_split_out: int | None = None, label: str | None = None):
+    """One kgb_gather_reduce launch (no autograd).  Returns ``(out, arg_or_None)``.
+    ``x2`` / ``n_split_src``: column ids >= n_split_src read ``x2`` (partitioned graphs: [owned | halo] sources without
+    a concatenated copy).  ``out2`` or ``out2_push`` (a ``HaloPushArgs`` destination table) / ``n_split_out``: output
+    rows >= n_split_out go to a second buffer or straight into the peers' windows."""
     lib = _lib.load()
     require_cuda(x, "x")
     F = int(x.shape[1])
@@ -106,6 +110,14 @@ def gather_reduce_raw(x: torch.Tensor, csr: Csr, op: int, *, col: torch.Tensor |
         a.partial = partial.data_ptr()
     a.work = csr.work(_stream(dev)).data_ptr()
     a.unit_order = _ptr(csr.unit_order())
+    if x2 is not None:
+        a.x2, a.ldx2, a.n_split_src = x2.data_ptr(), x2.stride(0), int(n_split_src)
+    if out2 is not None or out2_push is not None:
+        a.n_split_out = int(n_split_out)
+        if out2_push is not None:
+            a.out2_push = ctypes.addressof(out2_push)   # the caller's struct outlives this call
+        else:
+            a.out2, a.ldo2 = out2.data_ptr(), out2.stride(0)
     rec = None
     if PROFILE is not None:
         rec = {"start": torch.cuda.Event(enable_timing=True), "end": torch.cuda.Event(enable_timing=True)}
@@ -116,8 +128,10 @@ def gather_reduce_raw(x: torch.Tensor, csr: Csr, op: int, *, col: torch.Tensor |
         per_edge = (4 if edge_w is not None else 0) + (4 if src_scale is not None else 0)
         per_row = (4 if out_scale is not None else 0) + (4 * F if addend is not None else 0) + (4 * F if want_arg else 0)
         rec["bytes"] = _algorithmic_bytes(csr.nnz, n_rows, F, per_edge, per_row)
-        rec["label"] = (f"gather_reduce_{_OP_NAMES[op]}_F{F}" + ("_w" if per_edge else "")
-                        + ("_epi" if (addend is not None or bias is not None or act) else ""))
+        rec["label"] = label or (f"gather_reduce_{_OP_NAMES[op]}_F{F}" + ("_w" if per_edge else "")
+                                 + ("_epi" if (addend is not None or bias is not None or act) else ""))
+        if label:
+            rec["label"] += f"_F{F}"
         PROFILE.append(rec)
     return out, (arg[:, :F] if arg is not None else None)
 
@@ -859,11 +873,11 @@ class _SagePartitioned(torch.autograd.Function):
         need_x = ctx.needs_input_grad[0]
         send_csr = pg.send_csr
 
-        def send_back(rows):   # gradient of the halo rows -> their owners, on the communication stream
-            cs.wait_stream(cur)
+        def send_back(grad):   # transposed gather over the halo-source edges FUSED with the exchange: every finished
+            cs.wait_stream(cur)   # halo-row gradient is stored straight into its owner's window (communication stream)
             with torch.cuda.stream(cs):
-                back = pg.halo_grad_raw(rows)
-            rows.record_stream(cs)
+                back = pg.halo_grad_fused(grad, tgt_scale=scale)
+            grad.record_stream(cs)
             return back
 
         def land(back, acc):   # + per-owner segmented sum of the returned rows
@@ -877,8 +891,7 @@ class _SagePartitioned(torch.autograd.Function):
         if ctx.reorder:
             # out = act(S A_l z + S A_h halo(z) + x Ws + b), z = x Wn:  dz = A^T (S g) needs the exchange even when x
             # itself needs no gradient (it feeds dWn)
-            g_halo, _ = gather_reduce_raw(g, g_h.csc, _lib.OP_SUM, src_scale=scale)
-            back = send_back(g_halo)
+            back = send_back(g)
             g_ws = _dw_tc(x, g) if ctx.needs_input_grad[2] else None
             dz, _ = gather_reduce_raw(g, g_l.csc, _lib.OP_SUM, src_scale=scale)
             dz = land(back, dz)
@@ -894,8 +907,7 @@ class _SagePartitioned(torch.autograd.Function):
         if need_x:
             hi, lo = _split_weight(w_neigh, transpose=False)
             d_agg = linear_tc(g, hi, lo, K)
-            g_halo, _ = gather_reduce_raw(d_agg, g_h.csc, _lib.OP_SUM, src_scale=scale)
-            back = send_back(g_halo)
+            back = send_back(d_agg)
         g_wn = _dw_tc(agg, g) if ctx.needs_input_grad[1] else None
         g_ws = _dw_tc(x, g) if ctx.needs_input_grad[2] else None
         if need_x:
@@ -907,17 +919,21 @@ class _SagePartitioned(torch.autograd.Function):
 
 
 class _AggregatePartitioned(torch.autograd.Function):
-    """out = act(out_scale * sum_j src_scale_j * x_j + bias) over a 1-D node partition as ONE autograd node: a linear
-    aggregation (sum / mean / GCN-normalised sum) whose halo rows travel on the communication stream while the
-    local-source edges are reduced; in the backward the halo gradients are produced first and travel back while the
-    local transposed gather runs.  ``scales`` = (src_local [n_local] | None, src_halo [n_halo] | None,
-    dst [n_local] | None)."""
+    """out = act(out_scale * sum_j src_scale_j * x_j + bias) over a 1-D node partition as ONE autograd node (sum /
+    mean / GCN-normalised sum).
+    forward:  halo rows are pushed into this rank's window; ONE gather pass over the rank's edges reads owned
+              sources from ``x`` and halo sources from the window (split-source kernel: no [local | halo] copy, no
+              second pass over the output).
+    backward: the transposed gather over the halo-source edges runs on the communication stream and stores every
+              finished gradient row straight into its owner's window (fused gather + exchange) while the compute
+              stream reduces the local-source edges; the received rows are summed into their owners' rows by the
+              deterministic segmented sum.
+    ``scales`` = (src_ext [n_local + n_halo] | None, dst [n_local] | None)."""
 
     @staticmethod
     def forward(ctx, x, bias, pg, scales, relu: bool):
         x = _f32c(x, "x")
-        g_l, g_h, _ = pg.split
-        s_loc, s_halo, s_dst = scales
+        s_ext, s_dst = scales
         bias_c = _f32c(bias, "bias").contiguous() if bias is not None else None
         dev = x.device
         cur, cs = torch.cuda.current_stream(dev), pg._comm_stream()
@@ -925,11 +941,10 @@ class _AggregatePartitioned(torch.autograd.Function):
         with torch.cuda.stream(cs):
             halo = pg.halo_rows_raw(x)
         x.record_stream(cs)
-        part, _ = gather_reduce_raw(x, g_l.csr, _lib.OP_SUM, src_scale=s_loc, out_scale=s_dst)
         cur.wait_stream(cs)
         halo.record_stream(cur)
-        out, _ = gather_reduce_raw(halo, g_h.csr, _lib.OP_SUM, src_scale=s_halo, out_scale=s_dst, addend=part,
-                                   bias=bias_c, act=_lib.ACT_RELU if relu else _lib.ACT_NONE)
+        out, _ = gather_reduce_raw(x, pg.graph.csr, _lib.OP_SUM, x2=halo, n_split_src=pg.n_local, src_scale=s_ext,
+                                   out_scale=s_dst, bias=bias_c, act=_lib.ACT_RELU if relu else _lib.ACT_NONE)
         ctx.pg, ctx.scales, ctx.relu, ctx.has_bias = pg, scales, relu, bias is not None
         ctx.save_for_backward(*([out] if relu else []))
         return out
@@ -938,8 +953,10 @@ class _AggregatePartitioned(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         pg = ctx.pg
-        g_l, g_h, _ = pg.split
-        s_loc, s_halo, s_dst = ctx.scales
+        g_l = pg.split[0]
+        s_ext, s_dst = ctx.scales
+        s_loc = s_ext[:pg.n_local] if s_ext is not None else None
+        s_halo = s_ext[pg.n_local:] if s_ext is not None else None
         g = _f32c(g, "grad")
         out = ctx.saved_tensors[0] if ctx.relu else None
         g_bias = None
@@ -951,17 +968,16 @@ class _AggregatePartitioned(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dev = g.device
             cur, cs = torch.cuda.current_stream(dev), pg._comm_stream()
-            # transposed: the targets' rows are gathered (scaled by the per-target factor), the sources' rows written
-            g_halo, _ = gather_reduce_raw(g, g_h.csc, _lib.OP_SUM, src_scale=s_dst, out_scale=s_halo)
             cs.wait_stream(cur)
-            with torch.cuda.stream(cs):
-                back = pg.halo_grad_raw(g_halo)
-            g_halo.record_stream(cs)
+            with torch.cuda.stream(cs):   # transposed halo part + exchange in one kernel, on the communication stream
+                back = pg.halo_grad_fused(g, tgt_scale=s_dst, halo_scale=s_halo)
+            g.record_stream(cs)
             gx, _ = gather_reduce_raw(g, g_l.csc, _lib.OP_SUM, src_scale=s_dst, out_scale=s_loc)
             cur.wait_stream(cs)
             back.record_stream(cur)
             if pg.send_csr is not None:
-                gx, _ = gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm, addend=gx)
+                gx, _ = gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm, addend=gx,
+                                          label="halo_grad_land")
         return gx, g_bias, None, None, None
 
 
@@ -969,12 +985,12 @@ def aggregate_partitioned(x, pg, op: str = "sum", bias=None, relu: bool = False)
     """Linear neighbourhood aggregation of this rank's rows on a partitioned graph (``keras_geometric_b200.dist``):
     ``op`` in "sum", "mean", "gcn" (symmetric normalisation with the total in-degree, utils/main.py:20-33)."""
     if op == "sum":
-        scales = (None, None, None)
+        scales = (None, None)
     elif op == "mean":
-        scales = (None, None, pg.split[2])
+        scales = (None, pg.split[2])
     elif op == "gcn":
-        dis, dis_halo = pg.gcn_dis_split()
-        scales = (dis, dis_halo, dis)
+        dis, dis_ext = pg.gcn_dis_split()
+        scales = (dis_ext, dis)
     else:
         raise ValueError(f"aggregate_partitioned: unsupported aggregation {op!r}")
     return _AggregatePartitioned.apply(x, bias, pg, scales, relu)
