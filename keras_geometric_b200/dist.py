@@ -302,12 +302,16 @@ class PartitionedGraph:
         self._n_loops = self.n_local if n_loops_local else 0
         self._graph = None
         self._split = None
-        # deterministic backward of the pack: CSR of send_idx (which packed rows came from local row r)
+        # deterministic backward of the pack: CSR over the DISTINCT rows of send_idx (which returned gradient rows
+        # belong to owned row r).  Only rows somebody asked for are touched when the gradients land.
         if p.n_send:
-            s_ei = torch.stack([torch.zeros_like(p.send_idx), p.send_idx]).contiguous()
-            self.send_csr = build_csr(s_ei, self.n_local, 1, 0, by_source=False)
+            uniq, inv = torch.unique(p.send_idx.long(), return_inverse=True)
+            s_ei = torch.stack([torch.zeros_like(inv), inv]).to(torch.int32).contiguous()
+            self.send_csr = build_csr(s_ei, int(uniq.numel()), 1, 0, by_source=False)
+            self.send_rows = uniq.to(torch.int32)
         else:
             self.send_csr = None
+            self.send_rows = None
         self._dis_ext = None
 
     @property
@@ -476,6 +480,15 @@ class PartitionedGraph:
             win.barrier()                                   # every rank's rows have landed
         return win.back_view(self.plan.n_send, F)
 
+    def land_into(self, back: torch.Tensor, acc: torch.Tensor) -> torch.Tensor:
+        """acc[r] += sum of the returned gradient rows of owned row r, IN PLACE, for the rows some peer asked for
+        (deterministic segmented sum in slot order; every other row of ``acc`` is left untouched)."""
+        from . import _lib, ops
+        if self.send_csr is not None:
+            ops.gather_reduce_raw(back, self.send_csr, _lib.OP_SUM, col=self.send_csr.perm, addend=acc,
+                                  row_ids=self.send_rows, out=acc, label="halo_grad_land")
+        return acc
+
     def _dummy_row(self, F: int) -> torch.Tensor:
         d = getattr(self, "_dummy", None)
         if d is None or d.shape[1] < F:
@@ -534,11 +547,7 @@ def _exchange_fwd(x_local: torch.Tensor, pg: PartitionedGraph) -> torch.Tensor:
 
 def _land(back: torch.Tensor, pg: PartitionedGraph, F: int, device, dtype) -> torch.Tensor:
     """Deterministic per-owner sum of the returned gradient rows (CSR of the send list)."""
-    from . import _lib, ops
-    if pg.plan.n_send and pg.send_csr is not None:
-        g_local, _ = ops.gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm)
-        return g_local
-    return torch.zeros((pg.n_local, F), dtype=dtype, device=device)
+    return pg.land_into(back, torch.zeros((pg.n_local, F), dtype=dtype, device=device))
 
 
 class _HaloExchange(torch.autograd.Function):

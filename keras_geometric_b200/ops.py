@@ -871,7 +871,6 @@ class _SagePartitioned(torch.autograd.Function):
         cur, cs = torch.cuda.current_stream(dev), pg._comm_stream()
         K = int(x.shape[1])
         need_x = ctx.needs_input_grad[0]
-        send_csr = pg.send_csr
 
         def send_back(grad):   # transposed gather over the halo-source edges FUSED with the exchange: every finished
             cs.wait_stream(cur)   # halo-row gradient is stored straight into its owner's window (communication stream)
@@ -883,10 +882,7 @@ class _SagePartitioned(torch.autograd.Function):
         def land(back, acc):   # + per-owner segmented sum of the returned rows
             cur.wait_stream(cs)
             back.record_stream(cur)
-            if send_csr is None:
-                return acc
-            res, _ = gather_reduce_raw(back, send_csr, _lib.OP_SUM, col=send_csr.perm, addend=acc)
-            return res
+            return pg.land_into(back, acc)
 
         if ctx.reorder:
             # out = act(S A_l z + S A_h halo(z) + x Ws + b), z = x Wn:  dz = A^T (S g) needs the exchange even when x
@@ -975,9 +971,7 @@ class _AggregatePartitioned(torch.autograd.Function):
             gx, _ = gather_reduce_raw(g, g_l.csc, _lib.OP_SUM, src_scale=s_dst, out_scale=s_loc)
             cur.wait_stream(cs)
             back.record_stream(cur)
-            if pg.send_csr is not None:
-                gx, _ = gather_reduce_raw(back, pg.send_csr, _lib.OP_SUM, col=pg.send_csr.perm, addend=gx,
-                                          label="halo_grad_land")
+            gx = pg.land_into(back, gx)
         return gx, g_bias, None, None, None
 
 
