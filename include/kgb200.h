@@ -244,6 +244,10 @@ typedef struct kgb_halo_push_args {
   float* dst[KGB_MAX_PEERS];             /* peer p's window region (device pointer valid on this device)   */
   int64_t dst_row0[KGB_MAX_PEERS];       /* first row of this rank's block inside peer p's region          */
   int64_t ldd;             /* leading dimension of the window rows (floats)                                 */
+  int64_t slot_rot;        /* kgb_halo_push visits the slots in 256-slot chunks in a strided (golden-ratio)
+                              order that starts at the chunk holding this slot: one rank's stores are spread over
+                              all receivers at any moment, and with slot_rot = slot_begin[(rank + 1) % n_peers]
+                              the ranks start at different receivers - no GPU is stored into by everyone at once */
 } kgb_halo_push_args;
 int kgb_halo_push(int device, const kgb_halo_push_args* a, kgb_stream_t stream);
 

@@ -49,7 +49,7 @@ class HaloPushArgs(Structure):
 
     _fields_ = [("src", c_void_p), ("lds", c_int64), ("idx", c_void_p), ("F", c_int32), ("n_peers", c_int32),
                 ("slot_begin", c_int64 * (MAX_PEERS + 1)), ("dst", c_void_p * MAX_PEERS),
-                ("dst_row0", c_int64 * MAX_PEERS), ("ldd", c_int64)]
+                ("dst_row0", c_int64 * MAX_PEERS), ("ldd", c_int64), ("slot_rot", c_int64)]
 
 
 class HubTable(Structure):

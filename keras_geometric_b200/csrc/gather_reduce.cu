@@ -31,7 +31,13 @@ struct PushTab {
   float* dst[KGB_MAX_PEERS];
   int64_t dst_row0[KGB_MAX_PEERS];
   int64_t ldd;
+  // halo_push_kernel only: the walk visits 256-slot chunks in the order (k * perm_mul + perm_add) mod n_chunks, so at
+  // any moment the stores of one rank are spread over all receivers in proportion to their blocks, and different
+  // ranks start at different places - with the natural order all ranks store into peer 0 first, then all into
+  // peer 1 ... and the transfer runs at one receiver's ingest rate (measured: 330 GB/s per sender at 8 GPUs)
+  int64_t n_chunks, perm_mul, perm_add;
 };
+constexpr int PUSH_CHUNK = 256;
 
 __device__ __forceinline__ float* push_row(const PushTab& tab, int64_t s) {
   int p = 0;
@@ -832,16 +838,23 @@ halo_push_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __re
   const int gw = lane / G;
   const int nv = F / VEC;
   const int64_t n_slots = tab.slot_begin[tab.n_peers];
+  const int64_t n_walk = tab.n_chunks * PUSH_CHUNK;
   const int64_t gpb = (int64_t)(blockDim.x >> 5) * GPW;
   const int64_t stride = (int64_t)gridDim.x * gpb;
-  for (int64_t s0 = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; s0 < n_slots;
+  for (int64_t s0 = (int64_t)blockIdx.x * gpb + (int64_t)(threadIdx.x >> 5) * GPW + gw; s0 < n_walk;
        s0 += (int64_t)U * stride) {
     int64_t r[U];
     float v[U][NCH][VEC];
+    int64_t sl[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t s = s0 + (int64_t)u * stride;
-      r[u] = s < n_slots ? (idx ? (int64_t)__ldg(idx + s) : s) : -1;
+      const int64_t sw = s0 + (int64_t)u * stride;          // position in the walk
+      const int64_t k = sw / PUSH_CHUNK;
+      const int64_t kp = (int64_t)(((unsigned long long)k * (unsigned long long)tab.perm_mul +
+                                    (unsigned long long)tab.perm_add) % (unsigned long long)tab.n_chunks);
+      const int64_t s = kp * PUSH_CHUNK + (sw - k * PUSH_CHUNK);
+      sl[u] = s;
+      r[u] = (sw < n_walk && s < n_slots) ? (idx ? (int64_t)__ldg(idx + s) : s) : -1;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -853,7 +866,7 @@ halo_push_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __re
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (r[u] < 0) continue;
-      float* drow = push_row(tab, s0 + (int64_t)u * stride);
+      float* drow = push_row(tab, sl[u]);
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch)
         if ((gl + ch * G) < nv) st_vec<VEC>(drow + (gl + ch * G) * VEC, v[u][ch]);
@@ -1210,6 +1223,17 @@ int kgb_halo_push(int device, const kgb_halo_push_args* a, kgb_stream_t stream) 
   PushTab tab;
   tab.n_peers = a->n_peers;
   tab.ldd = a->ldd;
+  {
+    const int64_t total = a->slot_begin[a->n_peers];
+    tab.n_chunks = total > 0 ? ceil_div(total, (int64_t)PUSH_CHUNK) : 1;
+    int64_t mul = (int64_t)((double)tab.n_chunks * 0.6180339887) | 1;   // golden-ratio stride, made coprime below
+    auto gcd = [](int64_t x, int64_t y) { while (y) { const int64_t t = x % y; x = y; y = t; } return x; };
+    while (mul > 1 && gcd(mul, tab.n_chunks) != 1) mul -= 2;
+    if (mul < 1 || gcd(mul, tab.n_chunks) != 1) mul = 1;
+    tab.perm_mul = mul;
+    const int64_t rot = (a->slot_rot > 0 && a->slot_rot < total) ? a->slot_rot : 0;
+    tab.perm_add = (rot / PUSH_CHUNK) % tab.n_chunks;
+  }
   bool can4 = aligned16(a->src) && a->lds % 4 == 0 && a->ldd % 4 == 0;
   for (int p = 0; p <= a->n_peers; ++p) {
     tab.slot_begin[p] = a->slot_begin[p];

@@ -251,6 +251,7 @@ class PeerWindow:
             a.dst[p] = self.ptr[p] + (0 if forward else self.back_off[p])
             a.dst_row0[p] = row0[p]
         a.ldd = F
+        a.slot_rot = begin[(self.rank + 1) % self.world]   # stagger the receivers across the ranks
         return a
 
     def push(self, src: torch.Tensor, idx, F: int, forward: bool) -> None:
