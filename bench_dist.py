@@ -105,6 +105,12 @@ def run(args, world, rank, local_rank):
                          device=dev, dtype=torch.float64)
     allstats = [torch.zeros_like(stats) for _ in range(world)]
     dist.all_gather(allstats, stats)
+    mine = {}
+    for rec in prof:
+        d = mine.setdefault(rec["label"], [0.0, 0])
+        d[0] += rec["start"].elapsed_time(rec["end"]); d[1] += 1
+    per_rank_ms = [None] * world     # CUDA-event time of every launch group, per step, on every rank
+    dist.all_gather_object(per_rank_ms, {k: round(v[0] / args.steps, 3) for k, v in mine.items()})
     n_layers = len(layers)
     value = n_layers * e_global / (ms_step * 1e-3) / 1e9
     transport = "peer-memory windows (CUDA IPC + kgb_halo_push over NVLink)" if pg._window is not None else \
@@ -153,7 +159,8 @@ def run(args, world, rank, local_rank):
             "roofline": ({"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak,
                           "unit": "GB/s", "frac": kernels[dom]["frac"], "alg_frac": kernels[dom]["frac"],
                           "traffic": None} if dom else None),
-            "kernels": kernels, "gpu_launches": int(launches), "clocks": clocks,
+            "kernels": kernels, "launch_groups_ms_per_step_per_rank": per_rank_ms,
+            "gpu_launches": int(launches), "clocks": clocks,
             "halo": {"max_rows_per_rank": max(halo_rows), "bytes_per_step_busiest_direction": link_bytes,
                      "nvlink_floor_ms_at_770GBps": link_bytes / 770e9 * 1e3},
             "c5_strong": c5,
