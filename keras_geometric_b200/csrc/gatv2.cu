@@ -152,7 +152,7 @@ __device__ __forceinline__ void gat_fwd_range(const GatP& p, const LaneCtx<VEC, 
                                               int64_t k0, int64_t k1, float& m, float& l, float (&acc)[CC][VEC]) {
   constexpr int G = LPH * HPG;
 #ifndef KGB_GAT_U
-#define KGB_GAT_U 8
+#define KGB_GAT_U 4   // measured on C4 (H8C8 / H1C64 / H8C32): U=4 at 4 CTAs/SM 3.49 / 3.78 / 11.3 ms, U=8 at 3: 3.87 / 4.18 / 11.6
 #endif
   constexpr int UMAX = (KGB_GAT_U / CC) < 1 ? 1 : (KGB_GAT_U / CC);
   constexpr int U = (G < UMAX) ? G : UMAX;
@@ -247,8 +247,11 @@ __device__ __forceinline__ void gat_fwd_store(const GatP& p, const LaneCtx<VEC, 
   }
 }
 
+#ifndef KGB_GAT_MINB_FWD
+#define KGB_GAT_MINB_FWD 4
+#endif
 template <int VEC, int LPH, int CC, int HPG>
-__global__ void __launch_bounds__(256, 3) gatv2_fwd_kernel(const GatP p) {
+__global__ void __launch_bounds__(256, KGB_GAT_MINB_FWD) gatv2_fwd_kernel(const GatP p) {
   using Ctx = LaneCtx<VEC, LPH, CC, HPG>;
   constexpr int G = Ctx::G;
   Ctx L;
@@ -326,7 +329,7 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
                                                    float (&ga)[CC][VEC]) {
   constexpr int G = LPH * HPG;
 #ifndef KGB_GAT_U_DST
-#define KGB_GAT_U_DST 4
+#define KGB_GAT_U_DST 4   // with 4 CTAs/SM: 4.13 ms (H8C8 on C4); U=8 / 2 CTAs: 5.26, U=4 / 2 CTAs: 5.72
 #endif
   constexpr int UMAX = (KGB_GAT_U_DST / CC) < 1 ? 1 : (KGB_GAT_U_DST / CC);
   constexpr int U = (G < UMAX) ? G : UMAX;
@@ -408,10 +411,10 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
 }
 
 #ifndef KGB_GAT_MINB_DST
-#define KGB_GAT_MINB_DST 2
+#define KGB_GAT_MINB_DST 4
 #endif
 #ifndef KGB_GAT_MINB_SRC
-#define KGB_GAT_MINB_SRC 2
+#define KGB_GAT_MINB_SRC 4
 #endif
 template <int VEC, int LPH, int CC, int HPG>
 __global__ void __launch_bounds__(256, KGB_GAT_MINB_DST) gatv2_bwd_dst_kernel(const GatP p) {
@@ -483,7 +486,7 @@ __device__ __forceinline__ void gat_bwd_src_range(const GatP& p, const LaneCtx<V
                                                   int64_t k0, int64_t k1, float (&ghj)[CC][VEC]) {
   constexpr int G = LPH * HPG;
 #ifndef KGB_GAT_U_SRC
-#define KGB_GAT_U_SRC 2
+#define KGB_GAT_U_SRC 2   // with 4 CTAs/SM: 7.19 ms (H8C8 on C4); 2 CTAs/SM: 11.4; U=4 / 3 CTAs: 7.50; U=8 / 3: 13.5
 #endif
   constexpr int UMAX = (KGB_GAT_U_SRC / CC) < 1 ? 1 : (KGB_GAT_U_SRC / CC);
   constexpr int U = (G < UMAX) ? G : UMAX;

@@ -842,11 +842,15 @@ class _SagePartitioned(torch.autograd.Function):
                 halo = pg.halo_rows_raw(x)
             x.record_stream(cs)
             part, _ = gather_reduce_raw(x, g_l.csr, _lib.OP_SUM, out_scale=scale)
+            # the root transform does not need the halo: it runs while the rows are still travelling, and the
+            # neighbour transform adds it in its epilogue (one extra [n, N] round trip buys ~the whole GEMM of overlap)
+            hi, lo = _split_weight(w_self, transpose=True)
+            root = linear_tc(x, hi, lo, N)
             cur.wait_stream(cs)
             halo.record_stream(cur)
             agg, _ = gather_reduce_raw(halo, g_h.csr, _lib.OP_SUM, out_scale=scale, addend=part)
-            hi, lo = _split_weight_pair(w_neigh, w_self, transpose=True)
-            out = linear_tc2(agg, x, hi, lo, N, bias=bias_c, relu=relu)
+            hi, lo = _split_weight(w_neigh, transpose=True)
+            out = linear_tc(agg, hi, lo, N, c=root, bias=bias_c, relu=relu)
             ctx.save_for_backward(x, w_neigh, w_self, agg, *([out] if relu else []))
         ctx.pg, ctx.scale, ctx.relu, ctx.reorder, ctx.has_bias = pg, scale, relu, reorder, bias is not None
         return out
