@@ -105,7 +105,7 @@ __device__ __forceinline__ void accum(float& m, int32_t& a, float v, float w, in
 
 // Load the feature rows of U consecutive slots of the current index batch.  Slots past the end of the
 // batch carry index 0 (a valid row) and are simply never accumulated, so the loads need no predicate.
-template <int VEC, int G, int NCH, int U, bool HAS_W>
+template <int VEC, int G, int NCH, int U, bool HAS_W, bool SPLIT>
 __device__ __forceinline__ void load_batch_full(const GRP& p, int32_t myc, float myw, int j, int gl, unsigned gmask,
                                                 const bool (&on)[NCH], float (&v)[U][NCH][VEC], float (&w)[U],
                                                 int32_t (&c)[U]) {
@@ -120,7 +120,10 @@ __device__ __forceinline__ void load_batch_full(const GRP& p, int32_t myc, float
     w[u] = 1.f;
     if constexpr (HAS_W) w[u] = __shfl_sync(gmask, myw, j + u, G);
     const int64_t cu = c[u];
-    const float* rp = (cu < p.n_split_src) ? p.x + cu * p.ldx : p.x2 + (cu - p.n_split_src) * p.ldx2;
+    const float* rp = p.x + cu * p.ldx;
+    if constexpr (SPLIT) {
+      if (cu >= p.n_split_src) rp = p.x2 + (cu - p.n_split_src) * p.ldx2;
+    }
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) ld_vec<VEC>(rp + loff[ch], v[u][ch]);
   }
@@ -140,7 +143,7 @@ __device__ __forceinline__ void accum_all(float (&acc)[NCH][VEC], int32_t (&aidx
 }
 
 // Reduce CSR slots [k0, k1) of one row into acc (all lanes of the group call this together).
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT>
 __device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k1, int gl,
                                              unsigned gmask, const bool (&on)[NCH],
                                              float (&acc)[NCH][VEC], int32_t (&aidx)[NCH][VEC]) {
@@ -172,7 +175,7 @@ __device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k
       float v[U][NCH][VEC];
       float w[U];
       int32_t c[U];
-      load_batch_full<VEC, G, NCH, U, HAS_W>(p, myc, myw, j, gl, gmask, on, v, w, c);
+      load_batch_full<VEC, G, NCH, U, HAS_W, SPLIT>(p, myc, myw, j, gl, gmask, on, v, w, c);
       if (j + U <= cnt) {  // group-uniform: a full batch needs no predication
         accum_all<VEC, NCH, U, IS_MAX, HAS_W>(acc, aidx, v, w, c, on, negate);
       } else {
@@ -194,14 +197,14 @@ __device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k
   }
 }
 
-template <int VEC, int G, int NCH, bool IS_MAX>
+template <int VEC, int G, int NCH, bool IS_MAX, bool SPLIT>
 __device__ __forceinline__ void epilogue(const GRP& p, int64_t slot, int64_t deg, int gl,
                                          const bool (&on)[NCH], float (&acc)[NCH][VEC],
                                          int32_t (&aidx)[NCH][VEC]) {
   const int64_t row_out = p.row_ids ? (int64_t)__ldg(p.row_ids + slot) : slot;
   float os = 1.f;
   if (p.out_scale) os = __ldg(p.out_scale + slot);
-  if (row_out >= p.n_split_out) {
+  if (SPLIT && row_out >= p.n_split_out) {
     // second output space: a local buffer, or (fused halo-gradient exchange) the owner's window over NVLink
     const int64_t r2 = row_out - p.n_split_out;
     float* drow = p.has_push ? push_row(p.tab, r2) : p.out2 + r2 * p.ldo2;
@@ -266,7 +269,7 @@ __device__ __forceinline__ void epilogue(const GRP& p, int64_t slot, int64_t deg
 
 // Walk the contiguous edge range of CSR rows [ra, rb) of the block starting at row r0 (group-uniform
 // arguments).  my_hi holds rowptr[r0 + gl + 1] for lane gl of the group.
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT>
 __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int rb, int64_t k0, int64_t k1,
                                           int64_t my_hi, int gl, unsigned gmask, const bool (&on)[NCH]) {
   constexpr int UMAX = (8 / NCH) < 1 ? 1 : (8 / NCH);
@@ -304,7 +307,7 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
       float w[U];
       int32_t c[U];
       const int64_t kk0 = k + j;
-      load_batch_full<VEC, G, NCH, U, HAS_W>(p, myc, myw, j, gl, gmask, on, v, w, c);
+      load_batch_full<VEC, G, NCH, U, HAS_W, SPLIT>(p, myc, myw, j, gl, gmask, on, v, w, c);
       if (j + U <= cnt && kk0 + U <= cur_end) {
         // fast path (group-uniform): a full batch that lies inside the current row
         accum_all<VEC, NCH, U, IS_MAX, HAS_W>(acc, aidx, v, w, c, on, negate);
@@ -329,7 +332,7 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
         done = lim;
         if (done >= valid) break;
         // the current row is complete: flush it and move to the next one
-        epilogue<VEC, G, NCH, IS_MAX>(p, r0 + cur, cur_end - cur_start, gl, on, acc, aidx);
+        epilogue<VEC, G, NCH, IS_MAX, SPLIT>(p, r0 + cur, cur_end - cur_start, gl, on, acc, aidx);
         init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
         ++cur;
         cur_start = cur_end;
@@ -342,7 +345,7 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
   }
   // rows that end exactly at k1 (the last one with edges, then any empty rows)
   while (cur < rb) {
-    epilogue<VEC, G, NCH, IS_MAX>(p, r0 + cur, cur_end - cur_start, gl, on, acc, aidx);
+    epilogue<VEC, G, NCH, IS_MAX, SPLIT>(p, r0 + cur, cur_end - cur_start, gl, on, acc, aidx);
     init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
     ++cur;
     cur_start = cur_end;
@@ -357,7 +360,7 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
 #endif
 constexpr int UNIT_ROWS = KGB_GR_UNIT_ROWS;
 
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT>
 __device__ __forceinline__ void do_chunk(const GRP& p, int64_t t, int gl, unsigned gmask, const bool (&on)[NCH]) {
   // one chunk of a hub row -> raw partial
   float acc[NCH][VEC];
@@ -369,7 +372,7 @@ __device__ __forceinline__ void do_chunk(const GRP& p, int64_t t, int gl, unsign
   const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
   const int64_t k0 = rs + ci * p.hub_chunk;
   const int64_t k1 = (k0 + p.hub_chunk < re) ? k0 + p.hub_chunk : re;
-  reduce_range<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, k0, k1, gl, gmask, on, acc, aidx);
+  reduce_range<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT>(p, k0, k1, gl, gmask, on, acc, aidx);
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     if (!on[ch]) continue;
@@ -379,7 +382,7 @@ __device__ __forceinline__ void do_chunk(const GRP& p, int64_t t, int gl, unsign
   }
 }
 
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT>
 __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, int gw, unsigned gmask,
                                              const bool (&on)[NCH]) {
   // a block of G consecutive rows: lane gl holds rowptr[r0+gl], rowptr[r0+gl+1]
@@ -399,7 +402,7 @@ __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, i
     if (seg_end > cur) {
       const int64_t k0 = __shfl_sync(gmask, my_lo, cur, G);
       const int64_t k1 = __shfl_sync(gmask, my_hi, seg_end - 1, G);
-      walk_rows<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, r0, cur, seg_end, k0, k1, my_hi, gl, gmask, on);
+      walk_rows<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT>(p, r0, cur, seg_end, k0, k1, my_hi, gl, gmask, on);
     }
     cur = seg_end + 1;  // the hub row (if any) is written by hub_finish_kernel
   }
@@ -421,7 +424,7 @@ __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, i
 // with the id structure of power-law graphs (RMAT: the degree depends on the low id bits), which left
 // 27 % of the SM-cycles idle in the first version.  Which warp computes a row never changes the
 // result, so the output stays deterministic.
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT>
 __global__ void __launch_bounds__(256, ((VEC == 4 && G >= 16) ? (IS_MAX ? KGB_GR_MINB_MAX : KGB_GR_MINB_WIDE)
                                                               : KGB_GR_MINB_NARROW))
 gather_reduce_kernel(const GRP p) {
@@ -451,14 +454,14 @@ gather_reduce_kernel(const GRP p) {
     if (u >= n_units) break;
     if (u < chunk_units) {
       const int64_t t = u * GPW + gw;
-      if (t < p.n_chunks) do_chunk<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, t, gl, gmask, on);
+      if (t < p.n_chunks) do_chunk<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT>(p, t, gl, gmask, on);
     } else {
       int64_t ui = u - chunk_units;
       if (p.unit_order) ui = __ldg(p.unit_order + ui);
       const int64_t base = ui * UNIT_ROWS;
       for (int b = gw; b < BPU; b += GPW) {
         const int64_t r0 = base + (int64_t)b * G;
-        if (r0 < p.n_rows) do_row_block<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS>(p, r0, gl, gw, gmask, on);
+        if (r0 < p.n_rows) do_row_block<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT>(p, r0, gl, gw, gmask, on);
       }
     }
     if (!p.work) u += (int64_t)gridDim.x * wpb;
@@ -478,7 +481,7 @@ gather_reduce_kernel(const GRP p) {
 }
 
 // Merge the chunk partials of every hub row in chunk order, then run the epilogue.
-template <int VEC, int G, int NCH, bool IS_MAX>
+template <int VEC, int G, int NCH, bool IS_MAX, bool SPLIT>
 __global__ void __launch_bounds__(256) hub_finish_kernel(const GRP p) {
   constexpr int GPW = 32 / G;
   const int lane = threadIdx.x & 31;
@@ -538,7 +541,7 @@ __global__ void __launch_bounds__(256) hub_finish_kernel(const GRP p) {
       }
     }
     const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
-    epilogue<VEC, G, NCH, IS_MAX>(p, row, re - rs, gl, on, acc, aidx);
+    epilogue<VEC, G, NCH, IS_MAX, SPLIT>(p, row, re - rs, gl, on, acc, aidx);
   }
 }
 
@@ -945,23 +948,33 @@ static int launch_gr(int device, const GRP& p, bool is_max, cudaStream_t st) {
   const int64_t cap = (int64_t)sm_count(device) * 4;
   const int grid = (int)(need > cap ? cap : (need < 1 ? 1 : need));
   const bool ew = p.edge_w != nullptr, ss = p.src_scale != nullptr;
+  // the split-source / split-output variant is a separate instantiation: the common path pays nothing for it
+  const bool split = p.x2 != nullptr || p.n_split_out != INT64_MAX;
+#define KGB_GR_LAUNCH(MAXF, EW, SS)                                                                        \
+  do {                                                                                                     \
+    if (split) gather_reduce_kernel<VEC, G, NCH, MAXF, EW, SS, !MAXF><<<grid, 256, 0, st>>>(p);            \
+    else gather_reduce_kernel<VEC, G, NCH, MAXF, EW, SS, false><<<grid, 256, 0, st>>>(p);                  \
+  } while (0)
   if (is_max) {
     if (ew || ss) { set_error("max/min do not take edge weights"); return KGB_ERR_INVALID; }
-    gather_reduce_kernel<VEC, G, NCH, true, false, false><<<grid, 256, 0, st>>>(p);
+    if (split) { set_error("max/min do not take split operands"); return KGB_ERR_INVALID; }
+    KGB_GR_LAUNCH(true, false, false);
   } else if (ew && ss) {
-    gather_reduce_kernel<VEC, G, NCH, false, true, true><<<grid, 256, 0, st>>>(p);
+    KGB_GR_LAUNCH(false, true, true);
   } else if (ew) {
-    gather_reduce_kernel<VEC, G, NCH, false, true, false><<<grid, 256, 0, st>>>(p);
+    KGB_GR_LAUNCH(false, true, false);
   } else if (ss) {
-    gather_reduce_kernel<VEC, G, NCH, false, false, true><<<grid, 256, 0, st>>>(p);
+    KGB_GR_LAUNCH(false, false, true);
   } else {
-    gather_reduce_kernel<VEC, G, NCH, false, false, false><<<grid, 256, 0, st>>>(p);
+    KGB_GR_LAUNCH(false, false, false);
   }
+#undef KGB_GR_LAUNCH
   KGB_CHECK_LAUNCH();
   if (p.n_hubs > 0) {
     const int hgrid = grid_for(device, p.n_hubs, G);
-    if (is_max) hub_finish_kernel<VEC, G, NCH, true><<<hgrid, 256, 0, st>>>(p);
-    else hub_finish_kernel<VEC, G, NCH, false><<<hgrid, 256, 0, st>>>(p);
+    if (is_max) hub_finish_kernel<VEC, G, NCH, true, false><<<hgrid, 256, 0, st>>>(p);
+    else if (split) hub_finish_kernel<VEC, G, NCH, false, true><<<hgrid, 256, 0, st>>>(p);
+    else hub_finish_kernel<VEC, G, NCH, false, false><<<hgrid, 256, 0, st>>>(p);
     KGB_CHECK_LAUNCH();
   }
   return KGB_OK;
