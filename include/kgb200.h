@@ -36,7 +36,10 @@ enum {
 };
 
 enum { KGB_OP_SUM = 0, KGB_OP_MEAN = 1, KGB_OP_MAX = 2, KGB_OP_MIN = 3,
-       KGB_OP_MAX_RAW = 4 /* keras segment_max itself: empty segment = -inf, no inf -> 0 rewrite */ };
+       KGB_OP_MAX_RAW = 4 /* keras segment_max itself: empty segment = -inf, no inf -> 0 rewrite */,
+       KGB_OP_SQDEV = 5   /* second pass of the std aggregator (layers/aggregators.py:174-232): with the row means
+                             in `addend`, out = sqrt(max(sum_k (x[col_k] - mean_row)^2 / max(count, 1e-8), 0)),
+                             0 where count <= 1 */ };
 enum { KGB_ACT_NONE = 0, KGB_ACT_RELU = 1 };
 
 /* status bits written by kgb_csr_build into *status (device int32) */

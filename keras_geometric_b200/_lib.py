@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 from . import _build
 
-OP_SUM, OP_MEAN, OP_MAX, OP_MIN, OP_MAX_RAW = 0, 1, 2, 3, 4
+OP_SUM, OP_MEAN, OP_MAX, OP_MIN, OP_MAX_RAW, OP_SQDEV = 0, 1, 2, 3, 4, 5
 OPS = {"sum": OP_SUM, "mean": OP_MEAN, "max": OP_MAX, "min": OP_MIN, "max_raw": OP_MAX_RAW}
 MAX_OPS = (OP_MAX, OP_MIN, OP_MAX_RAW)
 ACT_NONE, ACT_RELU = 0, 1

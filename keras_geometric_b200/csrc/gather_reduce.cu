@@ -53,7 +53,7 @@ struct GRP {
   const int32_t* row_ids;
   const float* edge_w; const float* src_scale; const float* out_scale;
   const float* addend; int64_t ld_addend; float addend_scale;
-  const float* bias; int act; int mean; int negate; int raw_max;
+  const float* bias; int act; int mean; int negate; int raw_max; int sqdev;
   float* out; int64_t ldo; int32_t* arg;
   const int32_t* hub_row; const int32_t* hub_chunk_base; const int32_t* hub_nchunks;
   const int32_t* chunk_hub;
@@ -78,15 +78,36 @@ __device__ __forceinline__ void init_acc(float (&acc)[NCH][VEC], int32_t (&aidx)
     }
 }
 
+// SQDEV (std aggregator, second pass): the mean of the row that is about to be reduced rides in the argmax slots
+template <int VEC, int G, int NCH, bool SQDEV, class P>
+__device__ __forceinline__ void load_mu(const P& p, int64_t row, int gl, const bool (&on)[NCH],
+                                        int32_t (&aidx)[NCH][VEC]) {
+  if constexpr (SQDEV) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      float mu[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) mu[e] = 0.f;
+      if (on[ch]) ld_vec<VEC>(p.addend + row * p.ld_addend + (gl + ch * G) * VEC, mu);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) aidx[ch][e] = __float_as_int(mu[e]);
+    }
+  }
+}
+
 __device__ __forceinline__ float fmax_nan(float a, float b) {
   float d;
   asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));  // FMNMX.NAN: NaN propagates like torch's amax
   return d;
 }
 
-template <bool IS_MAX, bool HAS_W = true>
+template <bool IS_MAX, bool HAS_W = true, bool SQDEV = false>
 __device__ __forceinline__ void accum(float& m, int32_t& a, float v, float w, int32_t c, bool negate) {
-  if constexpr (IS_MAX) {
+  if constexpr (SQDEV) {
+    // sum of squared deviations from the row's mean, whose bits ride in the (otherwise unused) argmax slot
+    const float d = __fsub_rn(v, __int_as_float(a));
+    m = __fadd_rn(m, __fmul_rn(d, d));   // square, then add: like segment_sum(square(m - mean)) (aggregators.py:211-216)
+  } else if constexpr (IS_MAX) {
     // branch-free on purpose: an if/else chain compiles to divergent BSSY/BRA/BSYNC per element
     const float val = negate ? -v : v;
     const float mo = m;
@@ -130,7 +151,7 @@ __device__ __forceinline__ void load_batch_full(const GRP& p, int32_t myc, float
 }
 
 // Lanes whose `on` is false accumulate harmless duplicates; they are never stored.
-template <int VEC, int NCH, int U, bool IS_MAX, bool HAS_W>
+template <int VEC, int NCH, int U, bool IS_MAX, bool HAS_W, bool SQDEV>
 __device__ __forceinline__ void accum_all(float (&acc)[NCH][VEC], int32_t (&aidx)[NCH][VEC],
                                           const float (&v)[U][NCH][VEC], const float (&w)[U], const int32_t (&c)[U],
                                           const bool (&on)[NCH], bool negate) {
@@ -139,11 +160,11 @@ __device__ __forceinline__ void accum_all(float (&acc)[NCH][VEC], int32_t (&aidx
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) accum<IS_MAX, HAS_W>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
+      for (int e = 0; e < VEC; ++e) accum<IS_MAX, HAS_W, SQDEV>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
 }
 
 // Reduce CSR slots [k0, k1) of one row into acc (all lanes of the group call this together).
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV>
 __device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k1, int gl,
                                              unsigned gmask, const bool (&on)[NCH],
                                              float (&acc)[NCH][VEC], int32_t (&aidx)[NCH][VEC]) {
@@ -177,7 +198,7 @@ __device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k
       int32_t c[U];
       load_batch_full<VEC, G, NCH, U, HAS_W, SPLIT>(p, myc, myw, j, gl, gmask, on, v, w, c);
       if (j + U <= cnt) {  // group-uniform: a full batch needs no predication
-        accum_all<VEC, NCH, U, IS_MAX, HAS_W>(acc, aidx, v, w, c, on, negate);
+        accum_all<VEC, NCH, U, IS_MAX, HAS_W, SQDEV>(acc, aidx, v, w, c, on, negate);
       } else {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -186,7 +207,7 @@ __device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k
             for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
               for (int e = 0; e < VEC; ++e)
-                accum<IS_MAX, HAS_W>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
+                accum<IS_MAX, HAS_W, SQDEV>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
           }
         }
       }
@@ -197,7 +218,7 @@ __device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k
   }
 }
 
-template <int VEC, int G, int NCH, bool IS_MAX, bool SPLIT>
+template <int VEC, int G, int NCH, bool IS_MAX, bool SPLIT, bool SQDEV>
 __device__ __forceinline__ void epilogue(const GRP& p, int64_t slot, int64_t deg, int gl,
                                          const bool (&on)[NCH], float (&acc)[NCH][VEC],
                                          int32_t (&aidx)[NCH][VEC]) {
@@ -242,9 +263,14 @@ __device__ __forceinline__ void epilogue(const GRP& p, int64_t slot, int64_t deg
         if (r[e] != r[e]) a[e] = -1;
       }
       if (p.mean) r[e] = __fdiv_rn(r[e], den);
+      if constexpr (SQDEV) {
+        // population std (aggregators.py:218-226): sqrt(max(sum_sq / max(count, 1e-8), 0)); count <= 1 -> 0
+        r[e] = __fsqrt_rn(fmaxf(__fdiv_rn(r[e], den), 0.f));
+        if (deg <= 1) r[e] = 0.f;
+      }
       if (p.out_scale) r[e] = __fmul_rn(r[e], os);
     }
-    if (p.addend) {
+    if (!SQDEV && p.addend) {
       float ad[VEC];
       ld_vec<VEC>(p.addend + row_out * p.ld_addend + f0, ad);
 #pragma unroll
@@ -269,7 +295,7 @@ __device__ __forceinline__ void epilogue(const GRP& p, int64_t slot, int64_t deg
 
 // Walk the contiguous edge range of CSR rows [ra, rb) of the block starting at row r0 (group-uniform
 // arguments).  my_hi holds rowptr[r0 + gl + 1] for lane gl of the group.
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV>
 __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int rb, int64_t k0, int64_t k1,
                                           int64_t my_hi, int gl, unsigned gmask, const bool (&on)[NCH]) {
   constexpr int UMAX = (8 / NCH) < 1 ? 1 : (8 / NCH);
@@ -279,6 +305,7 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
   float acc[NCH][VEC];
   int32_t aidx[NCH][VEC];
   init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
+  load_mu<VEC, G, NCH, SQDEV>(p, r0 + ra, gl, on, aidx);
   int cur = ra;
   int64_t cur_start = k0;
   int64_t cur_end = __shfl_sync(gmask, my_hi, cur, G);
@@ -310,7 +337,7 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
       load_batch_full<VEC, G, NCH, U, HAS_W, SPLIT>(p, myc, myw, j, gl, gmask, on, v, w, c);
       if (j + U <= cnt && kk0 + U <= cur_end) {
         // fast path (group-uniform): a full batch that lies inside the current row
-        accum_all<VEC, NCH, U, IS_MAX, HAS_W>(acc, aidx, v, w, c, on, negate);
+        accum_all<VEC, NCH, U, IS_MAX, HAS_W, SQDEV>(acc, aidx, v, w, c, on, negate);
         continue;
       }
       // distribute the (up to U) loaded edges over the rows they belong to
@@ -326,15 +353,16 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
             for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
               for (int e = 0; e < VEC; ++e)
-                accum<IS_MAX, HAS_W>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
+                accum<IS_MAX, HAS_W, SQDEV>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
           }
         }
         done = lim;
         if (done >= valid) break;
         // the current row is complete: flush it and move to the next one
-        epilogue<VEC, G, NCH, IS_MAX, SPLIT>(p, r0 + cur, cur_end - cur_start, gl, on, acc, aidx);
+        epilogue<VEC, G, NCH, IS_MAX, SPLIT, SQDEV>(p, r0 + cur, cur_end - cur_start, gl, on, acc, aidx);
         init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
         ++cur;
+        load_mu<VEC, G, NCH, SQDEV>(p, r0 + cur, gl, on, aidx);
         cur_start = cur_end;
         cur_end = __shfl_sync(gmask, my_hi, cur, G);
       }
@@ -345,11 +373,11 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
   }
   // rows that end exactly at k1 (the last one with edges, then any empty rows)
   while (cur < rb) {
-    epilogue<VEC, G, NCH, IS_MAX, SPLIT>(p, r0 + cur, cur_end - cur_start, gl, on, acc, aidx);
+    epilogue<VEC, G, NCH, IS_MAX, SPLIT, SQDEV>(p, r0 + cur, cur_end - cur_start, gl, on, acc, aidx);
     init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
     ++cur;
     cur_start = cur_end;
-    if (cur < rb) cur_end = __shfl_sync(gmask, my_hi, cur, G);
+    if (cur < rb) cur_end = __shfl_sync(gmask, my_hi, cur, G);   // the remaining rows are empty: no mean needed
   }
 }
 
@@ -360,7 +388,7 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
 #endif
 constexpr int UNIT_ROWS = KGB_GR_UNIT_ROWS;
 
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV>
 __device__ __forceinline__ void do_chunk(const GRP& p, int64_t t, int gl, unsigned gmask, const bool (&on)[NCH]) {
   // one chunk of a hub row -> raw partial
   float acc[NCH][VEC];
@@ -368,11 +396,12 @@ __device__ __forceinline__ void do_chunk(const GRP& p, int64_t t, int gl, unsign
   init_acc<VEC, G, NCH, IS_MAX>(acc, aidx);
   const int h = __ldg(p.chunk_hub + t);
   const int64_t row = __ldg(p.hub_row + h);
+  load_mu<VEC, G, NCH, SQDEV>(p, row, gl, on, aidx);
   const int64_t ci = t - __ldg(p.hub_chunk_base + h);
   const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
   const int64_t k0 = rs + ci * p.hub_chunk;
   const int64_t k1 = (k0 + p.hub_chunk < re) ? k0 + p.hub_chunk : re;
-  reduce_range<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT>(p, k0, k1, gl, gmask, on, acc, aidx);
+  reduce_range<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT, SQDEV>(p, k0, k1, gl, gmask, on, acc, aidx);
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     if (!on[ch]) continue;
@@ -382,7 +411,7 @@ __device__ __forceinline__ void do_chunk(const GRP& p, int64_t t, int gl, unsign
   }
 }
 
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV>
 __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, int gw, unsigned gmask,
                                              const bool (&on)[NCH]) {
   // a block of G consecutive rows: lane gl holds rowptr[r0+gl], rowptr[r0+gl+1]
@@ -402,7 +431,7 @@ __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, i
     if (seg_end > cur) {
       const int64_t k0 = __shfl_sync(gmask, my_lo, cur, G);
       const int64_t k1 = __shfl_sync(gmask, my_hi, seg_end - 1, G);
-      walk_rows<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT>(p, r0, cur, seg_end, k0, k1, my_hi, gl, gmask, on);
+      walk_rows<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT, SQDEV>(p, r0, cur, seg_end, k0, k1, my_hi, gl, gmask, on);
     }
     cur = seg_end + 1;  // the hub row (if any) is written by hub_finish_kernel
   }
@@ -424,7 +453,7 @@ __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, i
 // with the id structure of power-law graphs (RMAT: the degree depends on the low id bits), which left
 // 27 % of the SM-cycles idle in the first version.  Which warp computes a row never changes the
 // result, so the output stays deterministic.
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV>
 __global__ void __launch_bounds__(256, ((VEC == 4 && G >= 16) ? (IS_MAX ? KGB_GR_MINB_MAX : KGB_GR_MINB_WIDE)
                                                               : KGB_GR_MINB_NARROW))
 gather_reduce_kernel(const GRP p) {
@@ -454,14 +483,14 @@ gather_reduce_kernel(const GRP p) {
     if (u >= n_units) break;
     if (u < chunk_units) {
       const int64_t t = u * GPW + gw;
-      if (t < p.n_chunks) do_chunk<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT>(p, t, gl, gmask, on);
+      if (t < p.n_chunks) do_chunk<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT, SQDEV>(p, t, gl, gmask, on);
     } else {
       int64_t ui = u - chunk_units;
       if (p.unit_order) ui = __ldg(p.unit_order + ui);
       const int64_t base = ui * UNIT_ROWS;
       for (int b = gw; b < BPU; b += GPW) {
         const int64_t r0 = base + (int64_t)b * G;
-        if (r0 < p.n_rows) do_row_block<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT>(p, r0, gl, gw, gmask, on);
+        if (r0 < p.n_rows) do_row_block<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT, SQDEV>(p, r0, gl, gw, gmask, on);
       }
     }
     if (!p.work) u += (int64_t)gridDim.x * wpb;
@@ -481,7 +510,7 @@ gather_reduce_kernel(const GRP p) {
 }
 
 // Merge the chunk partials of every hub row in chunk order, then run the epilogue.
-template <int VEC, int G, int NCH, bool IS_MAX, bool SPLIT>
+template <int VEC, int G, int NCH, bool IS_MAX, bool SPLIT, bool SQDEV>
 __global__ void __launch_bounds__(256) hub_finish_kernel(const GRP p) {
   constexpr int GPW = 32 / G;
   const int lane = threadIdx.x & 31;
@@ -541,7 +570,7 @@ __global__ void __launch_bounds__(256) hub_finish_kernel(const GRP p) {
       }
     }
     const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
-    epilogue<VEC, G, NCH, IS_MAX, SPLIT>(p, row, re - rs, gl, on, acc, aidx);
+    epilogue<VEC, G, NCH, IS_MAX, SPLIT, SQDEV>(p, row, re - rs, gl, on, acc, aidx);
   }
 }
 
@@ -952,10 +981,13 @@ static int launch_gr(int device, const GRP& p, bool is_max, cudaStream_t st) {
   const bool split = p.x2 != nullptr || p.n_split_out != INT64_MAX;
 #define KGB_GR_LAUNCH(MAXF, EW, SS)                                                                        \
   do {                                                                                                     \
-    if (split) gather_reduce_kernel<VEC, G, NCH, MAXF, EW, SS, !MAXF><<<grid, 256, 0, st>>>(p);            \
-    else gather_reduce_kernel<VEC, G, NCH, MAXF, EW, SS, false><<<grid, 256, 0, st>>>(p);                  \
+    if (split) gather_reduce_kernel<VEC, G, NCH, MAXF, EW, SS, !MAXF, false><<<grid, 256, 0, st>>>(p);     \
+    else gather_reduce_kernel<VEC, G, NCH, MAXF, EW, SS, false, false><<<grid, 256, 0, st>>>(p);           \
   } while (0)
-  if (is_max) {
+  if (p.sqdev) {
+    if (is_max || ew || ss || split) { set_error("the squared-deviation pass takes no weights / split operands"); return KGB_ERR_INVALID; }
+    gather_reduce_kernel<VEC, G, NCH, false, false, false, false, true><<<grid, 256, 0, st>>>(p);
+  } else if (is_max) {
     if (ew || ss) { set_error("max/min do not take edge weights"); return KGB_ERR_INVALID; }
     if (split) { set_error("max/min do not take split operands"); return KGB_ERR_INVALID; }
     KGB_GR_LAUNCH(true, false, false);
@@ -972,9 +1004,10 @@ static int launch_gr(int device, const GRP& p, bool is_max, cudaStream_t st) {
   KGB_CHECK_LAUNCH();
   if (p.n_hubs > 0) {
     const int hgrid = grid_for(device, p.n_hubs, G);
-    if (is_max) hub_finish_kernel<VEC, G, NCH, true, false><<<hgrid, 256, 0, st>>>(p);
-    else if (split) hub_finish_kernel<VEC, G, NCH, false, true><<<hgrid, 256, 0, st>>>(p);
-    else hub_finish_kernel<VEC, G, NCH, false, false><<<hgrid, 256, 0, st>>>(p);
+    if (p.sqdev) hub_finish_kernel<VEC, G, NCH, false, false, true><<<hgrid, 256, 0, st>>>(p);
+    else if (is_max) hub_finish_kernel<VEC, G, NCH, true, false, false><<<hgrid, 256, 0, st>>>(p);
+    else if (split) hub_finish_kernel<VEC, G, NCH, false, true, false><<<hgrid, 256, 0, st>>>(p);
+    else hub_finish_kernel<VEC, G, NCH, false, false, false><<<hgrid, 256, 0, st>>>(p);
     KGB_CHECK_LAUNCH();
   }
   return KGB_OK;
@@ -1029,7 +1062,9 @@ int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t 
   KGB_REQUIRE(a != nullptr, "args is NULL");
   KGB_REQUIRE(a->F > 0, "F must be positive (got %d)", a->F);
   KGB_REQUIRE(a->n_rows >= 0, "n_rows < 0");
-  KGB_REQUIRE(a->op >= KGB_OP_SUM && a->op <= KGB_OP_MAX_RAW, "bad op %d", a->op);
+  KGB_REQUIRE(a->op >= KGB_OP_SUM && a->op <= KGB_OP_SQDEV, "bad op %d", a->op);
+  KGB_REQUIRE(a->op != KGB_OP_SQDEV || (a->addend && !a->bias && a->act == KGB_ACT_NONE && !a->row_ids),
+              "KGB_OP_SQDEV needs the row means in `addend` and takes no bias / activation / row_ids");
   if (a->n_rows == 0) return KGB_OK;
   KGB_REQUIRE(a->x && a->rowptr && a->out, "x/rowptr/out must be non-NULL");
   KGB_REQUIRE(a->ldx >= a->F && a->ldo >= a->F, "leading dimension smaller than F");
@@ -1088,6 +1123,7 @@ int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t 
     p.addend_scale = a->addend_scale;
     p.bias = a->bias ? a->bias + f0 : nullptr; p.act = a->act;
     p.mean = (a->op == KGB_OP_MEAN); p.negate = (a->op == KGB_OP_MIN); p.raw_max = (a->op == KGB_OP_MAX_RAW);
+    p.sqdev = (a->op == KGB_OP_SQDEV);
     p.out = a->out + f0; p.ldo = a->ldo; p.arg = a->arg ? a->arg + f0 : nullptr;
     p.hub_row = a->hub_row; p.hub_chunk_base = a->hub_chunk_base; p.hub_nchunks = a->hub_nchunks;
     p.chunk_hub = a->chunk_hub;

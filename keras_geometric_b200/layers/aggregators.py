@@ -100,8 +100,8 @@ class MinAggregator(_KernelAggregator):
 
 
 class StdAggregator(Aggregator):
-    """aggregators.py:174-232: two-pass population std; count <= 1 -> 0.  Composition of the
-    segment kernels (mean, then sum of squared deviations)."""
+    """aggregators.py:174-232: two-pass population std; count <= 1 -> 0.  Two launches of the segment kernel: the
+    mean, then KGB_OP_SQDEV (squared deviations from the row's mean, sqrt and the count <= 1 rule in its epilogue)."""
 
     def aggregate(self, messages, target_idx, dim_size: int):
         messages = to_device_tensor(messages, what="messages")
@@ -111,13 +111,7 @@ class StdAggregator(Aggregator):
         graph, keep = _structure_for(target_idx, int(dim_size))
         if keep is not None:
             messages = messages[keep]
-        dst = graph.full_edge_index()[1].long()
-        mean = ops.segment_reduce(messages, graph, "mean")
-        sq = torch.square(messages - mean.index_select(0, dst))
-        var = ops.segment_reduce(sq, graph, "mean")
-        std = torch.sqrt(torch.clamp(var, min=0.0))
-        count = graph.csr.deg.unsqueeze(1)
-        return torch.where(count <= 1, torch.zeros_like(std), std)
+        return ops.segment_std(messages, graph)   # two fused passes (mean, squared deviations), no [E, F] temporaries
 
     @property
     def name(self) -> str:

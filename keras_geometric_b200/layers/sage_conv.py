@@ -109,6 +109,8 @@ class SAGEConv(MessagePassing):
         if default_hooks and not dropping:
             if agg_name in ("sum", "mean", "max", "min"):
                 return ops.gather_reduce(x, graph, agg_name)
+            if agg_name == "std":
+                return ops.gather_std(x, graph)          # fused with the gather: no [E, F] messages
             if agg_name == "pooling":
                 # Dense+act commute with the row gather: transform once per node, then fused max
                 return ops.gather_reduce(apply_dense(self.pool_mlp, x), graph, "max")
@@ -220,8 +222,8 @@ class SAGEConv(MessagePassing):
         if not self.built:
             self.build([tuple(x.shape), (2, 0)])
             self.built = True
-        if self.actual_aggregator not in ("mean", "sum", "max", "min") or (self.dropout_rate > 0 and training):
-            raise NotImplementedError("partitioned SAGEConv supports mean/sum/max/min without dropout")
+        if self.dropout_rate > 0 and training:
+            raise NotImplementedError("partitioned SAGEConv does not support dropout")
         w_neigh = value_of(self.lin_neigh.kernel)
         w_self = value_of(self.lin_self.kernel) if (self.root_weight and self.lin_self is not None) else None
         bias = value_of(self.bias) if (self.use_bias and self.bias is not None) else None
@@ -266,10 +268,16 @@ class SAGEConv(MessagePassing):
             out = self._aggregate_after_transform(x, pg.graph, w_neigh, w_self, bias, act_is_relu,
                                                    exchange=(pg.exchange_start, pg.exchange_finish))
         else:
-            x_ext = pg.exchange_start(x)                      # all-to-all in flight ...
+            # max / min / std / pooling: the [local | halo] source space (their backward needs the gathered rows)
+            src = apply_dense(self.pool_mlp, x) if self.actual_aggregator == "pooling" else x
+            x_ext = pg.exchange_start(src)                    # exchange in flight ...
             root = ops.linear(x, w_self) if w_self is not None else None   # ... behind the root transform
             pg.exchange_finish()
-            aggregated = ops.gather_reduce(x_ext, pg.graph, self.actual_aggregator)
+            if self.actual_aggregator == "std":
+                aggregated = ops.gather_std(x_ext, pg.graph)
+            else:
+                aggregated = ops.gather_reduce(x_ext, pg.graph,
+                                               "max" if self.actual_aggregator == "pooling" else self.actual_aggregator)
             out = ops.linear(aggregated, w_neigh, addend=root, bias=bias, act="relu" if act_is_relu else None)
             if self.activation is not None and not act_is_relu:
                 out = self.activation(out)

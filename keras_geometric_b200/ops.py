@@ -18,7 +18,7 @@ _ACT = {None: _lib.ACT_NONE, "linear": _lib.ACT_NONE, "relu": _lib.ACT_RELU}
 # When set to a list, every gather-reduce launch appends {label, start, end, bytes} with CUDA events
 # recorded on the launching stream (bench.py reads it for the per-kernel roofline).
 PROFILE = None
-_OP_NAMES = {0: "sum", 1: "mean", 2: "max", 3: "min", 4: "max"}
+_OP_NAMES = {0: "sum", 1: "mean", 2: "max", 3: "min", 4: "max", 5: "sqdev"}
 
 
 def _algorithmic_bytes(nnz, n_rows, F, per_edge_extra, per_row_extra):
@@ -353,6 +353,53 @@ def gather_reduce(x, graph: GraphStructure, op: str = "sum", *, weight=None, add
     if op not in _lib.OPS:
         raise ValueError(f"Invalid aggregator: {op}. Available aggregators: {list(_lib.OPS)}")
     return _GatherReduce.apply(x, addend, bias, graph, op, weight, addend_scale, act)
+
+
+class _GatherStd(torch.autograd.Function):
+    """Population standard deviation of the gathered rows per target (``StdAggregator``, layers/aggregators.py:174-232)
+    in two fused passes over the structure - the mean, then sqrt(mean squared deviation) with the row's mean held in
+    registers - instead of the reference's five [E, F] temporaries.  ``messages`` False: rows are x[col] (fused with
+    the gather); True: ``x`` holds one message per edge in COO order (the generic ``Aggregator.aggregate``).
+    Backward: d std_i / d m_e = (m_e - mean_i) / (n_i std_i); like the reference's autograd it is NaN for every edge
+    of a row whose variance is exactly 0 (sqrt'(0) = inf times a zero deviation), including the rows with a single
+    message whose output is forced to 0."""
+
+    @staticmethod
+    def forward(ctx, x, graph: GraphStructure, messages: bool):
+        x = _f32c(x, "x")
+        csr = graph.csr
+        col = csr.perm if messages else None
+        mean, _ = gather_reduce_raw(x, csr, _lib.OP_MEAN, col=col)
+        std, _ = gather_reduce_raw(x, csr, _lib.OP_SQDEV, col=col, addend=mean)
+        ctx.graph, ctx.messages = graph, messages
+        ctx.save_for_backward(x, mean, std)
+        return std
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, mean, std = ctx.saved_tensors
+        graph = ctx.graph
+        g = _f32c(g, "grad")
+        cnt = graph.csr.deg.to(torch.float32).unsqueeze(1)
+        c = torch.where(cnt <= 1, torch.zeros_like(g), g) / (torch.clamp(cnt, min=1e-8) * std)   # [n_dst, F]
+        b = c * mean
+        if ctx.messages:
+            dst = graph.full_edge_index()[1]
+            return x * gather_rows(c, dst) - gather_rows(b, dst), None, None
+        sc, _ = gather_reduce_raw(c, graph.csc, _lib.OP_SUM)      # sum over the targets each source feeds
+        sb, _ = gather_reduce_raw(b, graph.csc, _lib.OP_SUM)
+        return x * sc - sb, None, None
+
+
+def gather_std(x, graph: GraphStructure) -> torch.Tensor:
+    """std over the in-neighbour rows x[src] of every target, fused with the gather (no [E, F] tensor)."""
+    return _GatherStd.apply(x, graph, False)
+
+
+def segment_std(messages, graph: GraphStructure) -> torch.Tensor:
+    """``StdAggregator.aggregate(messages, target_idx, dim_size)`` over a prebuilt structure (COO-ordered messages)."""
+    return _GatherStd.apply(messages, graph, True)
 
 
 class _SegmentReduce(torch.autograd.Function):

@@ -166,6 +166,45 @@ def test_max_backward_run_to_run_identical(op, F):
     np.testing.assert_array_equal(np.isinf(g2), np.isinf(w2))
 
 
+@pytest.mark.parametrize("F", [1, 7, 32, 100, 256, 516])
+def test_fused_std_vs_oracle(F):
+    """KGB_OP_SQDEV (second pass of the std aggregator) fused with the gather and as the generic segment aggregator:
+    forward and gradient vs the oracle, including a hub row (chunked path), empty rows, single-message rows (output
+    forced to 0) and the reference's NaN gradients for rows whose variance is exactly 0."""
+    from keras_geometric_b200 import ops
+    from keras_geometric_b200.graph import GraphStructure
+    rng = np.random.default_rng(F)
+    n_dst, n_src, e = 211, 157, 6000
+    ei = rand_graph(rng, n_dst, n_src, e, hub=2500)
+    ei[1, -1] = n_dst - 3          # a row with exactly one message: std 0, NaN gradient like the reference
+    ei[1, -3:-1] = n_dst - 4       # a row whose two messages are equal: variance exactly 0
+    ei[0, -3:-1] = 5
+    x = rng.standard_normal((n_src, F)).astype(np.float32)
+    R = rng.standard_normal((n_dst, F)).astype(np.float32)
+    graph = GraphStructure(cuda(ei), n_dst, n_src, 0)
+    assert graph.csr.n_hubs >= 1
+    xo = torch.from_numpy(x).requires_grad_(True)
+    eio = torch.from_numpy(ei)
+    want = ref.aggregate("std", xo[eio[0].long()], eio[1], n_dst)
+    (gw,) = torch.autograd.grad((want * torch.from_numpy(R)).sum(), [xo])
+    xg = cuda(x).requires_grad_(True)
+    out = ops.gather_std(xg, graph)
+    close(out, want, msg=f"std F={F}")
+    (gx,) = torch.autograd.grad((out * cuda(R)).sum(), [xg])
+    assert np.isnan(gw.numpy()).any()          # the reference's 0 * inf on zero-variance rows
+    close(gx, gw, msg=f"std grad F={F}")       # equal_nan: NaN positions must coincide
+    # generic aggregator over materialised messages
+    m = rng.standard_normal((e, F)).astype(np.float32)
+    mo = torch.from_numpy(m).requires_grad_(True)
+    want2 = ref.aggregate("std", mo, eio[1], n_dst)
+    (gw2,) = torch.autograd.grad((want2 * torch.from_numpy(R)).sum(), [mo])
+    mg = cuda(m).requires_grad_(True)
+    out2 = ops.segment_std(mg, graph)
+    close(out2, want2, msg=f"segment std F={F}")
+    (gm,) = torch.autograd.grad((out2 * cuda(R)).sum(), [mg])
+    close(gm, gw2, msg=f"segment std grad F={F}")
+
+
 def test_unweighted_sum_matches_host_order_bitwise():
     """Non-hub rows accumulate in CSR (= original edge) order, like the sequential host scatter."""
     from keras_geometric_b200 import ops
