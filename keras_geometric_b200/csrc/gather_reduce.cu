@@ -265,7 +265,7 @@ __device__ __forceinline__ void epilogue(const GRP& p, int64_t slot, int64_t deg
       if (p.mean) r[e] = __fdiv_rn(r[e], den);
       if constexpr (SQDEV) {
         // population std (aggregators.py:218-226): sqrt(max(sum_sq / max(count, 1e-8), 0)); count <= 1 -> 0
-        r[e] = __fsqrt_rn(fmaxf(__fdiv_rn(r[e], den), 0.f));
+        r[e] = __fsqrt_rn(fmax_nan(__fdiv_rn(r[e], den), 0.f));   // NaN-propagating like torch.maximum
         if (deg <= 1) r[e] = 0.f;
       }
       if (p.out_scale) r[e] = __fmul_rn(r[e], os);

@@ -176,8 +176,8 @@ def test_fused_std_vs_oracle(F):
     rng = np.random.default_rng(F)
     n_dst, n_src, e = 211, 157, 6000
     ei = rand_graph(rng, n_dst, n_src, e, hub=2500)
-    ei[1, -1] = n_dst - 3          # a row with exactly one message: std 0, NaN gradient like the reference
-    ei[1, -3:-1] = n_dst - 4       # a row whose two messages are equal: variance exactly 0
+    ei[1, -1] = n_dst - 1          # (rand_graph leaves the last two rows empty) exactly one message: std 0,
+    ei[1, -3:-1] = n_dst - 2       # NaN gradient like the reference; two equal messages: variance exactly 0
     ei[0, -3:-1] = 5
     x = rng.standard_normal((n_src, F)).astype(np.float32)
     R = rng.standard_normal((n_dst, F)).astype(np.float32)
