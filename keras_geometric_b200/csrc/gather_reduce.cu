@@ -794,37 +794,70 @@ __global__ void __launch_bounds__(256) max_bwd_hub_total_kernel(const MaxBwdP p)
   }
 }
 
-// max |g| over the finite entries of g [rows, F] (bit patterns of non-negative floats order like unsigned integers)
+// max |g| over the finite entries of g [rows, F] (bit patterns of non-negative floats order like unsigned integers).
+// One warp per row (grid-stride), 128-bit loads when the rows allow it; no per-element index arithmetic.
+__device__ __forceinline__ uint32_t absbits_finite(float v, uint32_t m) {
+  const uint32_t b = __float_as_uint(v) & 0x7fffffffu;
+  return (b < 0x7f800000u && b > m) ? b : m;
+}
+
 __global__ void __launch_bounds__(256) max_bwd_absmax_kernel(const float* __restrict__ g, int64_t ldg, int64_t rows,
-                                                             int F, uint32_t* __restrict__ out_bits) {
-  const int64_t total = rows * (int64_t)F;
+                                                             int F, int vec4, uint32_t* __restrict__ out_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   uint32_t m = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / F;
-    const uint32_t b = __float_as_uint(__ldg(g + r * ldg + (i - r * F))) & 0x7fffffffu;
-    if (b < 0x7f800000u && b > m) m = b;
+  for (int64_t r = warp; r < rows; r += n_warps) {
+    const float* row = g + r * ldg;
+    if (vec4) {
+      for (int f = lane * 4; f < F; f += 128) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + f));
+        m = absbits_finite(v.x, m); m = absbits_finite(v.y, m); m = absbits_finite(v.z, m); m = absbits_finite(v.w, m);
+      }
+    } else {
+      for (int f = lane; f < F; f += 32) m = absbits_finite(__ldg(row + f), m);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const uint32_t t = __shfl_xor_sync(0xffffffffu, m, o);
     m = t > m ? t : m;
   }
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(out_bits, m);
+  if (lane == 0 && m) atomicMax(out_bits, m);
 }
 
 // gx += acc * 2^-shift (the fixed-point sums back to fp32, one correctly rounded conversion per element)
 __global__ void __launch_bounds__(256) max_bwd_convert_kernel(const MaxBwdP p, int64_t n_src) {
   const int shift = max_bwd_shift(p);
   const bool nonfinite = p.gmax_bits[1] != 0u;
-  const int64_t total = n_src * (int64_t)p.F;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / p.F;
-    const int f = (int)(i - r * p.F);
-    const long long q = p.acc[r * p.ldacc + f];
-    if (q != 0) {  // gx is zero on entry except where non-finite gradients landed (flagged, rare)
-      float* dst = p.gx + r * p.ldgx + f;
-      const float v = (float)ldexp((double)q, -shift);
-      *dst = nonfinite ? __fadd_rn(*dst, v) : v;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const bool pair = (p.F % 2 == 0) && (p.ldacc % 2 == 0) && (p.ldgx % 2 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(p.acc) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(p.gx) & 7u) == 0);
+  for (int64_t r = warp; r < n_src; r += n_warps) {   // one warp per row: no per-element index arithmetic
+    const long long* arow = p.acc + r * p.ldacc;
+    float* grow = p.gx + r * p.ldgx;
+    if (pair) {
+      for (int f = lane * 2; f < p.F; f += 64) {
+        const longlong2 q = *reinterpret_cast<const longlong2*>(arow + f);
+        if ((q.x | q.y) != 0) {  // gx is zero on entry except where non-finite gradients landed (flagged, rare)
+          float2 v = make_float2((float)ldexp((double)q.x, -shift), (float)ldexp((double)q.y, -shift));
+          if (nonfinite) {
+            const float2 o = *reinterpret_cast<const float2*>(grow + f);
+            v.x = __fadd_rn(o.x, v.x); v.y = __fadd_rn(o.y, v.y);
+          }
+          *reinterpret_cast<float2*>(grow + f) = v;
+        }
+      }
+    } else {
+      for (int f = lane; f < p.F; f += 32) {
+        const long long q = arow[f];
+        if (q != 0) {
+          const float v = (float)ldexp((double)q, -shift);
+          grow[f] = nonfinite ? __fadd_rn(grow[f], v) : v;
+        }
+      }
     }
   }
 }
@@ -1181,11 +1214,12 @@ int kgb_gather_max_bwd(int device, const float* g, int64_t ldg, const int32_t* a
   uint32_t* gmax_bits = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(acc_ws) + acc_bytes - 256);
   KGB_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, acc_bytes, st));
   {
-    int64_t tg = ceil_div(n_rows * (int64_t)F, 256 * 8);
+    int64_t tg = ceil_div(n_rows, 8);
     const int64_t cap = (int64_t)sm_count(device) * 8;
     if (tg > cap) tg = cap;
     if (tg < 1) tg = 1;
-    max_bwd_absmax_kernel<<<(int)tg, 256, 0, st>>>(g, ldg, n_rows, F, gmax_bits);
+    const int vec4 = (aligned16(g) && ldg % 4 == 0 && F % 4 == 0) ? 1 : 0;
+    max_bwd_absmax_kernel<<<(int)tg, 256, 0, st>>>(g, ldg, n_rows, F, vec4, gmax_bits);
     KGB_CHECK_LAUNCH();
   }
   int cnt_bits = 1;
@@ -1232,8 +1266,8 @@ int kgb_gather_max_bwd(int device, const float* g, int64_t ldg, const int32_t* a
       KGB_CHECK_LAUNCH();
     }
     {
-      int64_t tg = ceil_div(n_src_rows * (int64_t)Fs, 256 * 4);
-      const int64_t cap = (int64_t)sm_count(device) * 16;
+      int64_t tg = ceil_div(n_src_rows, 8);
+      const int64_t cap = (int64_t)sm_count(device) * 8;
       if (tg > cap) tg = cap;
       if (tg < 1) tg = 1;
       max_bwd_convert_kernel<<<(int)tg, 256, 0, st>>>(p, n_src_rows);
