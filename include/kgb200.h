@@ -185,7 +185,25 @@ typedef struct kgb_gather_reduce_args {
                               ldd / n_peers are read).  This is the fused "transposed gather + halo-gradient
                               exchange" kernel: the rows travel over NVLink while the rest is still being reduced.
                               Split-output rows take no addend / bias / activation / arg.                        */
+  const int32_t* col_hot;  /* optional copy of `col` with bit 31 set for "hot" rows: those are loaded with an L2
+                              evict_last hint, all others with evict_first.  Mark the most frequently gathered rows
+                              that together fit in the L2 (power-law graphs: the hubs); the result does not depend on
+                              it.  Measured on C4: +3 % at F = 256, a loss for narrower rows - off by default.        */
+  /* ---- dropout of the gathered rows, fused (training only) ----
+   * The reference drops the per-edge messages element-wise before they are weighted and reduced (GCNConv:
+   * layers/gcn_conv.py:238-242, SAGEConv: layers/sage_conv.py:295-297) and materialises [E, F] tensors to do so.
+   * Here element f of edge e survives when Philox4x32-10(counter = (edge id, f / 4), key = drop_seed) >= drop_p * 2^32
+   * and is scaled by 1 / (1 - drop_p); nothing is stored - the transposed (backward) pass regenerates the same mask
+   * from edge_id[] = original edge id of each slot (`perm` of the structure that is walked).  sum / mean only. */
+  float drop_p;            /* 0 = no dropout                                                                      */
+  uint64_t drop_seed;
+  const int32_t* edge_id;  /* [nnz], required when drop_p > 0                                                      */
 } kgb_gather_reduce_args;
+
+/* The mask the kernels apply, for tests: out[e, f] = 1 / (1 - p) or 0 for edge ids edge_id[e] (NULL: e itself);
+ * per_head != 0 selects the stream used by kgb_gatv2_* (one decision per edge and head).                         */
+int kgb_dropout_mask(int device, const int32_t* edge_id, int64_t n_edges, int32_t F, int32_t per_head, float p,
+                     uint64_t seed, float* out, kgb_stream_t stream);
 
 /* rows per task-queue unit of kgb_gather_reduce (unit u covers rows [u*R, (u+1)*R)) */
 int32_t kgb_gather_unit_rows(void);
@@ -283,10 +301,21 @@ typedef struct kgb_hub_table {
 int32_t kgb_gatv2_unit_rows(void);
 size_t kgb_gatv2_partial_bytes(int32_t n_chunks, int32_t H, int32_t C);
 
+/* Attention dropout (layers/gatv2_conv.py:252-253), fused: alpha of (edge e, head h) survives when
+ * Philox4x32-10(counter = (edge id, h / 4), key = seed) >= p * 2^32 and is scaled by 1 / (1 - p); the softmax still
+ * normalises over all edges.  edge_id = `perm` of the structure the call walks (CSR for fwd / bwd_dst, the transposed
+ * one for bwd_src), so all three passes regenerate the same mask.  NULL or p == 0: no dropout. */
+typedef struct kgb_gat_dropout {
+  float p;
+  uint64_t seed;
+  const int32_t* edge_id;
+} kgb_gat_dropout;
+
 int kgb_gatv2_fwd(int device, const float* hsrc, const float* hdst, int64_t n_src, int64_t n_dst,
                   int32_t H, int32_t C, const float* att, float slope,
                   const int64_t* rowptr, const int32_t* col, const float* bias,
-                  float* out, float* rowmax, float* rowden, const kgb_hub_table* hubs, kgb_stream_t stream);
+                  float* out, float* rowmax, float* rowden, const kgb_gat_dropout* drop,
+                  const kgb_hub_table* hubs, kgb_stream_t stream);
 /* Backward, pass 1 over the forward CSR (per target): g_hdst[i] (written), r[i,h] =
  * sum_c g[i,h,c] * agg[i,h,c] (written, workspace [n_dst,H]) and the attention-vector
  * gradient partials g_att_part [n_parts, H*C] (n_parts from kgb_gatv2_bwd_parts()).
@@ -297,14 +326,14 @@ int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float*
                       const float* att, float slope, const int64_t* rowptr, const int32_t* col,
                       const float* rowmax, const float* rowden, const float* bias,
                       float* g_hdst, float* r, float* g_att_part, int32_t n_parts,
-                      const kgb_hub_table* hubs, kgb_stream_t stream);
+                      const kgb_gat_dropout* drop, const kgb_hub_table* hubs, kgb_stream_t stream);
 /* Backward, pass 2 over the transposed structure (per source): g_hsrc[j] (written) = per-source gradient
  * (+ addend[j], optional [n_src, H*C]: on a square graph the per-target part g_hdst, saving a pass). */
 int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float* hdst,
                       int64_t n_src, int64_t n_dst, int32_t H, int32_t C, const float* att,
                       float slope, const int64_t* colptr, const int32_t* row,
                       const float* rowmax, const float* rowden, const float* r, const float* addend,
-                      float* g_hsrc, const kgb_hub_table* hubs, kgb_stream_t stream);
+                      float* g_hsrc, const kgb_gat_dropout* drop, const kgb_hub_table* hubs, kgb_stream_t stream);
 /* out[f] = sum_p part[p,f]  in fixed order (deterministic reduction of partials). */
 int kgb_reduce_parts(int device, const float* part, int32_t n_parts, int32_t F, float* out,
                      kgb_stream_t stream);

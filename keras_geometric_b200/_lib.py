@@ -38,6 +38,8 @@ class GatherReduceArgs(Structure):
         ("work", c_void_p), ("unit_order", c_void_p),
         ("x2", c_void_p), ("ldx2", c_int64), ("n_split_src", c_int64),
         ("out2", c_void_p), ("ldo2", c_int64), ("n_split_out", c_int64), ("out2_push", c_void_p),
+        ("col_hot", c_void_p),
+        ("drop_p", c_float), ("drop_seed", ctypes.c_uint64), ("edge_id", c_void_p),
     ]
 
 
@@ -50,6 +52,12 @@ class HaloPushArgs(Structure):
     _fields_ = [("src", c_void_p), ("lds", c_int64), ("idx", c_void_p), ("F", c_int32), ("n_peers", c_int32),
                 ("slot_begin", c_int64 * (MAX_PEERS + 1)), ("dst", c_void_p * MAX_PEERS),
                 ("dst_row0", c_int64 * MAX_PEERS), ("ldd", c_int64), ("slot_rot", c_int64)]
+
+
+class GatDropout(Structure):
+    """Mirror of ``struct kgb_gat_dropout`` (include/kgb200.h)."""
+
+    _fields_ = [("p", c_float), ("seed", ctypes.c_uint64), ("edge_id", c_void_p)]
 
 
 class HubTable(Structure):
@@ -89,6 +97,8 @@ SIGNATURES = {
     "kgb_gather_unit_rows": (c_int32, []),
     "kgb_gatv2_unit_rows": (c_int32, []),
     "kgb_gather_max_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "kgb_dropout_mask": (c_int, [c_int, c_void_p, c_int64, c_int32, c_int32, c_float, ctypes.c_uint64, c_void_p,
+                                 c_void_p]),
     "kgb_gather_rows": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_float, c_void_p, c_int64,
                                 c_void_p]),
     "kgb_window_alloc": (c_int, [c_int, c_size_t, POINTER(c_void_p)]),
@@ -99,15 +109,16 @@ SIGNATURES = {
     "kgb_halo_push": (c_int, [c_int, POINTER(HaloPushArgs), c_void_p]),
     "kgb_gatv2_partial_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "kgb_gatv2_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_float,
-                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(HubTable),
-                              c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(GatDropout),
+                              POINTER(HubTable), c_void_p]),
     "kgb_gatv2_bwd_parts": (c_int, [c_int, c_int64, c_int32, c_int32]),
     "kgb_gatv2_bwd_dst": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
                                   c_int32, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_void_p, c_int32, POINTER(HubTable), c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_int32, POINTER(GatDropout), POINTER(HubTable),
+                                  c_void_p]),
     "kgb_gatv2_bwd_src": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
                                   c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, POINTER(HubTable), c_void_p]),
+                                  c_void_p, POINTER(GatDropout), POINTER(HubTable), c_void_p]),
     "kgb_reduce_parts": (c_int, [c_int, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "kgb_linear_tc_rows": (c_int32, [c_int32]),
     "kgb_split_tf32": (c_int, [c_int, c_void_p, c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),

@@ -70,6 +70,58 @@ __device__ __forceinline__ void ld_vec(const float* __restrict__ p, float (&v)[V
   }
 }
 
+// ---- counter-based random numbers for in-kernel dropout ------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11): 4 x 32 random bits from a 128-bit counter and a 64-bit key; stateless, so the
+// forward pass and both backward passes regenerate the SAME mask for an (edge id, feature block) without storing it.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// 4 keep-bits for block `blk` (4 consecutive features, or 4 consecutive heads) of edge `eid`: bit i set <=> element i
+// of the block survives dropout (probability 1 - p, thr = p * 2^32).  `stream` separates independent uses.
+__device__ __forceinline__ uint32_t dropout_keep4(uint32_t eid, uint32_t blk, uint32_t stream, uint32_t seed_lo,
+                                                  uint32_t seed_hi, uint32_t thr) {
+  const uint4 r = philox4x32_10(make_uint4(eid, blk, stream, 0x6b676232u), seed_lo, seed_hi);
+  return (r.x >= thr ? 1u : 0u) | (r.y >= thr ? 2u : 0u) | (r.z >= thr ? 4u : 0u) | (r.w >= thr ? 8u : 0u);
+}
+
+// L2 eviction-priority policies for per-load cache hints (ld.global.L2::cache_hint)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+#ifdef KGB_HOT_COLD_NORMAL
+  asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+#else
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+#endif
+  return p;
+}
+
+// read-only load that tells the L2 how long to keep the line (hot rows: evict_last, read-once rows: evict_first)
+template <int VEC>
+__device__ __forceinline__ void ld_vec_hint(const float* __restrict__ p, float (&v)[VEC], uint64_t policy) {
+  if constexpr (VEC == 4) {
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "l"(policy));
+  } else if constexpr (VEC == 2) {
+    asm("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v[0]), "=f"(v[1]) : "l"(p), "l"(policy));
+  } else {
+    asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v[0]) : "l"(p), "l"(policy));
+  }
+}
+
 template <int VEC>
 __device__ __forceinline__ void st_vec(float* __restrict__ p, const float (&v)[VEC]) {
   if constexpr (VEC == 4) {

@@ -65,6 +65,13 @@ struct GRP {
   const float* x2; int64_t ldx2; int64_t n_split_src;   // n_split_src = INT64_MAX when x2 is unused
   float* out2; int64_t ldo2; int64_t n_split_out;       // n_split_out = INT64_MAX when unused
   int has_push; PushTab tab;                            // fused halo push: split-output rows go to the peers' windows
+  // optional copy of `col` whose bit 31 marks "hot" source rows (among the most frequently gathered rows that
+  // together fit in the L2).  Hot rows are loaded with an L2 evict_last hint, all others with evict_first, so the
+  // one-touch rows of a power-law graph stop pushing the hub rows out of the 126 MB L2.
+  const int32_t* col_hot;
+  // in-kernel dropout of the gathered rows (per edge and element, layers/gcn_conv.py:238-242, sage_conv.py:295-297):
+  // edge_id[k] = original edge id of slot k, so the forward (CSR) and transposed (CSC) passes regenerate one mask
+  const int32_t* edge_id; uint32_t drop_thr; float drop_scale; uint32_t seed_lo, seed_hi;
 };
 
 template <int VEC, int G, int NCH, bool IS_MAX>
@@ -126,45 +133,91 @@ __device__ __forceinline__ void accum(float& m, int32_t& a, float v, float w, in
 
 // Load the feature rows of U consecutive slots of the current index batch.  Slots past the end of the
 // batch carry index 0 (a valid row) and are simply never accumulated, so the loads need no predicate.
-template <int VEC, int G, int NCH, int U, bool HAS_W, bool SPLIT>
-__device__ __forceinline__ void load_batch_full(const GRP& p, int32_t myc, float myw, int j, int gl, unsigned gmask,
-                                                const bool (&on)[NCH], float (&v)[U][NCH][VEC], float (&w)[U],
-                                                int32_t (&c)[U]) {
+template <int VEC, int G, int NCH, int U, bool HAS_W, bool SPLIT, bool HOT, bool DROP>
+__device__ __forceinline__ void load_batch_full(const GRP& p, int32_t myc, float myw, int32_t mye, int j, int gl,
+                                                unsigned gmask, const bool (&on)[NCH], float (&v)[U][NCH][VEC],
+                                                float (&w)[U], int32_t (&c)[U], uint32_t (&mk)[U][NCH]) {
   // Lanes beyond the row width re-read the row's first vector (same sector as lane 0, no extra traffic)
   // so every load is unconditional: a predicated load would make v loop-carried and spill.
   int loff[NCH];
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) loff[ch] = on[ch] ? (gl + ch * G) * VEC : 0;
+  uint64_t pol_last = 0, pol_cold = 0;
+  if constexpr (HOT) {
+    pol_last = l2_policy_evict_last();
+    pol_cold = l2_policy_evict_first();
+  }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     c[u] = __shfl_sync(gmask, myc, j + u, G);
     w[u] = 1.f;
     if constexpr (HAS_W) w[u] = __shfl_sync(gmask, myw, j + u, G);
+    bool hot = false;
+    if constexpr (HOT) {  // the index batch carries the hot flag in its sign bit (set when the batch was fetched)
+      hot = c[u] < 0;
+      c[u] &= 0x7fffffff;
+    }
     const int64_t cu = c[u];
     const float* rp = p.x + cu * p.ldx;
     if constexpr (SPLIT) {
       if (cu >= p.n_split_src) rp = p.x2 + (cu - p.n_split_src) * p.ldx2;
     }
+    if constexpr (HOT) {
+      const uint64_t pol = hot ? pol_last : pol_cold;
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) ld_vec<VEC>(rp + loff[ch], v[u][ch]);
+      for (int ch = 0; ch < NCH; ++ch) ld_vec_hint<VEC>(rp + loff[ch], v[u][ch], pol);
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) ld_vec<VEC>(rp + loff[ch], v[u][ch]);
+    }
+  }
+  if constexpr (DROP) {
+    // keep-bits of every loaded (edge, feature block): pure ALU work (Philox) issued behind the loads
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t eid = (uint32_t)__shfl_sync(gmask, mye, j + u, G);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const uint32_t f0 = (uint32_t)((gl + ch * G) * VEC);
+        const uint32_t bits = dropout_keep4(eid, f0 >> 2, 0u, p.seed_lo, p.seed_hi, p.drop_thr);
+        mk[u][ch] = (VEC == 4) ? bits : (bits >> (f0 & 3u));   // VEC < 4: this lane's elements start at f0 % 4
+      }
+    }
   }
 }
 
+// column index of a slot, with the hot flag of that source row in the sign bit (HOT only)
+template <bool HOT>
+__device__ __forceinline__ int32_t load_col(const GRP& p, int64_t k) {
+  if constexpr (HOT) return __ldg(p.col_hot + k);   // same ids, hot flag already in bit 31
+  return __ldg(p.col + k);
+}
+
 // Lanes whose `on` is false accumulate harmless duplicates; they are never stored.
-template <int VEC, int NCH, int U, bool IS_MAX, bool HAS_W, bool SQDEV>
+// value of element e of a loaded row after dropout (identity without DROP)
+template <bool DROP>
+__device__ __forceinline__ float dropped(float v, uint32_t mk, int e, float scale) {
+  if constexpr (DROP) return ((mk >> e) & 1u) ? __fmul_rn(v, scale) : 0.f;
+  return v;
+}
+
+template <int VEC, int NCH, int U, bool IS_MAX, bool HAS_W, bool SQDEV, bool DROP>
 __device__ __forceinline__ void accum_all(float (&acc)[NCH][VEC], int32_t (&aidx)[NCH][VEC],
                                           const float (&v)[U][NCH][VEC], const float (&w)[U], const int32_t (&c)[U],
-                                          const bool (&on)[NCH], bool negate) {
+                                          const bool (&on)[NCH], bool negate, const uint32_t (&mk)[U][NCH],
+                                          float drop_scale) {
 #pragma unroll
   for (int u = 0; u < U; ++u)
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) accum<IS_MAX, HAS_W, SQDEV>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
+      for (int e = 0; e < VEC; ++e)
+        accum<IS_MAX, HAS_W, SQDEV>(acc[ch][e], aidx[ch][e], dropped<DROP>(v[u][ch][e], mk[u][ch], e, drop_scale), w[u],
+                                    c[u], negate);
 }
 
 // Reduce CSR slots [k0, k1) of one row into acc (all lanes of the group call this together).
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV, bool HOT, bool DROP>
 __device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k1, int gl,
                                              unsigned gmask, const bool (&on)[NCH],
                                              float (&acc)[NCH][VEC], int32_t (&aidx)[NCH][VEC]) {
@@ -174,31 +227,36 @@ __device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k
   const bool negate = p.negate != 0;
   int64_t k = k0;
   int32_t myc = 0;
+  int32_t mye = 0;
   float myw = 1.f;
   if (k + gl < k1) {
-    myc = __ldg(p.col + k + gl);
+    if constexpr (DROP) mye = __ldg(p.edge_id + k + gl);
+    myc = load_col<HOT>(p, k + gl);
     if constexpr (HAS_EW) myw = __ldg(p.edge_w + k + gl);
-    if constexpr (HAS_SS) myw = __fmul_rn(myw, __ldg(p.src_scale + myc));
+    if constexpr (HAS_SS) myw = __fmul_rn(myw, __ldg(p.src_scale + (myc & 0x7fffffff)));
   }
   while (k < k1) {
     const int64_t rem = k1 - k;
     const int cnt = rem < G ? (int)rem : G;
     const int64_t kn = k + G;
     int32_t nc = 0;
+    int32_t ne = 0;
     float nw = 1.f;
     if (kn + gl < k1) {  // prefetch the next index batch while this one is consumed
-      nc = __ldg(p.col + kn + gl);
+      if constexpr (DROP) ne = __ldg(p.edge_id + kn + gl);
+      nc = load_col<HOT>(p, kn + gl);
       if constexpr (HAS_EW) nw = __ldg(p.edge_w + kn + gl);
-      if constexpr (HAS_SS) nw = __fmul_rn(nw, __ldg(p.src_scale + nc));
+      if constexpr (HAS_SS) nw = __fmul_rn(nw, __ldg(p.src_scale + (nc & 0x7fffffff)));
     }
 #pragma unroll 1
     for (int j = 0; j < cnt; j += U) {
       float v[U][NCH][VEC];
       float w[U];
       int32_t c[U];
-      load_batch_full<VEC, G, NCH, U, HAS_W, SPLIT>(p, myc, myw, j, gl, gmask, on, v, w, c);
+      uint32_t mk[U][NCH];
+      load_batch_full<VEC, G, NCH, U, HAS_W, SPLIT, HOT, DROP>(p, myc, myw, mye, j, gl, gmask, on, v, w, c, mk);
       if (j + U <= cnt) {  // group-uniform: a full batch needs no predication
-        accum_all<VEC, NCH, U, IS_MAX, HAS_W, SQDEV>(acc, aidx, v, w, c, on, negate);
+        accum_all<VEC, NCH, U, IS_MAX, HAS_W, SQDEV, DROP>(acc, aidx, v, w, c, on, negate, mk, p.drop_scale);
       } else {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -207,12 +265,13 @@ __device__ __forceinline__ void reduce_range(const GRP& p, int64_t k0, int64_t k
             for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
               for (int e = 0; e < VEC; ++e)
-                accum<IS_MAX, HAS_W, SQDEV>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
+                accum<IS_MAX, HAS_W, SQDEV>(acc[ch][e], aidx[ch][e], dropped<DROP>(v[u][ch][e], mk[u][ch], e, p.drop_scale), w[u], c[u], negate);
           }
         }
       }
     }
     myc = nc;
+    mye = ne;
     myw = nw;
     k = kn;
   }
@@ -295,7 +354,7 @@ __device__ __forceinline__ void epilogue(const GRP& p, int64_t slot, int64_t deg
 
 // Walk the contiguous edge range of CSR rows [ra, rb) of the block starting at row r0 (group-uniform
 // arguments).  my_hi holds rowptr[r0 + gl + 1] for lane gl of the group.
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV, bool HOT, bool DROP>
 __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int rb, int64_t k0, int64_t k1,
                                           int64_t my_hi, int gl, unsigned gmask, const bool (&on)[NCH]) {
   constexpr int UMAX = (8 / NCH) < 1 ? 1 : (8 / NCH);
@@ -311,33 +370,38 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
   int64_t cur_end = __shfl_sync(gmask, my_hi, cur, G);
   int64_t k = k0;
   int32_t myc = 0;
+  int32_t mye = 0;
   float myw = 1.f;
   if (k + gl < k1) {
-    myc = __ldg(p.col + k + gl);
+    if constexpr (DROP) mye = __ldg(p.edge_id + k + gl);
+    myc = load_col<HOT>(p, k + gl);
     if constexpr (HAS_EW) myw = __ldg(p.edge_w + k + gl);
-    if constexpr (HAS_SS) myw = __fmul_rn(myw, __ldg(p.src_scale + myc));
+    if constexpr (HAS_SS) myw = __fmul_rn(myw, __ldg(p.src_scale + (myc & 0x7fffffff)));
   }
   while (k < k1) {
     const int64_t rem = k1 - k;
     const int cnt = rem < G ? (int)rem : G;
     const int64_t kn = k + G;
     int32_t nc = 0;
+    int32_t ne = 0;
     float nw = 1.f;
     if (kn + gl < k1) {  // prefetch the next index batch while this one is consumed
-      nc = __ldg(p.col + kn + gl);
+      if constexpr (DROP) ne = __ldg(p.edge_id + kn + gl);
+      nc = load_col<HOT>(p, kn + gl);
       if constexpr (HAS_EW) nw = __ldg(p.edge_w + kn + gl);
-      if constexpr (HAS_SS) nw = __fmul_rn(nw, __ldg(p.src_scale + nc));
+      if constexpr (HAS_SS) nw = __fmul_rn(nw, __ldg(p.src_scale + (nc & 0x7fffffff)));
     }
 #pragma unroll 1
     for (int j = 0; j < cnt; j += U) {
       float v[U][NCH][VEC];
       float w[U];
       int32_t c[U];
+      uint32_t mk[U][NCH];
       const int64_t kk0 = k + j;
-      load_batch_full<VEC, G, NCH, U, HAS_W, SPLIT>(p, myc, myw, j, gl, gmask, on, v, w, c);
+      load_batch_full<VEC, G, NCH, U, HAS_W, SPLIT, HOT, DROP>(p, myc, myw, mye, j, gl, gmask, on, v, w, c, mk);
       if (j + U <= cnt && kk0 + U <= cur_end) {
         // fast path (group-uniform): a full batch that lies inside the current row
-        accum_all<VEC, NCH, U, IS_MAX, HAS_W, SQDEV>(acc, aidx, v, w, c, on, negate);
+        accum_all<VEC, NCH, U, IS_MAX, HAS_W, SQDEV, DROP>(acc, aidx, v, w, c, on, negate, mk, p.drop_scale);
         continue;
       }
       // distribute the (up to U) loaded edges over the rows they belong to
@@ -353,7 +417,7 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
             for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
               for (int e = 0; e < VEC; ++e)
-                accum<IS_MAX, HAS_W, SQDEV>(acc[ch][e], aidx[ch][e], v[u][ch][e], w[u], c[u], negate);
+                accum<IS_MAX, HAS_W, SQDEV>(acc[ch][e], aidx[ch][e], dropped<DROP>(v[u][ch][e], mk[u][ch], e, p.drop_scale), w[u], c[u], negate);
           }
         }
         done = lim;
@@ -368,6 +432,7 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
       }
     }
     myc = nc;
+    mye = ne;
     myw = nw;
     k = kn;
   }
@@ -388,7 +453,7 @@ __device__ __forceinline__ void walk_rows(const GRP& p, int64_t r0, int ra, int 
 #endif
 constexpr int UNIT_ROWS = KGB_GR_UNIT_ROWS;
 
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV, bool HOT, bool DROP>
 __device__ __forceinline__ void do_chunk(const GRP& p, int64_t t, int gl, unsigned gmask, const bool (&on)[NCH]) {
   // one chunk of a hub row -> raw partial
   float acc[NCH][VEC];
@@ -401,7 +466,7 @@ __device__ __forceinline__ void do_chunk(const GRP& p, int64_t t, int gl, unsign
   const int64_t rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
   const int64_t k0 = rs + ci * p.hub_chunk;
   const int64_t k1 = (k0 + p.hub_chunk < re) ? k0 + p.hub_chunk : re;
-  reduce_range<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT, SQDEV>(p, k0, k1, gl, gmask, on, acc, aidx);
+  reduce_range<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT, SQDEV, HOT, DROP>(p, k0, k1, gl, gmask, on, acc, aidx);
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     if (!on[ch]) continue;
@@ -411,7 +476,7 @@ __device__ __forceinline__ void do_chunk(const GRP& p, int64_t t, int gl, unsign
   }
 }
 
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV, bool HOT, bool DROP>
 __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, int gw, unsigned gmask,
                                              const bool (&on)[NCH]) {
   // a block of G consecutive rows: lane gl holds rowptr[r0+gl], rowptr[r0+gl+1]
@@ -431,7 +496,7 @@ __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, i
     if (seg_end > cur) {
       const int64_t k0 = __shfl_sync(gmask, my_lo, cur, G);
       const int64_t k1 = __shfl_sync(gmask, my_hi, seg_end - 1, G);
-      walk_rows<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT, SQDEV>(p, r0, cur, seg_end, k0, k1, my_hi, gl, gmask, on);
+      walk_rows<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT, SQDEV, HOT, DROP>(p, r0, cur, seg_end, k0, k1, my_hi, gl, gmask, on);
     }
     cur = seg_end + 1;  // the hub row (if any) is written by hub_finish_kernel
   }
@@ -453,7 +518,7 @@ __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, i
 // with the id structure of power-law graphs (RMAT: the degree depends on the low id bits), which left
 // 27 % of the SM-cycles idle in the first version.  Which warp computes a row never changes the
 // result, so the output stays deterministic.
-template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV>
+template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV, bool HOT, bool DROP>
 __global__ void __launch_bounds__(256, ((VEC == 4 && G >= 16) ? (IS_MAX ? KGB_GR_MINB_MAX : KGB_GR_MINB_WIDE)
                                                               : KGB_GR_MINB_NARROW))
 gather_reduce_kernel(const GRP p) {
@@ -483,14 +548,14 @@ gather_reduce_kernel(const GRP p) {
     if (u >= n_units) break;
     if (u < chunk_units) {
       const int64_t t = u * GPW + gw;
-      if (t < p.n_chunks) do_chunk<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT, SQDEV>(p, t, gl, gmask, on);
+      if (t < p.n_chunks) do_chunk<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT, SQDEV, HOT, DROP>(p, t, gl, gmask, on);
     } else {
       int64_t ui = u - chunk_units;
       if (p.unit_order) ui = __ldg(p.unit_order + ui);
       const int64_t base = ui * UNIT_ROWS;
       for (int b = gw; b < BPU; b += GPW) {
         const int64_t r0 = base + (int64_t)b * G;
-        if (r0 < p.n_rows) do_row_block<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT, SQDEV>(p, r0, gl, gw, gmask, on);
+        if (r0 < p.n_rows) do_row_block<VEC, G, NCH, IS_MAX, HAS_EW, HAS_SS, SPLIT, SQDEV, HOT, DROP>(p, r0, gl, gw, gmask, on);
       }
     }
     if (!p.work) u += (int64_t)gridDim.x * wpb;
@@ -972,6 +1037,26 @@ __global__ void reduce_parts_kernel(const float* __restrict__ part, int n_parts,
   out[f] = s;
 }
 
+// keep an element when its 32 random bits are >= p * 2^32
+static inline uint32_t dropout_threshold(float p) {
+  const double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xffffffffu : (t < 1.0 ? 1u : (uint32_t)t);
+}
+
+// the dropout mask the kernels apply, written out for tests: out[e, f] = 1 / (1 - p) if element f of edge e survives
+__global__ void dropout_mask_kernel(const int32_t* __restrict__ edge_id, int64_t n_edges, int F, int per_head,
+                                    uint32_t thr, float scale, uint32_t seed_lo, uint32_t seed_hi,
+                                    float* __restrict__ out) {
+  const int64_t total = n_edges * (int64_t)F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i / F;
+    const uint32_t f = (uint32_t)(i - e * F);
+    const uint32_t eid = edge_id ? (uint32_t)__ldg(edge_id + e) : (uint32_t)e;
+    const uint32_t bits = dropout_keep4(eid, f >> 2, per_head ? 1u : 0u, seed_lo, seed_hi, thr);
+    out[i] = ((bits >> (f & 3u)) & 1u) ? scale : 0.f;
+  }
+}
+
 // ---- host-side dispatch ----------------------------------------------------------------------
 struct Shape {
   int vec, g, nch;
@@ -1012,14 +1097,22 @@ static int launch_gr(int device, const GRP& p, bool is_max, cudaStream_t st) {
   const bool ew = p.edge_w != nullptr, ss = p.src_scale != nullptr;
   // the split-source / split-output variant is a separate instantiation: the common path pays nothing for it
   const bool split = p.x2 != nullptr || p.n_split_out != INT64_MAX;
-#define KGB_GR_LAUNCH(MAXF, EW, SS)                                                                        \
-  do {                                                                                                     \
-    if (split) gather_reduce_kernel<VEC, G, NCH, MAXF, EW, SS, !MAXF, false><<<grid, 256, 0, st>>>(p);     \
-    else gather_reduce_kernel<VEC, G, NCH, MAXF, EW, SS, false, false><<<grid, 256, 0, st>>>(p);           \
+#define KGB_GR_LAUNCH(MAXF, EW, SS)                                                                            \
+  do {                                                                                                         \
+    if (split) gather_reduce_kernel<VEC, G, NCH, MAXF, EW, SS, !MAXF, false, false, false><<<grid, 256, 0, st>>>(p);  \
+    else if (drop && !EW && !MAXF) gather_reduce_kernel<VEC, G, NCH, false, false, SS, false, false, false, true><<<grid, 256, 0, st>>>(p); \
+    else if (hot && !EW) gather_reduce_kernel<VEC, G, NCH, MAXF, false, SS, false, false, true, false><<<grid, 256, 0, st>>>(p); \
+    else gather_reduce_kernel<VEC, G, NCH, MAXF, EW, SS, false, false, false, false><<<grid, 256, 0, st>>>(p); \
   } while (0)
+  const bool drop = p.drop_thr != 0u;
+  if (drop && (is_max || ew || split || p.sqdev)) {
+    set_error("in-kernel dropout is available for sum / mean without per-edge weights or split operands");
+    return KGB_ERR_INVALID;
+  }
+  const bool hot = p.col_hot != nullptr && !split;
   if (p.sqdev) {
     if (is_max || ew || ss || split) { set_error("the squared-deviation pass takes no weights / split operands"); return KGB_ERR_INVALID; }
-    gather_reduce_kernel<VEC, G, NCH, false, false, false, false, true><<<grid, 256, 0, st>>>(p);
+    gather_reduce_kernel<VEC, G, NCH, false, false, false, false, true, false, false><<<grid, 256, 0, st>>>(p);
   } else if (is_max) {
     if (ew || ss) { set_error("max/min do not take edge weights"); return KGB_ERR_INVALID; }
     if (split) { set_error("max/min do not take split operands"); return KGB_ERR_INVALID; }
@@ -1169,6 +1262,14 @@ int kgb_gather_reduce(int device, const kgb_gather_reduce_args* a, kgb_stream_t 
     p.n_split_src = a->x2 ? a->n_split_src : INT64_MAX;
     p.out2 = a->out2 ? a->out2 + f0 : nullptr; p.ldo2 = a->ldo2;
     p.n_split_out = split_out ? a->n_split_out : INT64_MAX;
+    p.col_hot = a->col_hot;
+    p.edge_id = a->edge_id; p.drop_thr = 0u; p.drop_scale = 1.f;
+    p.seed_lo = (uint32_t)(a->drop_seed & 0xffffffffull); p.seed_hi = (uint32_t)(a->drop_seed >> 32);
+    if (a->drop_p > 0.f) {
+      KGB_REQUIRE(a->drop_p < 1.f && a->edge_id != nullptr, "dropout needs 0 < p < 1 and the edge ids of the slots");
+      p.drop_thr = dropout_threshold(a->drop_p);
+      p.drop_scale = 1.f / (1.f - a->drop_p);
+    }
     p.has_push = a->out2_push ? 1 : 0;
     p.tab = tab;
     if (p.has_push)
@@ -1346,6 +1447,21 @@ int kgb_halo_push(int device, const kgb_halo_push_args* a, kgb_stream_t stream) 
     KGB_DISPATCH_SHAPE(s, (halo_push_kernel<V, G_, N_><<<grid, 256, 0, st>>>(a->src + f0, a->lds, a->idx, Fs, a->ldd, t2)));
     KGB_CHECK_LAUNCH();
   }
+  return KGB_OK;
+}
+
+int kgb_dropout_mask(int device, const int32_t* edge_id, int64_t n_edges, int32_t F, int32_t per_head, float p,
+                     uint64_t seed, float* out, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(n_edges >= 0 && F > 0 && p > 0.f && p < 1.f && out, "bad arguments");
+  if (n_edges == 0) return KGB_OK;
+  int64_t grid = ceil_div(n_edges * (int64_t)F, 256);
+  const int64_t cap = (int64_t)sm_count(device) * 16;
+  if (grid > cap) grid = cap;
+  dropout_mask_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(edge_id, n_edges, F, per_head, dropout_threshold(p),
+                                                                  1.f / (1.f - p), (uint32_t)(seed & 0xffffffffull),
+                                                                  (uint32_t)(seed >> 32), out);
+  KGB_CHECK_LAUNCH();
   return KGB_OK;
 }
 

@@ -42,7 +42,17 @@ struct GatP {
   int32_t* work;   // [2 * gridDim.y] zero on entry (queue head, finished CTAs) or NULL
   const int32_t* unit_order;  // optional permutation of the row units (heaviest first)
   int64_t n_rows;  // rows of the walked structure
+  // attention dropout (layers/gatv2_conv.py:252-253), fused: alpha of (edge, head) survives when Philox(edge id,
+  // head) >= thr and is scaled by 1 / (1 - p); edge_id[k] = original edge id of slot k of the walked structure
+  const int32_t* edge_id; uint32_t drop_thr; float drop_scale; uint32_t seed_lo, seed_hi;
 };
+
+// dropout factor of (edge, head): 1 / (1 - p) or 0; 1 when dropout is off
+__device__ __forceinline__ float gat_drop(const GatP& p, uint32_t eid, int head) {
+  if (p.drop_thr == 0u) return 1.f;
+  const uint32_t bits = dropout_keep4(eid, (uint32_t)head >> 2, 1u, p.seed_lo, p.seed_hi, p.drop_thr);
+  return ((bits >> (head & 3)) & 1u) ? p.drop_scale : 0.f;
+}
 
 template <int LPH>
 __device__ __forceinline__ float head_sum(float v, unsigned gmask) {
@@ -167,12 +177,15 @@ __device__ __forceinline__ void gat_fwd_range(const GatP& p, const LaneCtx<VEC, 
   m = -INFINITY;
   l = 0.f;
   int64_t k = k0;
+  const bool drop = p.drop_thr != 0u;
   int32_t myc = (k + L.gl < k1) ? __ldg(p.col + k + L.gl) : 0;
+  int32_t mye = (drop && k + L.gl < k1) ? __ldg(p.edge_id + k + L.gl) : 0;
   while (k < k1) {
     const int64_t rem = k1 - k;
     const int cnt = rem < G ? (int)rem : G;
     const int64_t kn = k + G;
     const int32_t nc = (kn + L.gl < k1) ? __ldg(p.col + kn + L.gl) : 0;
+    const int32_t ne = (drop && kn + L.gl < k1) ? __ldg(p.edge_id + kn + L.gl) : 0;
 #pragma unroll 1
     for (int j = 0; j < cnt; j += U) {
       float v[U][CC][VEC];
@@ -208,16 +221,18 @@ __device__ __forceinline__ void gat_fwd_range(const GatP& p, const LaneCtx<VEC, 
       for (int u = 0; u < U; ++u) {
         if ((j + u) < cnt) {
           const float pe = expf(s[u] - mb);
-          l += pe;
+          l += pe;   // the softmax normalises over ALL edges; dropout only thins the weighted sum
+          const float pd = drop ? pe * gat_drop(p, (uint32_t)__shfl_sync(L.gmask, mye, j + u, G), L.head) : pe;
 #pragma unroll
           for (int cc = 0; cc < CC; ++cc)
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[cc][e] = fmaf(pe, v[u][cc][e], acc[cc][e]);
+            for (int e = 0; e < VEC; ++e) acc[cc][e] = fmaf(pd, v[u][cc][e], acc[cc][e]);
         }
       }
       m = mb;
     }
     myc = nc;
+    mye = ne;
     k = kn;
   }
 }
@@ -360,12 +375,15 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
   const float m = __ldg(p.rowmax + row * p.H + hd);
   const float dinv = 1.f / (__ldg(p.rowden + row * p.H + hd) + 1e-10f);
   int64_t k = k0;
+  const bool drop = p.drop_thr != 0u;
   int32_t myc = (k + L.gl < k1) ? __ldg(p.col + k + L.gl) : 0;
+  int32_t mye = (drop && k + L.gl < k1) ? __ldg(p.edge_id + k + L.gl) : 0;
   while (k < k1) {
     const int64_t rem = k1 - k;
     const int cnt = rem < G ? (int)rem : G;
     const int64_t kn = k + G;
     const int32_t nc = (kn + L.gl < k1) ? __ldg(p.col + kn + L.gl) : 0;
+    const int32_t ne = (drop && kn + L.gl < k1) ? __ldg(p.edge_id + kn + L.gl) : 0;
 #pragma unroll 1
     for (int j = 0; j < cnt; j += U) {
       float v[U][CC][VEC];
@@ -388,7 +406,8 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
             dp = fmaf(gi[cc][e], v[u][cc][e], dp);
           }
         const float s = head_sum<LPH>(sp, L.gmask);
-        const float da = head_sum<LPH>(dp, L.gmask);
+        float da = head_sum<LPH>(dp, L.gmask);
+        if (drop) da *= gat_drop(p, (uint32_t)__shfl_sync(L.gmask, mye, j + u, G), L.head);   // d out / d alpha
         if ((j + u) < cnt) {
           const float alpha = expf(s - m) * dinv;
           const float ds = alpha * (da - r);
@@ -405,6 +424,7 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
       }
     }
     myc = nc;
+    mye = ne;
     k = kn;
   }
   return r;
@@ -500,12 +520,15 @@ __device__ __forceinline__ void gat_bwd_src_range(const GatP& p, const LaneCtx<V
   }
   const int hd = L.head < p.H ? L.head : 0;
   int64_t k = k0;
+  const bool drop = p.drop_thr != 0u;
   int32_t myc = (k + L.gl < k1) ? __ldg(p.col + k + L.gl) : 0;
+  int32_t mye = (drop && k + L.gl < k1) ? __ldg(p.edge_id + k + L.gl) : 0;
   while (k < k1) {
     const int64_t rem = k1 - k;
     const int cnt = rem < G ? (int)rem : G;
     const int64_t kn = k + G;
     const int32_t nc = (kn + L.gl < k1) ? __ldg(p.col + kn + L.gl) : 0;
+    const int32_t ne = (drop && kn + L.gl < k1) ? __ldg(p.edge_id + kn + L.gl) : 0;
 #pragma unroll 1
     for (int j = 0; j < cnt; j += U) {
       float hi[U][CC][VEC], gi[U][CC][VEC];
@@ -534,21 +557,25 @@ __device__ __forceinline__ void gat_bwd_src_range(const GatP& p, const LaneCtx<V
             dp = fmaf(L.on[cc] ? gi[u][cc][e] : 0.f, hj[cc][e], dp);
           }
         const float s = head_sum<LPH>(sp, L.gmask);
-        const float da = head_sum<LPH>(dp, L.gmask);
+        float da = head_sum<LPH>(dp, L.gmask);
+        const float d = drop ? gat_drop(p, (uint32_t)__shfl_sync(L.gmask, mye, j + u, G), L.head) : 1.f;
+        da *= d;
         if ((j + u) < cnt) {
           const float alpha = expf(s - m[u]) * dinv[u];
           const float ds = alpha * (da - r[u]);
+          const float ad = alpha * d;   // the message itself: alpha_e * dropout_e * h_j
 #pragma unroll
           for (int cc = 0; cc < CC; ++cc)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
               const float z = hi[u][cc][e] + hj[cc][e];
-              ghj[cc][e] += ds * L.a[cc][e] * (z > 0.f ? 1.f : p.slope) + alpha * gi[u][cc][e];
+              ghj[cc][e] += ds * L.a[cc][e] * (z > 0.f ? 1.f : p.slope) + ad * gi[u][cc][e];
             }
         }
       }
     }
     myc = nc;
+    mye = ne;
     k = kn;
   }
 }
@@ -674,6 +701,22 @@ static bool gat_can4(const GatP& p) {
          (!p.partial || aligned16(p.partial));
 }
 
+static int gat_set_dropout(GatP& p, const kgb_gat_dropout* d) {
+  p.edge_id = nullptr; p.drop_thr = 0u; p.drop_scale = 1.f; p.seed_lo = p.seed_hi = 0u;
+  if (!d || d->p <= 0.f) return KGB_OK;
+  if (!(d->p < 1.f) || !d->edge_id) {
+    set_error("attention dropout needs 0 < p < 1 and the edge ids of the walked structure");
+    return KGB_ERR_INVALID;
+  }
+  const double t = (double)d->p * 4294967296.0;
+  p.drop_thr = t >= 4294967295.0 ? 0xffffffffu : (t < 1.0 ? 1u : (uint32_t)t);
+  p.drop_scale = 1.f / (1.f - d->p);
+  p.edge_id = d->edge_id;
+  p.seed_lo = (uint32_t)(d->seed & 0xffffffffull);
+  p.seed_hi = (uint32_t)(d->seed >> 32);
+  return KGB_OK;
+}
+
 static void gat_set_hubs(GatP& p, const kgb_hub_table* hubs) {
   if (hubs && hubs->n_hubs > 0 && hubs->n_chunks > 0 && hubs->partial) {
     p.hub_row = hubs->hub_row; p.hub_chunk_base = hubs->hub_chunk_base; p.hub_nchunks = hubs->hub_nchunks;
@@ -731,8 +774,8 @@ size_t kgb_gatv2_partial_bytes(int32_t n_chunks, int32_t H, int32_t C) {
 
 int kgb_gatv2_fwd(int device, const float* hsrc, const float* hdst, int64_t n_src, int64_t n_dst, int32_t H,
                   int32_t C, const float* att, float slope, const int64_t* rowptr, const int32_t* col,
-                  const float* bias, float* out, float* rowmax, float* rowden, const kgb_hub_table* hubs,
-                  kgb_stream_t stream) {
+                  const float* bias, float* out, float* rowmax, float* rowden, const kgb_gat_dropout* drop,
+                  const kgb_hub_table* hubs, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(H > 0 && C > 0 && n_dst >= 0 && n_src >= 0, "bad sizes");
   if (n_dst == 0) return KGB_OK;
@@ -741,6 +784,7 @@ int kgb_gatv2_fwd(int device, const float* hsrc, const float* hdst, int64_t n_sr
   p.hsrc = hsrc; p.hdst = hdst; p.n_src = n_src; p.n_dst = n_dst; p.H = H; p.C = C; p.att = att; p.slope = slope;
   p.rowptr = rowptr; p.col = col; p.bias = bias; p.out = out; p.rowmax = rowmax; p.rowden = rowden;
   p.n_rows = n_dst;
+  if (gat_set_dropout(p, drop) != KGB_OK) return KGB_ERR_INVALID;
   gat_set_hubs(p, hubs);
   return gat_run(device, GAT_FWD, p, (cudaStream_t)stream, 6, 0, nullptr);
 }
@@ -755,7 +799,7 @@ int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float*
                       int64_t n_src, int64_t n_dst, int32_t H, int32_t C, const float* att, float slope,
                       const int64_t* rowptr, const int32_t* col, const float* rowmax, const float* rowden,
                       const float* bias, float* g_hdst, float* r, float* g_att_part, int32_t n_parts,
-                      const kgb_hub_table* hubs, kgb_stream_t stream) {
+                      const kgb_gat_dropout* drop, const kgb_hub_table* hubs, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(H > 0 && C > 0 && n_dst >= 0 && n_parts > 0, "bad sizes");
   KGB_REQUIRE(g_att_part, "g_att_part is NULL");
@@ -768,6 +812,7 @@ int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float*
   p.rowptr = rowptr; p.col = col; p.rowmax = const_cast<float*>(rowmax); p.rowden = const_cast<float*>(rowden);
   p.g = g; p.agg = agg; p.bias = bias; p.g_hdst = g_hdst; p.r_out = r; p.g_att_part = g_att_part;
   p.n_rows = n_dst;
+  if (gat_set_dropout(p, drop) != KGB_OK) return KGB_ERR_INVALID;
   gat_set_hubs(p, hubs);
   return gat_run(device, GAT_BWD_DST, p, st, 4, n_parts, g_hdst);
 }
@@ -775,7 +820,8 @@ int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float*
 int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float* hdst, int64_t n_src,
                       int64_t n_dst, int32_t H, int32_t C, const float* att, float slope, const int64_t* colptr,
                       const int32_t* row, const float* rowmax, const float* rowden, const float* r,
-                      const float* addend, float* g_hsrc, const kgb_hub_table* hubs, kgb_stream_t stream) {
+                      const float* addend, float* g_hsrc, const kgb_gat_dropout* drop, const kgb_hub_table* hubs,
+                      kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(H > 0 && C > 0 && n_src >= 0, "bad sizes");
   if (n_src == 0) return KGB_OK;
@@ -785,6 +831,7 @@ int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float
   p.rowptr = colptr; p.col = row; p.rowmax = const_cast<float*>(rowmax); p.rowden = const_cast<float*>(rowden);
   p.g = g; p.r_in = r; p.addend = addend; p.g_hsrc = g_hsrc;
   p.n_rows = n_src;
+  if (gat_set_dropout(p, drop) != KGB_OK) return KGB_ERR_INVALID;
   gat_set_hubs(p, hubs);
   return gat_run(device, GAT_BWD_SRC, p, (cudaStream_t)stream, 4, 0, g_hsrc);
 }

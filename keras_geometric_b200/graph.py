@@ -8,6 +8,7 @@ forward and backward.
 """
 from __future__ import annotations
 
+import os
 import weakref
 from collections import OrderedDict
 
@@ -34,7 +35,8 @@ class Csr:
     ``perm`` int32 [nnz] (original edge id of each slot, stable), ``deg`` int32 [n]."""
 
     __slots__ = ("n_rows", "n_cols", "nnz", "rowptr", "col", "perm", "deg", "hub_row", "hub_chunk_base",
-                 "hub_nchunks", "chunk_hub", "n_hubs", "n_chunks", "_inv_deg", "_partials", "_deg_f", "_work", "_unit_order")
+                 "hub_nchunks", "chunk_hub", "n_hubs", "n_chunks", "_inv_deg", "_partials", "_deg_f", "_work", "_unit_order",
+                 "_hot")
 
     def __init__(self):
         self._inv_deg = None
@@ -45,6 +47,7 @@ class Csr:
         self.hub_row = self.hub_chunk_base = self.hub_nchunks = self.chunk_hub = None
         self._work = {}
         self._unit_order = {}
+        self._hot = {}
 
     def work(self, stream_id: int) -> torch.Tensor:
         """Task-queue counters of kgb_gather_reduce (zero between launches), one pair per stream."""
@@ -68,6 +71,29 @@ class Csr:
             d = torch.nn.functional.pad(d, (0, (-self.n_rows) % ur)).view(-1, ur).sum(1)
             order = self._unit_order[ur] = torch.sort(d, descending=True, stable=True)[1].to(torch.int32)
         return order
+
+    def col_hot(self, F: int):
+        """Copy of ``col`` with bit 31 set on the K most frequently referenced rows, K = budget / row bytes
+        (KGB200_HOT_MB of the 126 MB L2; default 0 = off), for kgb_gather_reduce's L2 eviction hints.  On a power-law
+        graph 3 % of the rows carry > 60 % of the references; measured on C4 the hints gain 3 % at F = 256 and lose
+        6-19 % for narrower rows, so they are opt-in.  None when off or when the whole matrix fits in the L2."""
+        budget = int(os.environ.get("KGB200_HOT_MB", "0")) << 20
+        row_bytes = 4 * int(F)
+        if budget <= 0 or self.nnz < (1 << 20) or self.n_cols * row_bytes <= (96 << 20):
+            return None
+        K = max(1, budget // row_bytes)
+        K = 1 << (K.bit_length() - 1)          # few distinct sets per structure
+        if K >= self.n_cols:
+            return None
+        tagged = self._hot.get(K)
+        if tagged is None:
+            cnt = torch.bincount(self.col.long(), minlength=self.n_cols)
+            thr = torch.topk(cnt, K).values[-1].clamp(min=2)        # rows gathered once gain nothing from residency
+            hot = (cnt >= thr)[self.col.long()]
+            tagged = torch.where(hot, self.col | torch.tensor(-2 ** 31, dtype=torch.int32, device=self.col.device),
+                                 self.col).contiguous()
+            self._hot[K] = tagged
+        return tagged
 
     def hub_table(self, partial_bytes: int, stream_id: int, gat: bool = False):
         """ctypes ``kgb_hub_table`` for the GATv2 kernels (keeps the partial buffer alive on self)."""

@@ -139,10 +139,16 @@ class GATv2Conv(MessagePassing):
         graph = get_graph(edge_index, n, n_src, n_loops)
         att = value_of(self.att)
         bias = value_of(self.bias) if (self.use_bias and self.bias is not None) else None
-        if self.dropout_layer is not None and training:
+        if C > 512 or (C > 128 and C % 4 != 0):
+            # wider than the fused kernels' lane layout (per-head width / vector <= 128): the reference's per-edge
+            # formulation on top of the segment kernels (any output_dim is accepted, like the reference)
             return self._propagate_with_dropout(h_i, h_j, graph, att, bias, training)
+        # attention dropout (gatv2_conv.py:252-253, training only) is generated inside the fused kernels: alpha is
+        # never materialised
+        drop = float(self.dropout_rate) if (self.dropout_layer is not None and training) else 0.0
         fuse_bias = bias is not None and (self.concat or H == 1)
-        out = ops.gatv2_aggregate(h_j, h_i, att, graph, H, C, self.negative_slope, bias if fuse_bias else None)
+        out = ops.gatv2_aggregate(h_j, h_i, att, graph, H, C, self.negative_slope, bias if fuse_bias else None,
+                                  dropout=drop)
         if not self.concat and H > 1:
             out = out.reshape(n, H, C).mean(dim=1)
             if bias is not None:
@@ -150,8 +156,8 @@ class GATv2Conv(MessagePassing):
         return out
 
     def _propagate_with_dropout(self, h_i, h_j, graph, att, bias, training):
-        """Training with attention dropout (gatv2_conv.py:252-253): alpha must be materialised, so this
-        follows the reference's per-edge formulation on top of the segment kernels."""
+        """The reference's per-edge formulation (gatv2_conv.py:241-335) on top of the segment kernels, alpha
+        materialised: used for per-head widths beyond the fused kernels' layout."""
         n, H, C = int(h_i.shape[0]), self.heads, self.features_per_head
         hj_e = ops.take_rows(h_j, graph, "src").reshape(-1, H, C)
         hi_e = ops.take_rows(h_i, graph, "dst").reshape(-1, H, C)
@@ -163,7 +169,8 @@ class GATv2Conv(MessagePassing):
         p = torch.exp(s - m.index_select(0, dst))
         d = ops.segment_reduce(p, graph, "sum")
         alpha = p / (d.index_select(0, dst) + 1e-10)
-        alpha = self.dropout_layer(alpha, training=training)
+        if self.dropout_layer is not None and training:
+            alpha = self.dropout_layer(alpha, training=training)
         msg = (alpha.unsqueeze(-1) * hj_e).reshape(-1, H * C)
         agg = ops.segment_reduce(msg, graph, "sum").reshape(n, H, C)
         return self._final_update(agg, bias)

@@ -135,10 +135,13 @@ class GCNConv(MessagePassing):
             return out + bias if bias is not None else out
         graph = get_graph(edge_index, num_nodes, num_nodes, n_loops)
         self._current_training = training
-        fast = (not dropping) and type(self).message is GCNConv.message and type(self).update is GCNConv.update
+        fast = type(self).message is GCNConv.message and type(self).update is GCNConv.update
         if fast:
             h = ops.linear(x, kernel)  # dense transform once per node on the tensor cores (K8)
-            return ops.gather_reduce(h, graph, "sum", weight="gcn" if self.normalize else None, bias=bias)
+            # training: the reference drops the per-edge transformed messages element-wise (gcn_conv.py:238-242);
+            # the same dropout is generated inside the gather (Philox on the edge id), no [E, F] tensor exists
+            return ops.gather_reduce(h, graph, "sum", weight="gcn" if self.normalize else None, bias=bias,
+                                     dropout=float(self.dropout_rate) if dropping else 0.0)
         # per-edge path: dropout on the transformed messages (gcn_conv.py:238-242) or user overrides
         w = graph.gcn_norm()[1] if self.normalize else torch.ones(graph.nnz, dtype=x.dtype, device=x.device)
         self._current_edge_weights = w

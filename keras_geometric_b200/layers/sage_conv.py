@@ -106,6 +106,9 @@ class SAGEConv(MessagePassing):
         graph = get_graph(edge_index, num_nodes, num_nodes, 0)
         dropping = self.dropout_rate > 0 and bool(training)
         default_hooks = type(self).message is SAGEConv.message and self._uses_default("aggregate", "update")
+        if default_hooks and dropping and agg_name in ("sum", "mean"):
+            # per-edge dropout of x_j (sage_conv.py:295-297) generated inside the gather: no [E, F] messages
+            return ops.gather_reduce(x, graph, agg_name, dropout=float(self.dropout_rate))
         if default_hooks and not dropping:
             if agg_name in ("sum", "mean", "max", "min"):
                 return ops.gather_reduce(x, graph, agg_name)

@@ -51,6 +51,23 @@ class _prof:
         return False
 
 
+def next_dropout_seed() -> int:
+    """A fresh 63-bit seed for an in-kernel dropout mask, drawn from torch's default CPU generator (so
+    ``torch.manual_seed`` makes training runs reproducible)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def dropout_mask(edge_ids, n_edges: int, width: int, p: float, seed: int, per_head: bool = False, device=None):
+    """The mask the kernels apply ([n_edges, width]: 1 / (1 - p) or 0), written out by kgb_dropout_mask - for tests."""
+    lib = _lib.load()
+    dev = edge_ids.device if edge_ids is not None else torch.device(device or "cuda")
+    out = torch.empty((n_edges, width), dtype=torch.float32, device=dev)
+    _lib.check(lib.kgb_dropout_mask(dev.index if dev.index is not None else torch.cuda.current_device(), _ptr(edge_ids),
+                                    n_edges, width, int(per_head), float(p), int(seed), out.data_ptr(), _stream(dev)),
+               "kgb_dropout_mask")
+    return out
+
+
 def gat_bytes(nnz: int, n: int, H: int, C: int) -> int:
     """B_fwd(gatv2) = E'(4HC + 4) + N*4HC (h_i) + N*4HC (out) + N*H*8 (max, denom) + (N+1)*8."""
     return nnz * (4 * H * C + 4) + 2 * n * 4 * H * C + n * H * 8 + (n + 1) * 8
@@ -75,7 +92,8 @@ def gather_reduce_raw(x: torch.Tensor, csr: Csr, op: int, *, col: torch.Tensor |
                       edge_w=None, src_scale=None, out_scale=None, addend=None, addend_scale: float = 1.0,
                       bias=None, act: int = 0, want_arg: bool = False, row_ids=None, out=None,
                       n_out_rows: int | None = None, x2=None, n_split_src: int | None = None, out2=None,
-                      out2_push=None, n_split_out: int | None = None, label: str | None = None):
+                      out2_push=None, n_split_out: int | None = None, label: str | None = None,
+                      drop_p: float = 0.0, drop_seed: int = 0):
     """One kgb_gather_reduce launch (no autograd).  Returns ``(out, arg_or_None)``.
     ``x2`` / ``n_split_src``: column ids >= n_split_src read ``x2`` (partitioned graphs: [owned | halo] sources without
     a concatenated copy).  ``out2`` or ``out2_push`` (a ``HaloPushArgs`` destination table) / ``n_split_out``: output
@@ -110,6 +128,10 @@ def gather_reduce_raw(x: torch.Tensor, csr: Csr, op: int, *, col: torch.Tensor |
         a.partial = partial.data_ptr()
     a.work = csr.work(_stream(dev)).data_ptr()
     a.unit_order = _ptr(csr.unit_order())
+    if drop_p > 0.0:   # element-wise dropout of the gathered rows, regenerated from the original edge ids
+        a.drop_p, a.drop_seed, a.edge_id = float(drop_p), int(drop_seed), csr.perm.data_ptr()
+    elif col is None and x2 is None and out2 is None and out2_push is None and op != _lib.OP_SQDEV:
+        a.col_hot = _ptr(csr.col_hot(F))        # L2 eviction hints for the hub rows (None: off / everything fits)
     if x2 is not None:
         a.x2, a.ldx2, a.n_split_src = x2.data_ptr(), x2.stride(0), int(n_split_src)
     if out2 is not None or out2_push is not None:
@@ -266,8 +288,16 @@ class _GatherReduce(torch.autograd.Function):
     """out = act(scale_out * OP_k(w_k * x[col_k]) + addend_scale * addend + bias)."""
 
     @staticmethod
-    def forward(ctx, x, addend, bias, graph: GraphStructure, op_name: str, weight, addend_scale, act):
+    def forward(ctx, x, addend, bias, graph: GraphStructure, op_name: str, weight, addend_scale, act, drop_p=0.0,
+                drop_seed=0):
         op = _lib.OPS[op_name]
+        ctx.drop = (float(drop_p), int(drop_seed))
+        if drop_p > 0.0:
+            kw_drop = {"drop_p": float(drop_p), "drop_seed": int(drop_seed)}
+            if op in _lib.MAX_OPS or not (weight is None or isinstance(weight, (str, tuple))):
+                raise ValueError("fused dropout supports sum / mean without per-edge weight tensors")
+        else:
+            kw_drop = {}
         x = _f32c(x, "x")
         csr = graph.csr
         kw = {}
@@ -297,7 +327,7 @@ class _GatherReduce(torch.autograd.Function):
         if is_max and (addend is not None or bias is not None or act not in (None, "linear")):
             raise ValueError("max/min aggregation cannot be fused with an epilogue (ties are detected on the raw result)")
         out, arg = gather_reduce_raw(x, csr, op, addend=addend_c, addend_scale=addend_scale, bias=bias_c,
-                                     act=_ACT[act], want_arg=is_max, **kw)
+                                     act=_ACT[act], want_arg=is_max, **kw, **kw_drop)
         ctx.graph, ctx.op, ctx.act, ctx.addend_scale = graph, op, act, float(addend_scale)
         ctx.has_addend, ctx.has_bias = addend is not None, bias is not None
         ctx.n_src = int(x.shape[0])
@@ -337,21 +367,29 @@ class _GatherReduce(torch.autograd.Function):
                     kw = {"edge_w": permute_f32(ctx.w_coo, csc.perm)}
                 if op == _lib.OP_MEAN:
                     kw["src_scale"] = graph.csr.inv_deg
+                if ctx.drop[0] > 0.0:   # the transposed pass regenerates the forward's mask from the edge ids
+                    kw.update(drop_p=ctx.drop[0], drop_seed=ctx.drop[1])
                 gx, _ = gather_reduce_raw(g, csc, _lib.OP_SUM, **kw)
-        return gx, g_addend, g_bias, None, None, None, None, None
+        return gx, g_addend, g_bias, None, None, None, None, None, None, None
 
 
 def gather_reduce(x, graph: GraphStructure, op: str = "sum", *, weight=None, addend=None,
-                  addend_scale: float = 1.0, bias=None, act=None) -> torch.Tensor:
+                  addend_scale: float = 1.0, bias=None, act=None, dropout: float = 0.0,
+                  dropout_seed: int | None = None) -> torch.Tensor:
     """Fused gather + segmented reduction over ``graph`` (K3/K4, backward K5).
 
     Equivalent to the reference's ``take(x, src)`` -> message -> ``Aggregator.aggregate`` chain
     (layers/message_passing.py:195-212) without materialising any [E, F] tensor.
     ``weight``: None, ``"gcn"`` (symmetric normalisation, utils/main.py:20-33), a
     ``(src_scale [n_src], dst_scale [n_dst])`` pair (w_e = dst_scale[i] * src_scale[j]) or a COO-ordered
-    [nnz] tensor."""
+    [nnz] tensor.  ``dropout`` > 0: fused element-wise dropout of the gathered rows (sum / mean)."""
     if op not in _lib.OPS:
         raise ValueError(f"Invalid aggregator: {op}. Available aggregators: {list(_lib.OPS)}")
+    if dropout > 0.0:
+        # element-wise dropout of the gathered rows x[src] BEFORE weighting / reduction (the reference's per-edge
+        # message dropout), generated in the kernel: no [E, F] tensor, the backward regenerates the mask
+        seed = next_dropout_seed() if dropout_seed is None else int(dropout_seed)
+        return _GatherReduce.apply(x, addend, bias, graph, op, weight, addend_scale, act, float(dropout), seed)
     return _GatherReduce.apply(x, addend, bias, graph, op, weight, addend_scale, act)
 
 
@@ -464,12 +502,23 @@ def take_rows(x, graph: GraphStructure, which: str = "src") -> torch.Tensor:
     return _TakeRows.apply(x, graph, which)
 
 
+def _gat_drop(drop, structure: Csr):
+    """ctypes ``kgb_gat_dropout`` for a (p, seed) pair over ``structure`` (its ``perm`` = original edge ids), or NULL."""
+    if drop[0] <= 0.0:
+        return None
+    d = _lib.GatDropout()
+    d.p, d.seed, d.edge_id = drop[0], drop[1], structure.perm.data_ptr()
+    return ctypes.byref(d)
+
+
 class _GatV2(torch.autograd.Function):
     """Fused GATv2 attention + aggregation over a graph structure (K6)."""
 
     @staticmethod
-    def forward(ctx, h_src, h_dst, att, bias, graph: GraphStructure, H: int, C: int, slope: float):
+    def forward(ctx, h_src, h_dst, att, bias, graph: GraphStructure, H: int, C: int, slope: float, drop_p=0.0,
+                drop_seed=0):
         lib = _lib.load()
+        ctx.drop = (float(drop_p), int(drop_seed))
         same = h_src is h_dst
         h_src = _f32c(h_src, "h_src").contiguous()
         h_dst = h_src if same else _f32c(h_dst, "h_dst").contiguous()
@@ -486,7 +535,7 @@ class _GatV2(torch.autograd.Function):
             _lib.check(lib.kgb_gatv2_fwd(dev.index, h_src.data_ptr(), h_dst.data_ptr(), n_src, n_dst, H, C,
                                          att_c.data_ptr(), float(slope), csr.rowptr.data_ptr(), csr.col.data_ptr(),
                                          _ptr(bias_c), out.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(),
-                                         ctypes.byref(hubs), _stream(dev)), "kgb_gatv2_fwd")
+                                         _gat_drop(ctx.drop, csr), ctypes.byref(hubs), _stream(dev)), "kgb_gatv2_fwd")
         ctx.graph, ctx.H, ctx.C, ctx.slope, ctx.same = graph, H, C, float(slope), same
         ctx.has_bias = bias is not None
         ctx.save_for_backward(h_src, h_dst, att_c, out, rowmax, rowden, *([bias_c] if bias is not None else []))
@@ -516,6 +565,7 @@ class _GatV2(torch.autograd.Function):
                                              n_src, n_dst, H, C, att_c.data_ptr(), ctx.slope, csr.rowptr.data_ptr(),
                                              csr.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(), _ptr(bias_c),
                                              g_hdst.data_ptr(), r.data_ptr(), part.data_ptr(), n_parts,
+                                             _gat_drop(ctx.drop, csr),
                                              ctypes.byref(csr.hub_table(lib.kgb_gatv2_partial_bytes(csr.n_chunks, H, C), st, gat=True)),
                                              st), "kgb_gatv2_bwd_dst")
         g_att = torch.empty(H * C, dtype=torch.float32, device=dev)
@@ -527,19 +577,25 @@ class _GatV2(torch.autograd.Function):
                                              H, C, att_c.data_ptr(), ctx.slope, csc.rowptr.data_ptr(),
                                              csc.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(), r.data_ptr(),
                                              g_hdst.data_ptr() if ctx.same else None, g_hsrc.data_ptr(),
+                                             _gat_drop(ctx.drop, csc),
                                              ctypes.byref(csc.hub_table(lib.kgb_gatv2_partial_bytes(csc.n_chunks, H, C), st, gat=True)),
                                              st), "kgb_gatv2_bwd_src")
         g_bias = relu_bwd_colsum(g, None)[1] if ctx.has_bias else None   # column sums in one pass (kgb_relu_bwd_colsum)
         if ctx.same:   # the per-target part was added in the per-source kernel's epilogue
-            return g_hsrc, None, g_att, g_bias, None, None, None, None
-        return g_hsrc, g_hdst, g_att, g_bias, None, None, None, None
+            return g_hsrc, None, g_att, g_bias, None, None, None, None, None, None
+        return g_hsrc, g_hdst, g_att, g_bias, None, None, None, None, None, None
 
 
 def gatv2_aggregate(h_src, h_dst, att, graph: GraphStructure, heads: int, channels: int,
-                    negative_slope: float = 0.2, bias=None) -> torch.Tensor:
+                    negative_slope: float = 0.2, bias=None, dropout: float = 0.0,
+                    dropout_seed: int | None = None) -> torch.Tensor:
     """Attention logits, per-target softmax and weighted aggregation of GATv2 in one kernel
     (reference: layers/gatv2_conv.py:241-335).  ``h_*`` are [N, H*C], ``att`` has H*C entries;
     returns [n_dst, H*C] (+ bias when given)."""
+    if dropout > 0.0:   # attention dropout (training): one decision per (edge, head), generated inside the kernels
+        seed = next_dropout_seed() if dropout_seed is None else int(dropout_seed)
+        return _GatV2.apply(h_src, h_dst, att.reshape(-1), bias, graph, int(heads), int(channels),
+                            float(negative_slope), float(dropout), seed)
     return _GatV2.apply(h_src, h_dst, att.reshape(-1), bias, graph, int(heads), int(channels), float(negative_slope))
 
 

@@ -636,6 +636,129 @@ def test_full_size_properties_products_slice():
     assert torch.allclose((gx * x).sum(), ref_dot, rtol=1e-4)
 
 
+# ------------------------------------------------------------------------------ fused dropout (training paths)
+def test_dropout_mask_statistics_and_reproducibility():
+    """The in-kernel Philox mask: keep rate 1 - p within 5 sigma for every feature column and head, a pure function of
+    (edge id, element, seed), different for different seeds and for the per-head stream."""
+    from keras_geometric_b200 import ops
+    E, F, p = 200_000, 20, 0.3
+    m1 = ops.dropout_mask(None, E, F, p, 1234).cpu().numpy()
+    m2 = ops.dropout_mask(None, E, F, p, 1234).cpu().numpy()
+    m3 = ops.dropout_mask(None, E, F, p, 1235).cpu().numpy()
+    mh = ops.dropout_mask(None, E, F, p, 1234, per_head=True).cpu().numpy()
+    np.testing.assert_array_equal(m1, m2)
+    assert set(np.unique(m1)) == {0.0, np.float32(1.0 / (1.0 - p))}
+    sigma = np.sqrt(p * (1 - p) / E)
+    for m in (m1, m3, mh):
+        keep = (m > 0).mean(axis=0)
+        assert np.all(np.abs(keep - (1 - p)) < 5 * sigma), keep
+    assert 0.4 < ((m1 > 0) != (m3 > 0)).mean() < 0.44         # independent masks disagree with prob. 2 p (1 - p)
+    assert 0.4 < ((m1 > 0) != (mh > 0)).mean() < 0.44
+    # edge ids select the rows of the same mask
+    ids = torch.randperm(E, device="cuda")[:1000].to(torch.int32)
+    sub = ops.dropout_mask(ids, 1000, F, p, 1234).cpu().numpy()
+    np.testing.assert_array_equal(sub, m1[ids.cpu().numpy()])
+
+
+@pytest.mark.parametrize("F,op,weight", [(7, "sum", None), (64, "mean", None), (100, "sum", "gcn"), (260, "mean", None)])
+def test_fused_gather_dropout_matches_explicit_mask(F, op, weight):
+    """Fused element-wise dropout of the gathered rows (GCN / SAGE training path): identical, forward and backward, to
+    the reference's formulation with the SAME mask written out explicitly ([E, F] messages x mask, then weighted and
+    reduced), including hub rows and (GCN) appended self-loops."""
+    from keras_geometric_b200 import ops
+    from keras_geometric_b200.graph import GraphStructure
+    rng = np.random.default_rng(F)
+    n, e, p, seed = 300, 9000, 0.4, 99 + F
+    ei = rand_graph(rng, n, n, e, hub=3000)
+    loops = n if weight == "gcn" else 0
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    R = rng.standard_normal((n, F)).astype(np.float32)
+    graph = GraphStructure(cuda(ei), n, n, loops)
+    assert graph.csr.n_hubs >= 1
+    xg = cuda(x).requires_grad_(True)
+    out = ops.gather_reduce(xg, graph, op, weight=weight, dropout=p, dropout_seed=seed)
+    (gx,) = torch.autograd.grad((out * cuda(R)).sum(), [xg])
+    mask = ops.dropout_mask(None, e + loops, F, p, seed).cpu()       # edge ids: real edges, then the self-loops
+    eio = torch.from_numpy(ei)
+    if loops:
+        eio = ref.add_self_loops(eio, n)
+    xo = torch.from_numpy(x).requires_grad_(True)
+    msg = xo[eio[0].long()] * mask
+    if weight == "gcn":
+        msg = msg * ref.compute_gcn_normalization(eio, n).unsqueeze(1)
+    want = ref.aggregate(op, msg, eio[1], n)
+    (gw,) = torch.autograd.grad((want * torch.from_numpy(R)).sum(), [xo])
+    close(out, want, msg=f"dropout fwd {op} F={F}")
+    close(gx, gw, msg=f"dropout grad {op} F={F}")
+    # without a seed every call draws a new mask; the expectation is the plain aggregation
+    a = ops.gather_reduce(xg, graph, op, weight=weight, dropout=p)
+    b = ops.gather_reduce(xg, graph, op, weight=weight, dropout=p)
+    assert not torch.equal(a, b)
+
+
+@pytest.mark.parametrize("H,C", [(1, 8), (4, 16), (8, 8), (3, 5)])
+def test_fused_gatv2_attention_dropout_matches_explicit_mask(H, C):
+    """GATv2 attention dropout inside the fused kernels vs the reference's per-edge formulation with the same
+    (edge, head) mask written out: alpha = softmax over ALL edges, then alpha * mask (gatv2_conv.py:241-335)."""
+    from keras_geometric_b200 import ops
+    from keras_geometric_b200.graph import GraphStructure
+    from oracle import keras_ops as kops
+    rng = np.random.default_rng(H * 100 + C)
+    n, e, p, seed = 200, 5000, 0.35, 7 + H
+    ei = rand_graph(rng, n, n, e, hub=1500)
+    h = rng.standard_normal((n, H * C)).astype(np.float32)
+    att = (rng.standard_normal((1, H, C)) * 0.5).astype(np.float32)
+    R = rng.standard_normal((n, H * C)).astype(np.float32)
+    graph = GraphStructure(cuda(ei), n, n, n)
+    hg, ag = cuda(h).requires_grad_(True), cuda(att).requires_grad_(True)
+    out = ops.gatv2_aggregate(hg, hg, ag, graph, H, C, 0.2, None, dropout=p, dropout_seed=seed)
+    gh, ga = torch.autograd.grad((out * cuda(R)).sum(), [hg, ag])
+    mask = ops.dropout_mask(None, e + n, H, p, seed, per_head=True).cpu()
+    eio = ref.add_self_loops(torch.from_numpy(ei), n)
+    src, dst = eio[0].long(), eio[1].int()
+    ho, ao = torch.from_numpy(h).requires_grad_(True), torch.from_numpy(att).requires_grad_(True)
+    hh = ho.reshape(n, H, C)
+    z = torch.nn.functional.leaky_relu(hh[dst.long()] + hh[src], 0.2)
+    s = (z * ao).sum(-1)
+    m = kops.segment_max(s, dst, num_segments=n)
+    pe = torch.exp(s - m[dst.long()])
+    d = kops.segment_sum(pe, dst, num_segments=n)
+    alpha = pe / (d[dst.long()] + 1e-10) * mask
+    want = kops.segment_sum((alpha.unsqueeze(-1) * hh[src]).reshape(-1, H * C), dst, num_segments=n)
+    gwh, gwa = torch.autograd.grad((want * torch.from_numpy(R)).sum(), [ho, ao])
+    close(out, want, msg=f"gat dropout fwd H={H} C={C}")
+    close(gh, gwh, msg=f"gat dropout grad h H={H} C={C}")
+    close(ga.reshape(gwa.shape), gwa, msg=f"gat dropout grad att H={H} C={C}")
+
+
+def test_layers_training_dropout_is_unbiased_and_inference_unaffected():
+    """GCNConv / SAGEConv / GATv2Conv with dropout: training=False equals the dropout-free layer exactly, training=True
+    differs from call to call and averages to it (inverted dropout is unbiased in the linear layers)."""
+    import keras_geometric_b200 as kg
+    rng = np.random.default_rng(3)
+    n, e = 400, 4000
+    ei = rand_graph(rng, n, n, e)
+    x = cuda(rng.standard_normal((n, 16)).astype(np.float32))
+    for make in (lambda: kg.GCNConv(8, dropout_rate=0.5), lambda: kg.SAGEConv(8, aggregator="mean", activation=None,
+                                                                               root_weight=False, dropout_rate=0.5)):
+        torch.manual_seed(0)
+        layer = make()
+        base = layer([x, ei], training=False)
+        a, b = layer([x, ei], training=True), layer([x, ei], training=True)
+        assert not torch.equal(a, b) and not torch.equal(a, base)
+        avg = torch.stack([layer([x, ei], training=True) for _ in range(400)]).mean(0)
+        err = (avg - base).abs().max() / base.abs().max()
+        assert float(err) < 0.25, float(err)
+    gat = kg.GATv2Conv(8, heads=2, dropout=0.5)
+    base = gat([x, ei], training=False)
+    a = gat([x, ei], training=True)
+    assert tuple(a.shape) == tuple(base.shape) and not torch.equal(a, base)
+    wide = kg.GATv2Conv(516, heads=1)           # per-head width beyond the fused layout: per-edge path, still correct
+    o = wide([x, ei])
+    w_, a_, b_ = (t.detach().cpu() for t in (wide.linear_transform.kernel, wide.att, wide.bias))
+    close(o, ref.gatv2_conv(x.cpu(), torch.from_numpy(ei), w_, a_, b_, heads=1), msg="gat wide head")
+
+
 # ---------------------------------------------------------------------------------------- K8
 @pytest.mark.parametrize("M,K,N", [(1, 4, 4), (300, 100, 256), (5000, 256, 48), (20001, 48, 256), (70000, 64, 64),
                                    (513, 12, 7), (1000, 1433, 16), (128, 32, 64), (40000, 260, 132), (9999, 512, 300),

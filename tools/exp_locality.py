@@ -46,3 +46,15 @@ for name, order in (("degree_descending", torch.argsort(deg, descending=True, st
         o2, _ = ops.gather_reduce_raw(x2, g2.csr, _lib.OP_MEAN)
         res["max_abs_diff_vs_natural"] = float((o2 - o1[order]).abs().max())
 print(json.dumps(res))
+
+# ---- per-load L2 hints: hot rows (top-K by reference count) evict_last, the rest evict_first ----------------------
+hint = {}
+g = GraphStructure(ei, n, n, 0)
+g.csc
+for Fh in (256, 100, 48):
+    xx = torch.randn((n, Fh), device=dev, generator=gen)
+    for mb in ("0", "32", "64", "96"):
+        os.environ["KGB200_HOT_MB"] = mb
+        g.csr._hot.clear()
+        hint[f"F{Fh}_hot{mb}MB"] = round(timed(g, xx), 3)
+print(json.dumps({"l2_hints_mean_fwd_ms": hint}))
