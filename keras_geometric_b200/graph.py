@@ -75,8 +75,11 @@ class Csr:
     def col_hot(self, F: int):
         """Copy of ``col`` with bit 31 set on the K most frequently referenced rows, K = budget / row bytes
         (KGB200_HOT_MB of the 126 MB L2; default 0 = off), for kgb_gather_reduce's L2 eviction hints.  On a power-law
-        graph 3 % of the rows carry > 60 % of the references; measured on C4 the hints gain 3 % at F = 256 and lose
-        6-19 % for narrower rows, so they are opt-in.  None when off or when the whole matrix fits in the L2."""
+        graph 3 % of the rows carry > 60 % of the references.  Measured on C4 (mean gather, tools/exp_locality.py):
+        F = 256 6.08 -> 5.71 / 5.78 ms (32 / 64 MB), F = 100 3.05 -> 2.91 / 2.81 ms (64 / 96 MB), F = 48 2.07 ->
+        2.16 ms (a loss).  The best set depends on F and tagging costs ~1 ms per (structure, set), which the
+        end-to-end path (a fresh structure per step) would pay every step for a 1.5 % shorter step - so it is opt-in.
+        None when off or when the whole matrix fits in the L2 anyway."""
         budget = int(os.environ.get("KGB200_HOT_MB", "0")) << 20
         row_bytes = 4 * int(F)
         if budget <= 0 or self.nnz < (1 << 20) or self.n_cols * row_bytes <= (96 << 20):
