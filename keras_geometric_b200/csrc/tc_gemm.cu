@@ -23,7 +23,12 @@ namespace kgb {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;  // 32 fp32 = 128 bytes = one swizzle row
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 320;   // tc_dw_kernel: TMA, MMA, 4 transform, 4 epilogue warps
+#ifndef KGB_TC_NT
+#define KGB_TC_NT 4
+#endif
+constexpr int TC_NT = KGB_TC_NT;                         // transform (tf32 split) warps of the forward kernels
+constexpr int TC_GEMM_THREADS = 64 + 32 * TC_NT + 128;   // TMA, MMA, TC_NT transform, 4 epilogue warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -122,7 +127,11 @@ struct TcParams {
 // (transpose) -> (+C, +bias, ReLU) -> global.  Each thread holds 32 consecutive columns of ITS row; storing that
 // directly would touch 32 different rows per instruction, so the chunk goes through a padded shared tile and every
 // global access covers whole 128-byte row segments (4 rows x 128 B per warp instruction).
-// (Software-pipelining the TMEM reads over two register sets was measured slower: 168 registers, 0.70 -> 0.83 ms.)
+// (Software-pipelining the TMEM reads over two register sets was measured slower: 168 registers, 0.70 -> 0.83 ms.
+//  Storing each thread's 128 contiguous bytes straight from registers, without the shared-memory transpose, was also
+//  measured slower: 256->256 1.59 -> 1.89 ms, and 5.4 ms with an addend - its row-per-thread loads serialise.
+//  Eight instead of four transform warps change nothing (1.59 -> 1.60 ms): the split is not throughput-limited, it
+//  lengthens the TMA -> split -> MMA chain that three 64 KB stages have to cover.)
 template <int BN, int EPI_LD>
 __device__ __forceinline__ void tc_epilogue_tile(uint32_t taddr, float* stg, int lane, int64_t tile_row0, int M, int N,
                                                  const float* C, int64_t ldc, const float* bias, int relu, float* D,
@@ -184,7 +193,7 @@ struct TcCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                const TcParams p) {
@@ -207,7 +216,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(lo_rdy + s, 4);   // one arrival per transform warp
+      mbar_init(lo_rdy + s, TC_NT);   // one arrival per transform warp
       mbar_init(empty + s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -280,9 +289,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         umma_commit(tfull + b);    // accumulator ready for the epilogue
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + TC_NT) {
     // ===== transform warps: A -> (A_hi, A_lo) tf32 split (element-wise, so the swizzled layout is preserved) =====
-    const int t = threadIdx.x - 64;  // 0..127
+    const int t = threadIdx.x - 64;  // 0 .. 32 * TC_NT - 1
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
@@ -292,15 +301,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float4* src = reinterpret_cast<float4*>(sA(s));
         float4* dst = reinterpret_cast<float4*>(sAlo(s));
 #pragma unroll
-        for (int i = 0; i < Cfg::A_BYTES / 16 / 128; ++i) {
-          const float4 v = src[t + i * 128];
+        for (int i = 0; i < Cfg::A_BYTES / 16 / (32 * TC_NT); ++i) {
+          const float4 v = src[t + i * (32 * TC_NT)];
           float4 h, r;
           split_tf32(v.x, h.x, r.x);
           split_tf32(v.y, h.y, r.y);
           split_tf32(v.z, h.z, r.z);
           split_tf32(v.w, h.w, r.w);
-          src[t + i * 128] = h;   // the TMA tile becomes the (rounded) high operand in place
-          dst[t + i * 128] = r;
+          src[t + i * (32 * TC_NT)] = h;   // the TMA tile becomes the (rounded) high operand in place
+          dst[t + i * (32 * TC_NT)] = r;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
         __syncwarp();
@@ -386,7 +395,7 @@ struct Tc2Cfg {
 };
 
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_GEMM_THREADS, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                 const TcParams p) {
@@ -412,7 +421,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(ready + s, 8);
+      mbar_init(ready + s, 2 * TC_NT);
       mbar_init(empty + s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -483,7 +492,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         umma_commit2(tfull + b);
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + TC_NT) {
     const int t = threadIdx.x - 64;
     uint32_t it = 0;
     for (int pair = pair0; pair < n_pairs; pair += pair_stride) {
@@ -494,15 +503,15 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         float4* src = reinterpret_cast<float4*>(sA(s));
         float4* dst = reinterpret_cast<float4*>(sAlo(s));
 #pragma unroll
-        for (int i = 0; i < Cfg::A_BYTES / 16 / 128; ++i) {
-          const float4 v = src[t + i * 128];
+        for (int i = 0; i < Cfg::A_BYTES / 16 / (32 * TC_NT); ++i) {
+          const float4 v = src[t + i * (32 * TC_NT)];
           float4 h, r;
           split_tf32(v.x, h.x, r.x);
           split_tf32(v.y, h.y, r.y);
           split_tf32(v.z, h.z, r.z);
           split_tf32(v.w, h.w, r.w);
-          src[t + i * 128] = h;
-          dst[t + i * 128] = r;
+          src[t + i * (32 * TC_NT)] = h;
+          dst[t + i * (32 * TC_NT)] = r;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -818,7 +827,7 @@ static int tc_launch(int device, const CUtensorMap& ma, const CUtensorMap& ma2, 
   }
   int grid = sm_count(device);
   if (grid > p.n_tiles) grid = p.n_tiles;
-  tc_gemm_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, ma2, mh, ml, p);
+  tc_gemm_kernel<BN><<<grid, TC_GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, ma2, mh, ml, p);
   KGB_CHECK_LAUNCH();
   return KGB_OK;
 }
@@ -833,7 +842,7 @@ static int tc2_launch(int device, const CUtensorMap& ma, const CUtensorMap& ma2,
     KGB_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(sm_count(device) / 2 * 2);
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(TC_GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     int n = 0;
     KGB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, tc_gemm2_kernel<BN>, &cfg));  // co-resident CTA pairs
@@ -843,7 +852,7 @@ static int tc2_launch(int device, const CUtensorMap& ma, const CUtensorMap& ma2,
   if (resident <= 0) return KGB_ERR_UNSUPPORTED;
   int pairs = (p.n_tiles + 1) / 2;
   if (pairs > resident) pairs = resident;
-  tc_gemm2_kernel<BN><<<2 * pairs, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, ma2, mh, ml, p);
+  tc_gemm2_kernel<BN><<<2 * pairs, TC_GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, ma2, mh, ml, p);
   KGB_CHECK_LAUNCH();
   return KGB_OK;
 }
