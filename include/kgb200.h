@@ -325,8 +325,19 @@ int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float*
                       const float* hdst, int64_t n_src, int64_t n_dst, int32_t H, int32_t C,
                       const float* att, float slope, const int64_t* rowptr, const int32_t* col,
                       const float* rowmax, const float* rowden, const float* bias,
-                      float* g_hdst, float* r, float* g_att_part, int32_t n_parts,
+                      float* g_hdst, float* r, float* g_att_part, int32_t n_parts, float* rec,
                       const kgb_gat_dropout* drop, const kgb_hub_table* hubs, kgb_stream_t stream);
+/* Per-edge records (optional, `rec` above: [nnz, kgb_gatv2_rec_floats(H, C)] floats, one row per CSR slot, contents
+ * arbitrary on entry): the per-target pass stores alpha_e * dropout_e and the logit gradient ds_e per head plus the
+ * sign bits of z = h_i + h_j, and kgb_gatv2_bwd_src_rec computes the per-source gradient from them with ONE row
+ * gather per edge (g_i) - no h rows, no logits, no exp - instead of kgb_gatv2_bwd_src's two gathers and three scalar
+ * lookups.  slot_map[k'] = CSR slot of the edge in slot k' of the transposed structure.  kgb_gatv2_rec_floats
+ * returns 0 for shapes without this path (more than one lane group per row: H * C / 4 > 32). */
+int32_t kgb_gatv2_rec_floats(int32_t H, int32_t C);
+int kgb_gatv2_bwd_src_rec(int device, const float* g, int64_t n_src, int64_t n_dst, int32_t H, int32_t C,
+                          const float* att, float slope, const int64_t* colptr, const int32_t* row,
+                          const int32_t* slot_map, const float* rec, const float* addend, float* g_hsrc,
+                          const kgb_hub_table* hubs, kgb_stream_t stream);
 /* Backward, pass 2 over the transposed structure (per source): g_hsrc[j] (written) = per-source gradient
  * (+ addend[j], optional [n_src, H*C]: on a square graph the per-target part g_hdst, saving a pass). */
 int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float* hdst,

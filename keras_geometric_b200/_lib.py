@@ -114,8 +114,11 @@ SIGNATURES = {
     "kgb_gatv2_bwd_parts": (c_int, [c_int, c_int64, c_int32, c_int32]),
     "kgb_gatv2_bwd_dst": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
                                   c_int32, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_void_p, c_int32, POINTER(GatDropout), POINTER(HubTable),
-                                  c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_int32, c_void_p, POINTER(GatDropout),
+                                  POINTER(HubTable), c_void_p]),
+    "kgb_gatv2_rec_floats": (c_int32, [c_int32, c_int32]),
+    "kgb_gatv2_bwd_src_rec": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_float, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(HubTable), c_void_p]),
     "kgb_gatv2_bwd_src": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
                                   c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, POINTER(GatDropout), POINTER(HubTable), c_void_p]),

@@ -45,6 +45,14 @@ struct GatP {
   // attention dropout (layers/gatv2_conv.py:252-253), fused: alpha of (edge, head) survives when Philox(edge id,
   // head) >= thr and is scaled by 1 / (1 - p); edge_id[k] = original edge id of slot k of the walked structure
   const int32_t* edge_id; uint32_t drop_thr; float drop_scale; uint32_t seed_lo, seed_hi;
+  // per-edge records of the backward (one row of rec_ld floats per CSR slot, written by the per-target pass, read by
+  // the per-source pass through slot_map[transposed slot] = CSR slot):
+  //   [0, H)   alpha_e * dropout_e            (the message weight)
+  //   [H, 2H)  ds_e = alpha_e (d_e <g_i, h_j> - r_i)   (gradient of the logit)
+  //   [2H, ..) sign bits of z = h_i + h_j, bit (e * G + lane) for element e of the group's lane `lane`
+  // With them the per-source pass needs neither h_i nor the logits: one row gather (g_i) instead of two plus three
+  // scalar lookups, no dot products, no exp.  Shapes with one lane group per row (CC == 1, all heads in the group).
+  float* rec; int rec_ld; const int32_t* slot_map;
 };
 
 // dropout factor of (edge, head): 1 / (1 - p) or 0; 1 when dropout is off
@@ -407,7 +415,8 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
           }
         const float s = head_sum<LPH>(sp, L.gmask);
         float da = head_sum<LPH>(dp, L.gmask);
-        if (drop) da *= gat_drop(p, (uint32_t)__shfl_sync(L.gmask, mye, j + u, G), L.head);   // d out / d alpha
+        const float dfac = drop ? gat_drop(p, (uint32_t)__shfl_sync(L.gmask, mye, j + u, G), L.head) : 1.f;
+        da *= dfac;   // d out / d alpha
         if ((j + u) < cnt) {
           const float alpha = expf(s - m) * dinv;
           const float ds = alpha * (da - r);
@@ -420,6 +429,29 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
               ghi[cc][e] += ds * L.a[cc][e] * (z > 0.f ? 1.f : p.slope);
               ga[cc][e] = fmaf(ds, lz, ga[cc][e]);
             }
+          if constexpr (CC == 1) {
+            if (p.rec) {   // per-edge record for the per-source pass (group-uniform branch)
+              constexpr int NW = (VEC * G + 31) / 32;
+              float* rrow = p.rec + (k + j + u) * (int64_t)p.rec_ld;
+              if (L.head < p.H && (L.gl % LPH) == 0) {
+                rrow[L.head] = alpha * dfac;
+                rrow[p.H + L.head] = ds;
+              }
+              const int gshift = ((threadIdx.x & 31) / G) * G;
+              unsigned wbits[NW];
+#pragma unroll
+              for (int w = 0; w < NW; ++w) wbits[w] = 0u;
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) {
+                unsigned b = __ballot_sync(L.gmask, L.on[0] && (hi[0][e] + v[u][0][e]) > 0.f) >> gshift;
+                if (G < 32) b &= (1u << G) - 1u;
+                wbits[(e * G) / 32] |= b << ((e * G) % 32);   // G divides 32: a ballot never straddles two words
+              }
+#pragma unroll
+              for (int w = 0; w < NW; ++w)
+                if (L.gl == w) reinterpret_cast<unsigned*>(rrow + 2 * p.H)[w] = wbits[w];
+            }
+          }
         }
       }
     }
@@ -614,6 +646,95 @@ __global__ void __launch_bounds__(256, KGB_GAT_MINB_SRC) gatv2_bwd_src_kernel(co
   gat_queue_reset(p);
 }
 
+// per-source pass from the per-edge records: g_hsrc[j] = sum over out-edges (alpha d) g_i + ds a lrelu'(z)
+template <int VEC, int LPH, int CC, int HPG>
+__device__ __forceinline__ void gat_bwd_src_rec_range(const GatP& p, const LaneCtx<VEC, LPH, CC, HPG>& L, int64_t k0,
+                                                      int64_t k1, float (&ghj)[CC][VEC]) {
+  constexpr int G = LPH * HPG;
+#ifndef KGB_GAT_U_SRC_REC
+#define KGB_GAT_U_SRC_REC 8
+#endif
+  constexpr int U = (G < KGB_GAT_U_SRC_REC) ? G : KGB_GAT_U_SRC_REC;
+  const int HC = p.H * p.C;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) ghj[0][e] = 0.f;
+  const int hd = L.head < p.H ? L.head : 0;
+  int64_t k = k0;
+  int32_t myc = 0, mys = 0;
+  if (k + L.gl < k1) {
+    myc = __ldg(p.col + k + L.gl);
+    mys = __ldg(p.slot_map + k + L.gl);
+  }
+  while (k < k1) {
+    const int64_t rem = k1 - k;
+    const int cnt = rem < G ? (int)rem : G;
+    const int64_t kn = k + G;
+    int32_t nc = 0, ns = 0;
+    if (kn + L.gl < k1) {
+      nc = __ldg(p.col + kn + L.gl);
+      ns = __ldg(p.slot_map + kn + L.gl);
+    }
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += U) {
+      float gi[U][VEC], ad[U], ds[U];
+      unsigned sb[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = __shfl_sync(L.gmask, myc, j + u, G);       // slots past cnt carry row / slot 0: loaded, unused
+        const float* rrow = p.rec + (int64_t)__shfl_sync(L.gmask, mys, j + u, G) * p.rec_ld;
+        ld_vec<VEC>(p.g + i * HC + L.off[0], gi[u]);
+        ad[u] = __ldg(rrow + hd);
+        ds[u] = __ldg(rrow + p.H + hd);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          sb[u][e] = (__ldg(reinterpret_cast<const unsigned*>(rrow + 2 * p.H) + (e * G) / 32) >> ((e * G) % 32 + L.gl)) & 1u;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if ((j + u) < cnt) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e)
+            ghj[0][e] += ds[u] * L.a[0][e] * (sb[u][e] ? 1.f : p.slope) + ad[u] * gi[u][e];
+        }
+      }
+    }
+    myc = nc;
+    mys = ns;
+    k = kn;
+  }
+}
+
+template <int VEC, int LPH, int CC, int HPG>
+__global__ void __launch_bounds__(256, 4) gatv2_bwd_src_rec_kernel(const GatP p) {
+  using Ctx = LaneCtx<VEC, LPH, CC, HPG>;
+  constexpr int G = Ctx::G;
+  if constexpr (CC == 1) {
+    Ctx L;
+    L.init(p);
+    const int HC = p.H * p.C;
+    gat_schedule<G>(
+        p,
+        [&](int64_t t, int64_t row, int64_t k0, int64_t k1, bool) {
+          float ghj[CC][VEC];
+          gat_bwd_src_rec_range<VEC, LPH, CC, HPG>(p, L, k0, k1, ghj);
+          if (L.on[0]) st_vec<VEC>(p.partial + t * HC + L.off[0], ghj[0]);
+        },
+        [&](int64_t row, int64_t rs, int64_t re) {
+          float ghj[CC][VEC];
+          gat_bwd_src_rec_range<VEC, LPH, CC, HPG>(p, L, rs, re, ghj);
+          if (!L.on[0]) return;
+          if (p.addend) {
+            float adv[VEC];
+            ld_vec<VEC>(p.addend + row * HC + L.off[0], adv);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) ghj[0][e] += adv[e];
+          }
+          st_vec<VEC>(p.g_hsrc + row * HC + L.off[0], ghj[0]);
+        });
+    gat_queue_reset(p);
+  }
+}
+
 // hub rows of either backward pass: out[row,:] = sum over the row's chunks (chunk order) of partial[c,:]
 __global__ void __launch_bounds__(256) gat_sum_finish_kernel(const GatP p, float* __restrict__ out) {
   const int HC = p.H * p.C;
@@ -655,13 +776,14 @@ static bool gat_shape(int H, int C, bool can4, GatShape* s) {
   return true;
 }
 
-enum { GAT_FWD = 0, GAT_BWD_DST = 1, GAT_BWD_SRC = 2, GAT_FWD_FINISH = 3 };
+enum { GAT_FWD = 0, GAT_BWD_DST = 1, GAT_BWD_SRC = 2, GAT_FWD_FINISH = 3, GAT_BWD_SRC_REC = 4 };
 
 template <int VEC, int LPH, int CC, int HPG>
 static void gat_launch(int which, dim3 grid, cudaStream_t st, const GatP& p) {
   if (which == GAT_FWD) gatv2_fwd_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
   else if (which == GAT_FWD_FINISH) gatv2_fwd_finish_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
   else if (which == GAT_BWD_DST) gatv2_bwd_dst_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
+  else if (which == GAT_BWD_SRC_REC) gatv2_bwd_src_rec_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
   else gatv2_bwd_src_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
 }
 
@@ -799,7 +921,7 @@ int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float*
                       int64_t n_src, int64_t n_dst, int32_t H, int32_t C, const float* att, float slope,
                       const int64_t* rowptr, const int32_t* col, const float* rowmax, const float* rowden,
                       const float* bias, float* g_hdst, float* r, float* g_att_part, int32_t n_parts,
-                      const kgb_gat_dropout* drop, const kgb_hub_table* hubs, kgb_stream_t stream) {
+                      float* rec, const kgb_gat_dropout* drop, const kgb_hub_table* hubs, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(H > 0 && C > 0 && n_dst >= 0 && n_parts > 0, "bad sizes");
   KGB_REQUIRE(g_att_part, "g_att_part is NULL");
@@ -812,9 +934,43 @@ int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float*
   p.rowptr = rowptr; p.col = col; p.rowmax = const_cast<float*>(rowmax); p.rowden = const_cast<float*>(rowden);
   p.g = g; p.agg = agg; p.bias = bias; p.g_hdst = g_hdst; p.r_out = r; p.g_att_part = g_att_part;
   p.n_rows = n_dst;
+  if (rec) {
+    p.rec_ld = kgb_gatv2_rec_floats(H, C);
+    KGB_REQUIRE(p.rec_ld > 0 && aligned16(rec), "per-edge records are not available for H=%d C=%d", H, C);
+    KGB_REQUIRE(gat_can4(p) == (C % 4 == 0), "per-edge records need 16-byte aligned operands");
+    p.rec = rec;
+  }
   if (gat_set_dropout(p, drop) != KGB_OK) return KGB_ERR_INVALID;
   gat_set_hubs(p, hubs);
   return gat_run(device, GAT_BWD_DST, p, st, 4, n_parts, g_hdst);
+}
+
+int32_t kgb_gatv2_rec_floats(int32_t H, int32_t C) {
+  if (H <= 0 || C <= 0) return 0;
+  GatShape s;
+  if (!gat_shape(H, C, C % 4 == 0, &s) || s.cc != 1 || s.nhb != 1) return 0;
+  const int G = s.lph * s.hpg;
+  const int nw = (s.vec * G + 31) / 32;
+  return (2 * H + nw + 3) / 4 * 4;
+}
+
+int kgb_gatv2_bwd_src_rec(int device, const float* g, int64_t n_src, int64_t n_dst, int32_t H, int32_t C,
+                          const float* att, float slope, const int64_t* colptr, const int32_t* row,
+                          const int32_t* slot_map, const float* rec, const float* addend, float* g_hsrc,
+                          const kgb_hub_table* hubs, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(H > 0 && C > 0 && n_src >= 0, "bad sizes");
+  if (n_src == 0) return KGB_OK;
+  KGB_REQUIRE(g && att && colptr && slot_map && rec && g_hsrc, "NULL pointer");
+  GatP p = {};
+  p.n_src = n_src; p.n_dst = n_dst; p.H = H; p.C = C; p.att = att; p.slope = slope;
+  p.rowptr = colptr; p.col = row; p.g = g; p.addend = addend; p.g_hsrc = g_hsrc;
+  p.rec = const_cast<float*>(rec); p.slot_map = slot_map; p.rec_ld = kgb_gatv2_rec_floats(H, C);
+  p.n_rows = n_src;
+  KGB_REQUIRE(p.rec_ld > 0 && aligned16(rec), "per-edge records are not available for H=%d C=%d", H, C);
+  gat_set_hubs(p, hubs);
+  KGB_REQUIRE(gat_can4(p) == (C % 4 == 0), "per-edge records need 16-byte aligned operands");
+  return gat_run(device, GAT_BWD_SRC_REC, p, (cudaStream_t)stream, 4, 0, g_hsrc);
 }
 
 int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float* hdst, int64_t n_src,

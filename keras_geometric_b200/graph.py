@@ -202,6 +202,14 @@ class GraphStructure:
             self._csc = build_csr(self.edge_index, self.n_src, self.n_dst, self.n_loops, by_source=True)
         return self._csc
 
+    def csc_to_csr(self) -> torch.Tensor:
+        """slot_map[k'] = CSR slot of the edge stored in slot k' of the CSC (int32 [nnz]); built once per graph."""
+        if getattr(self, "_c2r", None) is None:
+            inv = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+            inv[self.csr.perm.long()] = torch.arange(self.nnz, dtype=torch.int32, device=self.device)
+            self._c2r = inv[self.csc.perm.long()].contiguous()
+        return self._c2r
+
     def gcn_norm(self):
         """(dis [n_dst], w_coo [nnz]) of utils/main.py:20-33 via kgb_gcn_norm."""
         if self._gcn is None:

@@ -6,6 +6,7 @@ CUDA stream with borrowed ``data_ptr()``s.  No function has a CPU or eager-PyTor
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 from torch.autograd.function import once_differentiable
@@ -560,11 +561,15 @@ class _GatV2(torch.autograd.Function):
         g_hdst = torch.empty_like(h_dst)
         r = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
         part = torch.empty((n_parts, H * C), dtype=torch.float32, device=dev)
+        # per-edge records (alpha * dropout, d logit, sign bits of z): the per-source pass then gathers one row per
+        # edge instead of two and recomputes nothing.  Shapes with one lane group per row, both h operands aligned.
+        rec_ld = int(lib.kgb_gatv2_rec_floats(H, C)) if (os.environ.get("KGB200_GAT_REC", "1") != "0") else 0
+        rec = torch.empty((csr.nnz, rec_ld), dtype=torch.float32, device=dev) if (rec_ld > 0 and csr.nnz > 0) else None
         with _prof(f"gatv2_bwd_dst_H{H}_C{C}", gat_bytes(csr.nnz, n_dst, H, C), dev):
             _lib.check(lib.kgb_gatv2_bwd_dst(dev.index, g.data_ptr(), out.data_ptr(), h_src.data_ptr(), h_dst.data_ptr(),
                                              n_src, n_dst, H, C, att_c.data_ptr(), ctx.slope, csr.rowptr.data_ptr(),
                                              csr.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(), _ptr(bias_c),
-                                             g_hdst.data_ptr(), r.data_ptr(), part.data_ptr(), n_parts,
+                                             g_hdst.data_ptr(), r.data_ptr(), part.data_ptr(), n_parts, _ptr(rec),
                                              _gat_drop(ctx.drop, csr),
                                              ctypes.byref(csr.hub_table(lib.kgb_gatv2_partial_bytes(csr.n_chunks, H, C), st, gat=True)),
                                              st), "kgb_gatv2_bwd_dst")
@@ -572,6 +577,18 @@ class _GatV2(torch.autograd.Function):
         _lib.check(lib.kgb_reduce_parts(dev.index, part.data_ptr(), n_parts, H * C, g_att.data_ptr(), st),
                    "kgb_reduce_parts")
         g_hsrc = torch.empty_like(h_src)
+        if rec is not None:
+            with _prof(f"gatv2_bwd_src_H{H}_C{C}", gat_bytes(csc.nnz, n_src, H, C), dev):
+                _lib.check(lib.kgb_gatv2_bwd_src_rec(dev.index, g.data_ptr(), n_src, n_dst, H, C, att_c.data_ptr(),
+                                                     ctx.slope, csc.rowptr.data_ptr(), csc.col.data_ptr(),
+                                                     graph.csc_to_csr().data_ptr(), rec.data_ptr(),
+                                                     g_hdst.data_ptr() if ctx.same else None, g_hsrc.data_ptr(),
+                                                     ctypes.byref(csc.hub_table(lib.kgb_gatv2_partial_bytes(csc.n_chunks, H, C), st, gat=True)),
+                                                     st), "kgb_gatv2_bwd_src_rec")
+            g_bias = relu_bwd_colsum(g, None)[1] if ctx.has_bias else None
+            if ctx.same:
+                return g_hsrc, None, g_att, g_bias, None, None, None, None, None, None
+            return g_hsrc, g_hdst, g_att, g_bias, None, None, None, None, None, None
         with _prof(f"gatv2_bwd_src_H{H}_C{C}", gat_bytes(csc.nnz, n_src, H, C), dev):
             _lib.check(lib.kgb_gatv2_bwd_src(dev.index, g.data_ptr(), h_src.data_ptr(), h_dst.data_ptr(), n_src, n_dst,
                                              H, C, att_c.data_ptr(), ctx.slope, csc.rowptr.data_ptr(),
