@@ -118,7 +118,7 @@ def build_model(feats, hidden, classes, seed=0):
 def run_ours(args):
     import keras_geometric_b200  # noqa: F401
     from keras_geometric_b200 import _lib, ops
-    from keras_geometric_b200.graph import clear_cache, get_graph
+    from keras_geometric_b200.graph import clear_cache
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -220,38 +220,53 @@ def run_ours(args):
             roofline["note"] = "no ncu traffic figure for this kernel: frac = algorithmic"
 
     # ---- end-to-end through the public API with host buffers ----------------------------------------
+    # Every step gets a FRESH copy of its inputs from pinned host memory (edge_index, then x) and rebuilds the CSR +
+    # CSC of that edge list; the loss is read back to the host.  The copies are double-buffered like a data loader's
+    # prefetch: while step i computes, the copy stream moves step i+1's inputs into the other device buffer.  All K
+    # copies (including the first, which nothing hides) and all K steps are inside the timed region.
     x_host = x.cpu().pin_memory()
     ei_host = ei.cpu().pin_memory()
-    e2e_steps = max(2, min(args.steps, 5))
-
+    e2e_steps = max(2, min(args.steps, 10))
     copy_stream = torch.cuda.Stream(device=dev)
-    ei_landed = torch.cuda.Event()
+    bufs = [(ei, x), (torch.empty_like(ei), torch.empty_like(x))]   # two resident input slots
+    landed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
-        clear_cache()  # a fresh edge list arrives every step: the CSR/CSC build is inside the timed region
-        cur = torch.cuda.current_stream(dev)
-        eid = ei_host.to(dev, non_blocking=True)
-        ei_landed.record(cur)
-        copy_stream.wait_event(ei_landed)
-        with torch.cuda.stream(copy_stream):  # x follows edge_index over PCIe while the structure is built
-            xd = x_host.to(dev, non_blocking=True)
-        graph = get_graph(eid, n, n, 0)
-        graph.csc  # noqa: B018  (the source-major orientation the backward walks)
-        cur.wait_stream(copy_stream)
-        xd.record_stream(cur)
-        return float(step(xd, eid).item())  # device -> host read of the loss
+    def issue_copy(slot):
+        # slot was last read by step i-2, whose loss the host has already read back: free to overwrite
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(copy_stream):
+            bufs[slot][0].copy_(ei_host, non_blocking=True)
+            bufs[slot][1].copy_(x_host, non_blocking=True)
+            landed[slot].record(copy_stream)
 
-    e2e_step()
+    def e2e_run(k):
+        issue_copy(0)
+        last = 0.0
+        for i in range(k):
+            slot = i & 1
+            if i + 1 < k:
+                issue_copy(slot ^ 1)               # prefetch the next step's inputs behind this step's compute
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(landed[slot])
+            clear_cache()                          # a fresh edge list every step: CSR + CSC builds are timed
+            eid, xd = bufs[slot]
+            # the layers build the structure themselves: CSR at the first layer's forward, CSC at the first backward
+            last = float(step(xd, eid).item())     # device -> host read of the loss ends the step
+        return last
+
+    e2e_run(2)
     torch.cuda.synchronize()
     w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    e2e_run(e2e_steps)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - w0) * 1e3 / e2e_steps
-    e2e = {"value": n_layers * e / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS", "ms_per_step": e2e_ms,
+    e2e = {"value": n_layers * e / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS", "ms_per_step": e2e_ms, "steps": e2e_steps,
            "h2d_bytes_per_step": x_host.numel() * 4 + ei_host.numel() * 4, "d2h_bytes_per_step": 4,
-           "includes": "H2D of edge_index then x from pinned memory (x overlaps the CSR+CSC build), fwd+bwd+SGD; only "
-                       "the 4-byte loss returns to the host (a training step - the [N,47] logits stay on the device)"}
+           "includes": "per step: H2D of edge_index and x from pinned memory (double-buffered: step i+1's copy runs on "
+                       "a copy stream behind step i's compute; the first copy is exposed and timed), CSR + CSC build "
+                       "of the freshly copied edge list, fwd+bwd+SGD, and the 4-byte loss read back to the host (a "
+                       "training step - the [N,47] logits stay on the device)"}
+    bufs = None
 
     out = {
         "metric": "aggregated edges/sec per layer fwd+bwd", "value": value, "unit": "GTEPS", "n_gpus": 1,

@@ -1067,6 +1067,9 @@ static Shape pick_shape(int F, bool can_vec4) {
   Shape s;
   s.vec = (can_vec4 && F % 4 == 0) ? 4 : 1;
   const int nv = F / s.vec;
+  // (Rows of 9..32 vectors on half as many lanes with two vectors per lane - half the index / address work per loaded
+  //  byte, more groups per warp - were measured slower on C4: F = 48 mean 2.04 -> 2.63 ms, F = 100 2.75 -> 3.78 ms;
+  //  the extra groups per warp diverge on the power-law row lengths.)
   if (nv <= 32) {
     s.g = pow2_ceil(nv);
     s.nch = 1;

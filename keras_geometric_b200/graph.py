@@ -73,15 +73,21 @@ class Csr:
         return order
 
     def col_hot(self, F: int):
-        """Copy of ``col`` with bit 31 set on the K most frequently referenced rows, K = budget / row bytes
-        (KGB200_HOT_MB of the 126 MB L2; default 0 = off), for kgb_gather_reduce's L2 eviction hints.  On a power-law
-        graph 3 % of the rows carry > 60 % of the references.  Measured on C4 (mean gather, tools/exp_locality.py):
-        F = 256 6.08 -> 5.71 / 5.78 ms (32 / 64 MB), F = 100 3.05 -> 2.91 / 2.81 ms (64 / 96 MB), F = 48 2.07 ->
-        2.16 ms (a loss).  The best set depends on F and tagging costs ~1 ms per (structure, set), which the
-        end-to-end path (a fresh structure per step) would pay every step for a 1.5 % shorter step - so it is opt-in.
-        None when off or when the whole matrix fits in the L2 anyway."""
-        budget = int(os.environ.get("KGB200_HOT_MB", "0")) << 20
+        """Copy of ``col`` with bit 31 set on the K most frequently referenced rows, K = budget / row bytes, for
+        kgb_gather_reduce's L2 eviction hints (hot rows evict_last, one-touch rows evict_first).  On a power-law
+        graph 3 % of the rows carry > 60 % of the references.  Measured on C4 (mean gather forward / transposed
+        backward, tools/exp_kernels.py mean): F = 256 6.07 / 6.37 -> 5.71 / 5.92 ms with a 32 MB set; F = 100 2.75 ->
+        2.77 ms (64 MB set, no gain), F = 48 a loss.  Tagging costs ~1 ms per (structure, set), so in the default mode
+        (KGB200_HOT_MB unset or "auto") a set is only built for rows of >= 800 bytes and only at the THIRD use of the
+        structure at that width - a static training graph pays it once, a structure that lives for one step (fresh
+        edge list every step) never does.  KGB200_HOT_MB=<n> forces an n MB set from the first use at every width,
+        0 turns the hints off.  None when off, not yet due, or when the whole matrix fits in the L2 anyway."""
         row_bytes = 4 * int(F)
+        mode = os.environ.get("KGB200_HOT_MB", "auto")
+        if mode == "auto":
+            budget = (32 << 20) if row_bytes >= 800 else 0
+        else:
+            budget = int(mode) << 20
         if budget <= 0 or self.nnz < (1 << 20) or self.n_cols * row_bytes <= (96 << 20):
             return None
         K = max(1, budget // row_bytes)
@@ -90,6 +96,11 @@ class Csr:
             return None
         tagged = self._hot.get(K)
         if tagged is None:
+            if mode == "auto":
+                uses = self._hot.get(("uses", K), 0) + 1
+                self._hot[("uses", K)] = uses
+                if uses < 3:
+                    return None
             cnt = torch.bincount(self.col.long(), minlength=self.n_cols)
             thr = torch.topk(cnt, K).values[-1].clamp(min=2)        # rows gathered once gain nothing from residency
             hot = (cnt >= thr)[self.col.long()]
@@ -137,8 +148,25 @@ class Csr:
         return buf
 
 
-def build_csr(edge_index: torch.Tensor, n_seg: int, n_val: int, n_loops: int, by_source: bool) -> Csr:
-    """Run kgb_csr_build (+ hub table).  ``edge_index`` int32 [2,E] contiguous on CUDA."""
+class _PendingCsr:
+    """A structure whose kernels are enqueued but whose hub counts / status the host has not read yet."""
+    __slots__ = ("c", "meta", "keep", "event", "limits", "oob_msg")
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    st = _SIDE_STREAMS.get(dev.index)
+    if st is None:
+        st = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def _launch_csr(edge_index: torch.Tensor, n_seg: int, n_val: int, n_loops: int, by_source: bool,
+                side: "torch.cuda.Stream | None" = None) -> _PendingCsr:
+    """Allocate the outputs on the current stream and enqueue kgb_csr_build + kgb_csr_hubs - on ``side`` when given
+    (it first waits for the current stream, so reused allocator blocks are safe to overwrite)."""
     require_cuda(edge_index, "edge_index")
     assert edge_index.dtype == torch.int32 and edge_index.is_contiguous() and edge_index.dim() == 2
     lib = _lib.load()
@@ -154,27 +182,49 @@ def build_csr(edge_index: torch.Tensor, n_seg: int, n_val: int, n_loops: int, by
     meta = torch.zeros(4, dtype=torch.int32, device=dev)  # [status, n_hubs, n_chunks, -]
     ws_bytes = lib.kgb_csr_build_workspace_bytes(M, n_seg)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    st = _stream(dev)
-    _lib.check(lib.kgb_csr_build(dev.index, edge_index.data_ptr(), E, int(by_source), n_seg, n_val, n_loops,
-                                 c.rowptr.data_ptr(), c.col.data_ptr(), c.perm.data_ptr(), c.deg.data_ptr(),
-                                 meta.data_ptr(), ws.data_ptr(), ws_bytes, st), "kgb_csr_build")
     max_hubs = M // HUB_THRESHOLD + 1
     max_chunks = M // HUB_CHUNK + max_hubs + 1
     hub = torch.empty(3 * max_hubs + max_chunks, dtype=torch.int32, device=dev)
     c.hub_row, c.hub_chunk_base, c.hub_nchunks = hub[:max_hubs], hub[max_hubs:2 * max_hubs], hub[2 * max_hubs:3 * max_hubs]
     c.chunk_hub = hub[3 * max_hubs:]
+    pend = _PendingCsr()
+    pend.c, pend.meta, pend.keep, pend.event, pend.limits = c, meta, [ws, edge_index], None, (max_hubs, max_chunks)
+    pend.oob_msg = (f"edge_index contains node ids outside [0, {n_seg if not by_source else n_val}) / "
+                    f"[0, {n_val if not by_source else n_seg})")
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream(dev))
+        for t in (c.rowptr, c.col, c.perm, c.deg, meta, ws, hub):
+            t.record_stream(side)   # freed blocks are not handed out again before the side stream is done with them
+    st = side.cuda_stream if side is not None else _stream(dev)
+    _lib.check(lib.kgb_csr_build(dev.index, edge_index.data_ptr(), E, int(by_source), n_seg, n_val, n_loops,
+                                 c.rowptr.data_ptr(), c.col.data_ptr(), c.perm.data_ptr(), c.deg.data_ptr(),
+                                 meta.data_ptr(), ws.data_ptr(), ws_bytes, st), "kgb_csr_build")
     _lib.check(lib.kgb_csr_hubs(dev.index, c.rowptr.data_ptr(), n_seg, HUB_THRESHOLD, HUB_CHUNK,
                                 c.hub_row.data_ptr(), c.hub_chunk_base.data_ptr(), c.hub_nchunks.data_ptr(),
                                 c.chunk_hub.data_ptr(), max_hubs, max_chunks, meta[1:].data_ptr(), st),
                "kgb_csr_hubs")
-    status, n_hubs, n_chunks, _ = meta.tolist()  # the one host sync of a structure build
-    del ws
+    if side is not None:
+        pend.event = torch.cuda.Event()
+        pend.event.record(side)
+    return pend
+
+
+def _finish_csr(pend: _PendingCsr) -> Csr:
+    c = pend.c
+    if pend.event is not None:   # built on the side stream: order the consumer's stream behind it
+        torch.cuda.current_stream(c.rowptr.device).wait_event(pend.event)
+    status, n_hubs, n_chunks, _ = pend.meta.tolist()  # the one host sync of a structure build
+    pend.keep = None
     if status & _lib.STATUS_OOB_INDEX:
-        raise IndexError(f"edge_index contains node ids outside [0, {n_seg if not by_source else n_val}) / "
-                         f"[0, {n_val if not by_source else n_seg})")
-    assert n_hubs <= max_hubs and n_chunks <= max_chunks
+        raise IndexError(pend.oob_msg)
+    assert n_hubs <= pend.limits[0] and n_chunks <= pend.limits[1]
     c.n_hubs, c.n_chunks = int(n_hubs), int(n_chunks)
     return c
+
+
+def build_csr(edge_index: torch.Tensor, n_seg: int, n_val: int, n_loops: int, by_source: bool) -> Csr:
+    """Run kgb_csr_build (+ hub table).  ``edge_index`` int32 [2,E] contiguous on CUDA."""
+    return _finish_csr(_launch_csr(edge_index, n_seg, n_val, n_loops, by_source))
 
 
 class GraphStructure:
@@ -194,13 +244,33 @@ class GraphStructure:
         self.device = edge_index.device
         self.csr = build_csr(edge_index, self.n_dst, self.n_src, self.n_loops, by_source=False)
         self._csc = None
+        self._csc_pending = None
         self._gcn = None
 
     @property
     def csc(self) -> Csr:
         if self._csc is None:
-            self._csc = build_csr(self.edge_index, self.n_src, self.n_dst, self.n_loops, by_source=True)
+            if self._csc_pending is not None:
+                pend, self._csc_pending = self._csc_pending, None
+                self._csc = _finish_csr(pend)
+            else:
+                self._csc = build_csr(self.edge_index, self.n_src, self.n_dst, self.n_loops, by_source=True)
         return self._csc
+
+    def prefetch_csc(self) -> None:
+        """Enqueue the build of the source-major orientation on a side stream without waiting for it: called by the
+        forward of every op whose backward walks the CSC, so that on a fresh edge list the second radix sort runs
+        beside the forward pass instead of in front of the backward one.  The host reads the hub counts when ``csc``
+        is first touched.  No-op when the CSC exists, is already on its way, or the graph is small.
+        Opt-in (KGB200_PREFETCH_CSC=1): on the C4 end-to-end step it changed nothing (59.65 vs 59.62 ms) - the
+        persistent gather CTAs fill the register files and the GEMM CTAs the shared memory, so the sort kernels of the
+        side stream only run in the gaps the main stream leaves anyway."""
+        if self._csc is not None or self._csc_pending is not None or self.nnz < (1 << 20):
+            return
+        if os.environ.get("KGB200_PREFETCH_CSC", "0") != "1":
+            return
+        self._csc_pending = _launch_csr(self.edge_index, self.n_src, self.n_dst, self.n_loops, by_source=True,
+                                        side=_side_stream(self.device))
 
     def csc_to_csr(self) -> torch.Tensor:
         """slot_map[k'] = CSR slot of the edge stored in slot k' of the CSC (int32 [nnz]); built once per graph."""

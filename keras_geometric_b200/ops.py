@@ -301,6 +301,8 @@ class _GatherReduce(torch.autograd.Function):
             kw_drop = {}
         x = _f32c(x, "x")
         csr = graph.csr
+        if ctx.needs_input_grad[0] and op not in _lib.MAX_OPS:
+            graph.prefetch_csc()    # the backward walks the other orientation: build it beside the forward pass
         kw = {}
         ctx.weight_kind = None
         if weight is not None:
@@ -528,6 +530,8 @@ class _GatV2(torch.autograd.Function):
         dev = h_src.device
         n_src, n_dst = int(h_src.shape[0]), int(h_dst.shape[0])
         csr = graph.csr
+        if any(ctx.needs_input_grad[:3]):
+            graph.prefetch_csc()    # the per-source backward pass walks the other orientation
         out = torch.empty((n_dst, H * C), dtype=torch.float32, device=dev)
         rowmax = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
         rowden = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
@@ -562,8 +566,11 @@ class _GatV2(torch.autograd.Function):
         r = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
         part = torch.empty((n_parts, H * C), dtype=torch.float32, device=dev)
         # per-edge records (alpha * dropout, d logit, sign bits of z): the per-source pass then gathers one row per
-        # edge instead of two and recomputes nothing.  Shapes with one lane group per row, both h operands aligned.
-        rec_ld = int(lib.kgb_gatv2_rec_floats(H, C)) if (os.environ.get("KGB200_GAT_REC", "1") != "0") else 0
+        # edge instead of two and recomputes nothing.  Measured on C4 (+ self-loops, tools/exp_gat.py): the per-source
+        # pass gets faster (H8C8 8.84 -> 7.32 ms) but writing the records costs the per-target pass more (4.93 ->
+        # 9.98 ms; H1C64 5.76 -> 10.4), so the recomputing path stays the default and this one is opt-in
+        # (KGB200_GAT_REC=1; covered by test_gatv2_record_path).
+        rec_ld = int(lib.kgb_gatv2_rec_floats(H, C)) if (os.environ.get("KGB200_GAT_REC", "0") == "1") else 0
         rec = torch.empty((csr.nnz, rec_ld), dtype=torch.float32, device=dev) if (rec_ld > 0 and csr.nnz > 0) else None
         with _prof(f"gatv2_bwd_dst_H{H}_C{C}", gat_bytes(csr.nnz, n_dst, H, C), dev):
             _lib.check(lib.kgb_gatv2_bwd_dst(dev.index, g.data_ptr(), out.data_ptr(), h_src.data_ptr(), h_dst.data_ptr(),
@@ -839,6 +846,10 @@ class _SageLayer(torch.autograd.Function):
         w_neigh, w_self = _f32c(w_neigh, "w_neigh"), _f32c(w_self, "w_self")
         bias_c = _f32c(bias, "bias").contiguous() if bias is not None else None
         N = int(w_neigh.shape[1])
+        if any(ctx.needs_input_grad):
+            # training: this layer's or a later layer's backward walks the source-major orientation; on a fresh edge
+            # list its build runs on a side stream beside the forward pass (no-op once the structure has it)
+            graph.prefetch_csc()
         agg, _ = gather_reduce_raw(x, graph.csr, op)
         hi, lo = _split_weight_pair(w_neigh, w_self, transpose=True)   # [agg | x] @ [w_neigh ; w_self] in one pass
         out = linear_tc2(agg, x, hi, lo, N, bias=bias_c, relu=relu)

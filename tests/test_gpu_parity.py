@@ -555,6 +555,28 @@ def test_gatv2_kernel_vs_oracle(H, C):
         close(a_, b_, msg=f"gat grad {nm} H={H} C={C}")
 
 
+@pytest.mark.parametrize("H,C", [(8, 8), (1, 64), (4, 32), (2, 7)])
+def test_gatv2_record_path(H, C, monkeypatch):
+    """The opt-in per-edge record backward (KGB200_GAT_REC=1) gives the gradients of the recomputing default."""
+    from keras_geometric_b200 import ops
+    from keras_geometric_b200.graph import GraphStructure
+    rng = np.random.default_rng(H * 31 + C)
+    n, e = 300, 6000
+    ei = rand_graph(rng, n, n, e, hub=700)
+    graph = GraphStructure(cuda(ei), n, n, n)
+    h = cuda((rng.standard_normal((n, H * C)) * 0.7).astype(np.float32))
+    att = cuda((rng.standard_normal((1, H, C)) * 0.5).astype(np.float32))
+    R = cuda(rng.standard_normal((n, H * C)).astype(np.float32))
+    grads = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("KGB200_GAT_REC", flag)
+        hg, ag = h.clone().requires_grad_(True), att.clone().requires_grad_(True)
+        out = ops.gatv2_aggregate(hg, hg, ag, graph, H, C, 0.2, None)
+        grads[flag] = torch.autograd.grad((out * R).sum(), [hg, ag])
+    for a_, b_, nm in zip(grads["1"], grads["0"], ["h", "att"]):
+        close(a_, b_.cpu(), msg=f"gat record path grad {nm} H={H} C={C}")
+
+
 def test_gatv2_bipartite_and_dropout_path():
     from keras_geometric_b200 import GATv2Conv
     rng = np.random.default_rng(3)
@@ -634,6 +656,51 @@ def test_full_size_properties_products_slice():
     (gx,) = torch.autograd.grad((ops.gather_reduce(xr, graph, "sum") * y).sum(), [xr])
     ref_dot = (ops.gather_reduce(x, graph, "sum") * y).sum()
     assert torch.allclose((gx * x).sum(), ref_dot, rtol=1e-4)
+
+
+def test_csc_prefetch_side_stream_and_l2_hints_change_nothing(monkeypatch):
+    """The source-major orientation built on the side stream beside the forward pass (GraphStructure.prefetch_csc) is
+    bit-identical to the one built in line, and neither it nor the L2 eviction hints (armed at the third use of a
+    structure) change a single bit of outputs or gradients."""
+    from keras_geometric_b200 import ops
+    from keras_geometric_b200.graph import GraphStructure
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    n, e, F = 300_000, 3_000_000, 256
+    dst = (torch.rand(e, device="cuda", generator=gen) ** 3 * n).long().clamp_(max=n - 1)
+    src = (torch.rand(e, device="cuda", generator=gen) ** 2 * n).long().clamp_(max=n - 1)
+    ei = torch.stack([src, dst]).to(torch.int32)
+    x = torch.randn((n, F), device="cuda", generator=gen)
+    R = torch.randn((n, F), device="cuda", generator=gen)
+
+    def run(graph, reps=1):
+        outs = []
+        for _ in range(reps):
+            xr = x.clone().requires_grad_(True)
+            out = ops.gather_reduce(xr, graph, "mean")
+            (gx,) = torch.autograd.grad(out, [xr], R)
+            outs.append((out, gx))
+        return outs
+
+    monkeypatch.setenv("KGB200_PREFETCH_CSC", "0")
+    monkeypatch.setenv("KGB200_HOT_MB", "0")
+    g0 = GraphStructure(ei, n, n, 0)
+    (o0, gx0), = run(g0)
+    assert g0._csc_pending is None
+    monkeypatch.setenv("KGB200_PREFETCH_CSC", "1")
+    monkeypatch.setenv("KGB200_HOT_MB", "auto")
+    g1 = GraphStructure(ei, n, n, 0)
+    xr = x.clone().requires_grad_(True)
+    out = ops.gather_reduce(xr, g1, "mean")
+    assert g1._csc_pending is not None and g1._csc is None      # on its way, the host has not waited
+    (gx,) = torch.autograd.grad(out, [xr], R)
+    assert g1._csc_pending is None and g1._csc is not None
+    for name in ("rowptr", "col", "perm", "deg"):
+        assert torch.equal(getattr(g1.csc, name), getattr(g0.csc, name)), name
+    assert (g1.csc.n_hubs, g1.csc.n_chunks) == (g0.csc.n_hubs, g0.csc.n_chunks)
+    assert torch.equal(out, o0) and torch.equal(gx, gx0)
+    for o, g in run(g1, reps=3):                                 # third and later uses run with the tagged columns
+        assert torch.equal(o, o0) and torch.equal(g, gx0)
+    assert any(isinstance(k, int) for k in g1.csr._hot), "hints were never armed"
 
 
 # ------------------------------------------------------------------------------ fused dropout (training paths)

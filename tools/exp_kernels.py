@@ -53,4 +53,20 @@ if "max" in which:
             torch.autograd.grad(o, x, R)
         res.update(collect(fb))
         del x, R
+if "mean" in which:
+    # mean gather forward + transposed backward at the C4 step's widths; run with KGB200_HOT_MB=0/auto to measure the
+    # L2 eviction hints
+    res["hot_mb"] = os.environ.get("KGB200_HOT_MB", "auto")
+    g = GraphStructure(ei, n, n, 0)
+    g.csc
+    for F in (48, 100, 256):
+        x = torch.randn((n, F), device=dev, generator=gen).requires_grad_(True)
+        R = torch.randn((n, F), device=dev, generator=gen)
+
+        def fb():
+            o = ops.gather_reduce(x, g, "mean")
+            torch.autograd.grad(o, x, R)
+        fb()   # third use of the structure at this width arms the L2 hints (auto mode) before anything is timed
+        res.update({k + ("_bwd" if k.endswith("_w") else "_fwd"): v for k, v in collect(fb, reps=5).items()})
+        del x, R
 print(json.dumps(res))
