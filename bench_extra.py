@@ -27,7 +27,7 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _time(fn, reps=5, warm=2):
+def _time(fn, reps=5, warm=3):
     """median CUDA-event time of fn() in ms on the current stream"""
     for _ in range(warm):
         fn()

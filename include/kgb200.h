@@ -316,16 +316,17 @@ int kgb_gatv2_fwd(int device, const float* hsrc, const float* hdst, int64_t n_sr
                   const int64_t* rowptr, const int32_t* col, const float* bias,
                   float* out, float* rowmax, float* rowden, const kgb_gat_dropout* drop,
                   const kgb_hub_table* hubs, kgb_stream_t stream);
-/* Backward, pass 1 over the forward CSR (per target): g_hdst[i] (written), r[i,h] =
- * sum_c g[i,h,c] * agg[i,h,c] (written, workspace [n_dst,H]) and the attention-vector
- * gradient partials g_att_part [n_parts, H*C] (n_parts from kgb_gatv2_bwd_parts()).
+/* Backward, pass 1 over the forward CSR (per target): g_hdst[i] (written), the per-(target, head) record
+ * stat[i,h] = (rowmax, 1 / (rowden + 1e-10), r = sum_c g[i,h,c] * agg[i,h,c], 0) (written, workspace [n_dst,H,4],
+ * 16-byte aligned: the three scalars the per-source pass needs per edge come from ONE 16-byte load) and the
+ * attention-vector gradient partials g_att_part [n_parts, H*C] (n_parts from kgb_gatv2_bwd_parts()).
  * `agg` is the forward output; `bias` (optional) is the vector the forward fused into it (subtracted again). */
 int kgb_gatv2_bwd_parts(int device, int64_t n_dst, int32_t H, int32_t C);
 int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float* hsrc,
                       const float* hdst, int64_t n_src, int64_t n_dst, int32_t H, int32_t C,
                       const float* att, float slope, const int64_t* rowptr, const int32_t* col,
                       const float* rowmax, const float* rowden, const float* bias,
-                      float* g_hdst, float* r, float* g_att_part, int32_t n_parts, float* rec,
+                      float* g_hdst, float* stat, float* g_att_part, int32_t n_parts, float* rec,
                       const kgb_gat_dropout* drop, const kgb_hub_table* hubs, kgb_stream_t stream);
 /* Per-edge records (optional, `rec` above: [nnz, kgb_gatv2_rec_floats(H, C)] floats, one row per CSR slot, contents
  * arbitrary on entry): the per-target pass stores alpha_e * dropout_e and the logit gradient ds_e per head plus the
@@ -339,11 +340,12 @@ int kgb_gatv2_bwd_src_rec(int device, const float* g, int64_t n_src, int64_t n_d
                           const int32_t* slot_map, const float* rec, const float* addend, float* g_hsrc,
                           const kgb_hub_table* hubs, kgb_stream_t stream);
 /* Backward, pass 2 over the transposed structure (per source): g_hsrc[j] (written) = per-source gradient
- * (+ addend[j], optional [n_src, H*C]: on a square graph the per-target part g_hdst, saving a pass). */
+ * (+ addend[j], optional [n_src, H*C]: on a square graph the per-target part g_hdst, saving a pass).
+ * `stat` is the [n_dst,H,4] record array kgb_gatv2_bwd_dst wrote. */
 int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float* hdst,
                       int64_t n_src, int64_t n_dst, int32_t H, int32_t C, const float* att,
                       float slope, const int64_t* colptr, const int32_t* row,
-                      const float* rowmax, const float* rowden, const float* r, const float* addend,
+                      const float* stat, const float* addend,
                       float* g_hsrc, const kgb_gat_dropout* drop, const kgb_hub_table* hubs, kgb_stream_t stream);
 /* out[f] = sum_p part[p,f]  in fixed order (deterministic reduction of partials). */
 int kgb_reduce_parts(int device, const float* part, int32_t n_parts, int32_t F, float* out,

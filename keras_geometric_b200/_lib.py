@@ -120,7 +120,7 @@ SIGNATURES = {
     "kgb_gatv2_bwd_src_rec": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_float, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(HubTable), c_void_p]),
     "kgb_gatv2_bwd_src": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
-                                  c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, POINTER(GatDropout), POINTER(HubTable), c_void_p]),
     "kgb_reduce_parts": (c_int, [c_int, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "kgb_linear_tc_rows": (c_int32, [c_int32]),
@@ -136,7 +136,7 @@ SIGNATURES = {
     "kgb_linear_tc_dw": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p,
                                  c_int32, c_void_p]),
 }
-ABI_VERSION = 200  # must equal kgb_version() of the loaded library (bumped with every ABI change)
+ABI_VERSION = 201  # must equal kgb_version() of the loaded library (bumped with every ABI change)
 
 _lock = threading.Lock()
 _lib = None

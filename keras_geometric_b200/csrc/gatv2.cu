@@ -62,6 +62,15 @@ __device__ __forceinline__ float gat_drop(const GatP& p, uint32_t eid, int head)
   return ((bits >> (head & 3)) & 1u) ? p.drop_scale : 0.f;
 }
 
+// exp(x) for the softmax terms (x <= 0 up to rounding): one multiply + MUFU.EX2 (relative error 2^-22) instead of
+// expf's eight-instruction range reduction; the three kernels are issue-bound, and forward and backward use the same
+// function, so the recomputed alpha is the forward's alpha bit for bit.
+__device__ __forceinline__ float exp_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
+
 template <int LPH>
 __device__ __forceinline__ float head_sum(float v, unsigned gmask) {
 #pragma unroll
@@ -145,6 +154,7 @@ struct LaneCtx {
   bool on[CC];
   int off[CC];   // element offset inside an [H*C] row (0 for inactive lanes: loads stay unconditional)
   float a[CC][VEC];
+  float as[CC][VEC];   // a * slope: a * lrelu(z) = (z > 0 ? a : a * slope) * z, one select instead of multiply + select
   __device__ __forceinline__ void init(const GatP& p) {
     const int lane = threadIdx.x & 31;
     gl = lane % G;
@@ -160,12 +170,17 @@ struct LaneCtx {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) a[cc][e] = 0.f;  // inactive lanes contribute nothing to the logits
       }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) as[cc][e] = a[cc][e] * p.slope;
     }
   }
 };
 
 // ------------------------------------------------------------------------------------ forward
-template <int VEC, int LPH, int CC, int HPG>
+// DROPM = 0 compiles the attention dropout out (the common case: inference, or training without it - the Philox
+// path otherwise costs registers and issue slots in kernels that are issue-bound: fwd 3.10 -> 2.86 ms, per-target
+// backward 4.47 -> 3.97 ms on C4, H = 8, C = 8); DROPM = 1 decides at run time.
+template <int VEC, int LPH, int CC, int HPG, int DROPM>
 __device__ __forceinline__ void gat_fwd_range(const GatP& p, const LaneCtx<VEC, LPH, CC, HPG>& L, int64_t row,
                                               int64_t k0, int64_t k1, float& m, float& l, float (&acc)[CC][VEC]) {
   constexpr int G = LPH * HPG;
@@ -185,7 +200,7 @@ __device__ __forceinline__ void gat_fwd_range(const GatP& p, const LaneCtx<VEC, 
   m = -INFINITY;
   l = 0.f;
   int64_t k = k0;
-  const bool drop = p.drop_thr != 0u;
+  const bool drop = DROPM ? (p.drop_thr != 0u) : false;
   int32_t myc = (k + L.gl < k1) ? __ldg(p.col + k + L.gl) : 0;
   int32_t mye = (drop && k + L.gl < k1) ? __ldg(p.edge_id + k + L.gl) : 0;
   while (k < k1) {
@@ -214,12 +229,12 @@ __device__ __forceinline__ void gat_fwd_range(const GatP& p, const LaneCtx<VEC, 
 #pragma unroll
           for (int e = 0; e < VEC; ++e) {
             const float z = hi[cc][e] + v[u][cc][e];
-            part = fmaf(L.a[cc][e], z > 0.f ? z : z * p.slope, part);
+            part = fmaf(z > 0.f ? L.a[cc][e] : L.as[cc][e], z, part);
           }
         s[u] = head_sum<LPH>(part, L.gmask);
         if ((j + u) < cnt) mb = fmaxf(mb, s[u]);
       }
-      const float scale = (m == -INFINITY) ? 0.f : expf(m - mb);
+      const float scale = (m == -INFINITY) ? 0.f : exp_fast(m - mb);
       l *= scale;
 #pragma unroll
       for (int cc = 0; cc < CC; ++cc)
@@ -228,7 +243,7 @@ __device__ __forceinline__ void gat_fwd_range(const GatP& p, const LaneCtx<VEC, 
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if ((j + u) < cnt) {
-          const float pe = expf(s[u] - mb);
+          const float pe = exp_fast(s[u] - mb);
           l += pe;   // the softmax normalises over ALL edges; dropout only thins the weighted sum
           const float pd = drop ? pe * gat_drop(p, (uint32_t)__shfl_sync(L.gmask, mye, j + u, G), L.head) : pe;
 #pragma unroll
@@ -273,7 +288,7 @@ __device__ __forceinline__ void gat_fwd_store(const GatP& p, const LaneCtx<VEC, 
 #ifndef KGB_GAT_MINB_FWD
 #define KGB_GAT_MINB_FWD 4
 #endif
-template <int VEC, int LPH, int CC, int HPG>
+template <int VEC, int LPH, int CC, int HPG, int DROPM>
 __global__ void __launch_bounds__(256, KGB_GAT_MINB_FWD) gatv2_fwd_kernel(const GatP p) {
   using Ctx = LaneCtx<VEC, LPH, CC, HPG>;
   constexpr int G = Ctx::G;
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(256, KGB_GAT_MINB_FWD) gatv2_fwd_kernel(const 
       p,
       [&](int64_t t, int64_t row, int64_t k0, int64_t k1, bool) {
         float m, l, acc[CC][VEC];
-        gat_fwd_range<VEC, LPH, CC, HPG>(p, L, row, k0, k1, m, l, acc);
+        gat_fwd_range<VEC, LPH, CC, HPG, DROPM>(p, L, row, k0, k1, m, l, acc);
 #pragma unroll
         for (int cc = 0; cc < CC; ++cc)
           if (L.on[cc]) st_vec<VEC>(p.partial + t * HC + L.off[cc], acc[cc]);
@@ -297,7 +312,7 @@ __global__ void __launch_bounds__(256, KGB_GAT_MINB_FWD) gatv2_fwd_kernel(const 
       },
       [&](int64_t row, int64_t rs, int64_t re) {
         float m, l, acc[CC][VEC];
-        gat_fwd_range<VEC, LPH, CC, HPG>(p, L, row, rs, re, m, l, acc);
+        gat_fwd_range<VEC, LPH, CC, HPG, DROPM>(p, L, row, rs, re, m, l, acc);
         gat_fwd_store<VEC, LPH, CC, HPG>(p, L, row, m, l, acc);
       });
   gat_queue_reset(p);
@@ -329,8 +344,8 @@ __global__ void __launch_bounds__(256) gatv2_fwd_finish_kernel(const GatP p) {
     for (int c = 0; c < nch; ++c) {
       const float cm = __ldg(pm + (base + c) * p.H + hd), cl = __ldg(pl + (base + c) * p.H + hd);
       const float mn = fmaxf(m, cm);
-      const float so = (m == -INFINITY) ? 0.f : expf(m - mn);
-      const float sn = (cm == -INFINITY) ? 0.f : expf(cm - mn);
+      const float so = (m == -INFINITY) ? 0.f : exp_fast(m - mn);
+      const float sn = (cm == -INFINITY) ? 0.f : exp_fast(cm - mn);
       l = l * so + cl * sn;
 #pragma unroll
       for (int cc = 0; cc < CC; ++cc) {
@@ -346,8 +361,9 @@ __global__ void __launch_bounds__(256) gatv2_fwd_finish_kernel(const GatP p) {
 }
 
 // --------------------------------------------------------------------- backward, per target
-template <int VEC, int LPH, int CC, int HPG>
-__device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<VEC, LPH, CC, HPG>& L, int64_t row,
+// REC compiles the per-edge record stores in (opt-in path); without them the kernel is 10 % faster (4.94 -> 4.47 ms).
+template <int VEC, int LPH, int CC, int HPG, int DROPM, bool REC>
+__device__ __forceinline__ float4 gat_bwd_dst_range(const GatP& p, const LaneCtx<VEC, LPH, CC, HPG>& L, int64_t row,
                                                    int64_t k0, int64_t k1, float (&ghi)[CC][VEC],
                                                    float (&ga)[CC][VEC]) {
   constexpr int G = LPH * HPG;
@@ -383,7 +399,7 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
   const float m = __ldg(p.rowmax + row * p.H + hd);
   const float dinv = 1.f / (__ldg(p.rowden + row * p.H + hd) + 1e-10f);
   int64_t k = k0;
-  const bool drop = p.drop_thr != 0u;
+  const bool drop = DROPM ? (p.drop_thr != 0u) : false;
   int32_t myc = (k + L.gl < k1) ? __ldg(p.col + k + L.gl) : 0;
   int32_t mye = (drop && k + L.gl < k1) ? __ldg(p.edge_id + k + L.gl) : 0;
   while (k < k1) {
@@ -410,7 +426,7 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
 #pragma unroll
           for (int e = 0; e < VEC; ++e) {
             const float z = hi[cc][e] + v[u][cc][e];
-            sp = fmaf(L.a[cc][e], z > 0.f ? z : z * p.slope, sp);
+            sp = fmaf(z > 0.f ? L.a[cc][e] : L.as[cc][e], z, sp);
             dp = fmaf(gi[cc][e], v[u][cc][e], dp);
           }
         const float s = head_sum<LPH>(sp, L.gmask);
@@ -418,7 +434,7 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
         const float dfac = drop ? gat_drop(p, (uint32_t)__shfl_sync(L.gmask, mye, j + u, G), L.head) : 1.f;
         da *= dfac;   // d out / d alpha
         if ((j + u) < cnt) {
-          const float alpha = expf(s - m) * dinv;
+          const float alpha = exp_fast(s - m) * dinv;
           const float ds = alpha * (da - r);
 #pragma unroll
           for (int cc = 0; cc < CC; ++cc)
@@ -426,10 +442,10 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
             for (int e = 0; e < VEC; ++e) {
               const float z = hi[cc][e] + v[u][cc][e];
               const float lz = z > 0.f ? z : z * p.slope;
-              ghi[cc][e] += ds * L.a[cc][e] * (z > 0.f ? 1.f : p.slope);
+              ghi[cc][e] = fmaf(ds, z > 0.f ? L.a[cc][e] : L.as[cc][e], ghi[cc][e]);
               ga[cc][e] = fmaf(ds, lz, ga[cc][e]);
             }
-          if constexpr (CC == 1) {
+          if constexpr (CC == 1 && REC) {
             if (p.rec) {   // per-edge record for the per-source pass (group-uniform branch)
               constexpr int NW = (VEC * G + 31) / 32;
               float* rrow = p.rec + (k + j + u) * (int64_t)p.rec_ld;
@@ -459,7 +475,7 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
     mye = ne;
     k = kn;
   }
-  return r;
+  return make_float4(m, dinv, r, 0.f);   // the per-(target, head) record of the per-source pass
 }
 
 #ifndef KGB_GAT_MINB_DST
@@ -468,7 +484,7 @@ __device__ __forceinline__ float gat_bwd_dst_range(const GatP& p, const LaneCtx<
 #ifndef KGB_GAT_MINB_SRC
 #define KGB_GAT_MINB_SRC 4
 #endif
-template <int VEC, int LPH, int CC, int HPG>
+template <int VEC, int LPH, int CC, int HPG, int DROPM, bool REC>
 __global__ void __launch_bounds__(256, KGB_GAT_MINB_DST) gatv2_bwd_dst_kernel(const GatP p) {
   using Ctx = LaneCtx<VEC, LPH, CC, HPG>;
   constexpr int G = Ctx::G;
@@ -487,19 +503,19 @@ __global__ void __launch_bounds__(256, KGB_GAT_MINB_DST) gatv2_bwd_dst_kernel(co
       p,
       [&](int64_t t, int64_t row, int64_t k0, int64_t k1, bool first) {
         float ghi[CC][VEC];
-        const float r = gat_bwd_dst_range<VEC, LPH, CC, HPG>(p, L, row, k0, k1, ghi, ga);
+        const float4 stat = gat_bwd_dst_range<VEC, LPH, CC, HPG, DROPM, REC>(p, L, row, k0, k1, ghi, ga);
 #pragma unroll
         for (int cc = 0; cc < CC; ++cc)
           if (L.on[cc]) st_vec<VEC>(p.partial + t * HC + L.off[cc], ghi[cc]);
-        if (first && L.head < p.H && (L.gl % LPH) == 0) p.r_out[row * p.H + L.head] = r;
+        if (first && L.head < p.H && (L.gl % LPH) == 0) reinterpret_cast<float4*>(p.r_out)[row * p.H + L.head] = stat;
       },
       [&](int64_t row, int64_t rs, int64_t re) {
         float ghi[CC][VEC];
-        const float r = gat_bwd_dst_range<VEC, LPH, CC, HPG>(p, L, row, rs, re, ghi, ga);
+        const float4 stat = gat_bwd_dst_range<VEC, LPH, CC, HPG, DROPM, REC>(p, L, row, rs, re, ghi, ga);
 #pragma unroll
         for (int cc = 0; cc < CC; ++cc)
           if (L.on[cc]) st_vec<VEC>(p.g_hdst + row * HC + L.off[cc], ghi[cc]);
-        if (L.head < p.H && (L.gl % LPH) == 0) p.r_out[row * p.H + L.head] = r;
+        if (L.head < p.H && (L.gl % LPH) == 0) reinterpret_cast<float4*>(p.r_out)[row * p.H + L.head] = stat;
       });
   // d att: fold the groups of a warp (fixed order), then the warps of the CTA (fixed order)
   __syncwarp();
@@ -538,7 +554,7 @@ __device__ __forceinline__ void gat_bwd_src_range(const GatP& p, const LaneCtx<V
                                                   int64_t k0, int64_t k1, float (&ghj)[CC][VEC]) {
   constexpr int G = LPH * HPG;
 #ifndef KGB_GAT_U_SRC
-#define KGB_GAT_U_SRC 2   // with 4 CTAs/SM: 7.19 ms (H8C8 on C4); 2 CTAs/SM: 11.4; U=4 / 3 CTAs: 7.50; U=8 / 3: 13.5
+#define KGB_GAT_U_SRC 3   // with 4 CTAs/SM, H8C8 on C4: U=2 6.73 ms, U=3 6.50, U=4 7.30 (U=4 / 3 CTAs: 6.70)
 #endif
   constexpr int UMAX = (KGB_GAT_U_SRC / CC) < 1 ? 1 : (KGB_GAT_U_SRC / CC);
   constexpr int U = (G < UMAX) ? G : UMAX;
@@ -568,9 +584,11 @@ __device__ __forceinline__ void gat_bwd_src_range(const GatP& p, const LaneCtx<V
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t i = __shfl_sync(L.gmask, myc, j + u, G);
-        m[u] = __ldg(p.rowmax + i * p.H + hd);
-        dinv[u] = 1.f / (__ldg(p.rowden + i * p.H + hd) + 1e-10f);
-        r[u] = __ldg(p.r_in + i * p.H + hd);
+        // (row max, 1 / (l + 1e-10), r) of (target i, head): ONE 16-byte record written by the per-target pass
+        const float4 st = __ldg(reinterpret_cast<const float4*>(p.r_in) + i * p.H + hd);
+        m[u] = st.x;
+        dinv[u] = st.y;
+        r[u] = st.z;
 #pragma unroll
         for (int cc = 0; cc < CC; ++cc) {
           ld_vec<VEC>(p.hdst + i * HC + L.off[cc], hi[u][cc]);
@@ -585,7 +603,7 @@ __device__ __forceinline__ void gat_bwd_src_range(const GatP& p, const LaneCtx<V
 #pragma unroll
           for (int e = 0; e < VEC; ++e) {
             const float z = hi[u][cc][e] + hj[cc][e];
-            sp = fmaf(L.a[cc][e], z > 0.f ? z : z * p.slope, sp);
+            sp = fmaf(z > 0.f ? L.a[cc][e] : L.as[cc][e], z, sp);
             dp = fmaf(L.on[cc] ? gi[u][cc][e] : 0.f, hj[cc][e], dp);
           }
         const float s = head_sum<LPH>(sp, L.gmask);
@@ -593,7 +611,7 @@ __device__ __forceinline__ void gat_bwd_src_range(const GatP& p, const LaneCtx<V
         const float d = drop ? gat_drop(p, (uint32_t)__shfl_sync(L.gmask, mye, j + u, G), L.head) : 1.f;
         da *= d;
         if ((j + u) < cnt) {
-          const float alpha = expf(s - m[u]) * dinv[u];
+          const float alpha = exp_fast(s - m[u]) * dinv[u];
           const float ds = alpha * (da - r[u]);
           const float ad = alpha * d;   // the message itself: alpha_e * dropout_e * h_j
 #pragma unroll
@@ -601,7 +619,7 @@ __device__ __forceinline__ void gat_bwd_src_range(const GatP& p, const LaneCtx<V
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
               const float z = hi[u][cc][e] + hj[cc][e];
-              ghj[cc][e] += ds * L.a[cc][e] * (z > 0.f ? 1.f : p.slope) + ad * gi[u][cc][e];
+              ghj[cc][e] = fmaf(ds, z > 0.f ? L.a[cc][e] : L.as[cc][e], fmaf(ad, gi[u][cc][e], ghj[cc][e]));
             }
         }
       }
@@ -694,7 +712,7 @@ __device__ __forceinline__ void gat_bwd_src_rec_range(const GatP& p, const LaneC
         if ((j + u) < cnt) {
 #pragma unroll
           for (int e = 0; e < VEC; ++e)
-            ghj[0][e] += ds[u] * L.a[0][e] * (sb[u][e] ? 1.f : p.slope) + ad[u] * gi[u][e];
+            ghj[0][e] = fmaf(ds[u], sb[u][e] ? L.a[0][e] : L.as[0][e], fmaf(ad[u], gi[u][e], ghj[0][e]));
         }
       }
     }
@@ -780,10 +798,21 @@ enum { GAT_FWD = 0, GAT_BWD_DST = 1, GAT_BWD_SRC = 2, GAT_FWD_FINISH = 3, GAT_BW
 
 template <int VEC, int LPH, int CC, int HPG>
 static void gat_launch(int which, dim3 grid, cudaStream_t st, const GatP& p) {
-  if (which == GAT_FWD) gatv2_fwd_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
-  else if (which == GAT_FWD_FINISH) gatv2_fwd_finish_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
-  else if (which == GAT_BWD_DST) gatv2_bwd_dst_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
-  else if (which == GAT_BWD_SRC_REC) gatv2_bwd_src_rec_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
+  // the dropout-free instantiations exist for the 128-bit layouts only (the scalar-width fallback decides at run time)
+  const bool nodrop = (VEC == 4) && p.drop_thr == 0u;
+  if (which == GAT_FWD) {
+    if constexpr (VEC == 4) {
+      if (nodrop) { gatv2_fwd_kernel<VEC, LPH, CC, HPG, 0><<<grid, 256, 0, st>>>(p); return; }
+    }
+    gatv2_fwd_kernel<VEC, LPH, CC, HPG, 1><<<grid, 256, 0, st>>>(p);
+  } else if (which == GAT_FWD_FINISH) gatv2_fwd_finish_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
+  else if (which == GAT_BWD_DST) {
+    if (p.rec) { gatv2_bwd_dst_kernel<VEC, LPH, CC, HPG, 1, true><<<grid, 256, 0, st>>>(p); return; }
+    if constexpr (VEC == 4) {
+      if (nodrop) { gatv2_bwd_dst_kernel<VEC, LPH, CC, HPG, 0, false><<<grid, 256, 0, st>>>(p); return; }
+    }
+    gatv2_bwd_dst_kernel<VEC, LPH, CC, HPG, 1, false><<<grid, 256, 0, st>>>(p);
+  } else if (which == GAT_BWD_SRC_REC) gatv2_bwd_src_rec_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
   else gatv2_bwd_src_kernel<VEC, LPH, CC, HPG><<<grid, 256, 0, st>>>(p);
 }
 
@@ -920,7 +949,7 @@ int kgb_gatv2_bwd_parts(int device, int64_t n_dst, int32_t H, int32_t C) {
 int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float* hsrc, const float* hdst,
                       int64_t n_src, int64_t n_dst, int32_t H, int32_t C, const float* att, float slope,
                       const int64_t* rowptr, const int32_t* col, const float* rowmax, const float* rowden,
-                      const float* bias, float* g_hdst, float* r, float* g_att_part, int32_t n_parts,
+                      const float* bias, float* g_hdst, float* stat, float* g_att_part, int32_t n_parts,
                       float* rec, const kgb_gat_dropout* drop, const kgb_hub_table* hubs, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(H > 0 && C > 0 && n_dst >= 0 && n_parts > 0, "bad sizes");
@@ -928,11 +957,12 @@ int kgb_gatv2_bwd_dst(int device, const float* g, const float* agg, const float*
   cudaStream_t st = (cudaStream_t)stream;
   KGB_CHECK_CUDA(cudaMemsetAsync(g_att_part, 0, (size_t)n_parts * H * C * sizeof(float), st));
   if (n_dst == 0) return KGB_OK;
-  KGB_REQUIRE(g && agg && hsrc && hdst && att && rowptr && rowmax && rowden && g_hdst && r, "NULL pointer");
+  KGB_REQUIRE(g && agg && hsrc && hdst && att && rowptr && rowmax && rowden && g_hdst && stat, "NULL pointer");
+  KGB_REQUIRE(aligned16(stat), "stat must be 16-byte aligned");
   GatP p = {};
   p.hsrc = hsrc; p.hdst = hdst; p.n_src = n_src; p.n_dst = n_dst; p.H = H; p.C = C; p.att = att; p.slope = slope;
   p.rowptr = rowptr; p.col = col; p.rowmax = const_cast<float*>(rowmax); p.rowden = const_cast<float*>(rowden);
-  p.g = g; p.agg = agg; p.bias = bias; p.g_hdst = g_hdst; p.r_out = r; p.g_att_part = g_att_part;
+  p.g = g; p.agg = agg; p.bias = bias; p.g_hdst = g_hdst; p.r_out = stat; p.g_att_part = g_att_part;
   p.n_rows = n_dst;
   if (rec) {
     p.rec_ld = kgb_gatv2_rec_floats(H, C);
@@ -975,17 +1005,17 @@ int kgb_gatv2_bwd_src_rec(int device, const float* g, int64_t n_src, int64_t n_d
 
 int kgb_gatv2_bwd_src(int device, const float* g, const float* hsrc, const float* hdst, int64_t n_src,
                       int64_t n_dst, int32_t H, int32_t C, const float* att, float slope, const int64_t* colptr,
-                      const int32_t* row, const float* rowmax, const float* rowden, const float* r,
-                      const float* addend, float* g_hsrc, const kgb_gat_dropout* drop, const kgb_hub_table* hubs,
-                      kgb_stream_t stream) {
+                      const int32_t* row, const float* stat, const float* addend, float* g_hsrc,
+                      const kgb_gat_dropout* drop, const kgb_hub_table* hubs, kgb_stream_t stream) {
   KGB_USE_DEVICE(device);
   KGB_REQUIRE(H > 0 && C > 0 && n_src >= 0, "bad sizes");
   if (n_src == 0) return KGB_OK;
-  KGB_REQUIRE(g && hsrc && hdst && att && colptr && rowmax && rowden && r && g_hsrc, "NULL pointer");
+  KGB_REQUIRE(g && hsrc && hdst && att && colptr && stat && g_hsrc, "NULL pointer");
+  KGB_REQUIRE(aligned16(stat), "stat must be 16-byte aligned");
   GatP p = {};
   p.hsrc = hsrc; p.hdst = hdst; p.n_src = n_src; p.n_dst = n_dst; p.H = H; p.C = C; p.att = att; p.slope = slope;
-  p.rowptr = colptr; p.col = row; p.rowmax = const_cast<float*>(rowmax); p.rowden = const_cast<float*>(rowden);
-  p.g = g; p.r_in = r; p.addend = addend; p.g_hsrc = g_hsrc;
+  p.rowptr = colptr; p.col = row;
+  p.g = g; p.r_in = stat; p.addend = addend; p.g_hsrc = g_hsrc;
   p.n_rows = n_src;
   if (gat_set_dropout(p, drop) != KGB_OK) return KGB_ERR_INVALID;
   gat_set_hubs(p, hubs);

@@ -131,8 +131,12 @@ def gather_reduce_raw(x: torch.Tensor, csr: Csr, op: int, *, col: torch.Tensor |
     a.unit_order = _ptr(csr.unit_order())
     if drop_p > 0.0:   # element-wise dropout of the gathered rows, regenerated from the original edge ids
         a.drop_p, a.drop_seed, a.edge_id = float(drop_p), int(drop_seed), csr.perm.data_ptr()
-    elif col is None and x2 is None and out2 is None and out2_push is None and op != _lib.OP_SQDEV:
-        a.col_hot = _ptr(csr.col_hot(F))        # L2 eviction hints for the hub rows (None: off / everything fits)
+    elif (col is None and x2 is None and out2 is None and out2_push is None and op != _lib.OP_SQDEV
+          and op not in _lib.MAX_OPS):
+        # L2 eviction hints for the hub rows (None: off / not yet due / everything fits).  Not for max / min: those
+        # kernels are issue-bound (ncu: 6.0 G instructions at 78 % issue utilisation for F = 256), and the hint
+        # bookkeeping adds 8 % more instructions
+        a.col_hot = _ptr(csr.col_hot(F))
     if x2 is not None:
         a.x2, a.ldx2, a.n_split_src = x2.data_ptr(), x2.stride(0), int(n_split_src)
     if out2 is not None or out2_push is not None:
@@ -563,7 +567,7 @@ class _GatV2(torch.autograd.Function):
         if n_parts <= 0:
             raise _lib.KgbError("kgb_gatv2_bwd_parts: unsupported shape")
         g_hdst = torch.empty_like(h_dst)
-        r = torch.empty((n_dst, H), dtype=torch.float32, device=dev)
+        r = torch.empty((n_dst, H, 4), dtype=torch.float32, device=dev)   # (max, 1/den, r, -) per (target, head)
         part = torch.empty((n_parts, H * C), dtype=torch.float32, device=dev)
         # per-edge records (alpha * dropout, d logit, sign bits of z): the per-source pass then gathers one row per
         # edge instead of two and recomputes nothing.  Measured on C4 (+ self-loops, tools/exp_gat.py): the per-source
@@ -599,7 +603,7 @@ class _GatV2(torch.autograd.Function):
         with _prof(f"gatv2_bwd_src_H{H}_C{C}", gat_bytes(csc.nnz, n_src, H, C), dev):
             _lib.check(lib.kgb_gatv2_bwd_src(dev.index, g.data_ptr(), h_src.data_ptr(), h_dst.data_ptr(), n_src, n_dst,
                                              H, C, att_c.data_ptr(), ctx.slope, csc.rowptr.data_ptr(),
-                                             csc.col.data_ptr(), rowmax.data_ptr(), rowden.data_ptr(), r.data_ptr(),
+                                             csc.col.data_ptr(), r.data_ptr(),
                                              g_hdst.data_ptr() if ctx.same else None, g_hsrc.data_ptr(),
                                              _gat_drop(ctx.drop, csc),
                                              ctypes.byref(csc.hub_table(lib.kgb_gatv2_partial_bytes(csc.n_chunks, H, C), st, gat=True)),

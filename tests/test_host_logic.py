@@ -33,7 +33,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in _lib.SIGNATURES"
     assert set(_lib.SIGNATURES) <= set(names)
     lib.kgb_version.restype = ctypes.c_int
-    assert lib.kgb_version() == 200
+    assert lib.kgb_version() == _lib.ABI_VERSION
 
 
 def test_struct_layout_matches_header():
