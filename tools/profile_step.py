@@ -32,3 +32,15 @@ s = sum(v[1] for v in tot.values())
 print(f"total device time per step {s/2/1e3:.2f} ms")
 for k, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:22]:
     print(f"{t/2/1e3:8.2f} ms/step  n={n//2:3d}  {k}")
+# idle time between consecutive kernels of the two profiled steps: where the device waits for the host
+evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA],
+             key=lambda e: e.time_range.start)
+span = evs[-1].time_range.end - evs[0].time_range.start
+gaps = []
+for a, b in zip(evs, evs[1:]):
+    g = b.time_range.start - a.time_range.end
+    if g > 3:
+        gaps.append((g, re.sub(r"<.*", "", a.name)[:40], re.sub(r"<.*", "", b.name)[:40]))
+print(f"span per step {span/2/1e3:.2f} ms, idle per step {sum(g for g, _, _ in gaps)/2/1e3:.2f} ms in {len(gaps)//2} gaps > 3 us")
+for g, a, b in sorted(gaps, reverse=True)[:14]:
+    print(f"{g:8.0f} us  after {a}  before {b}")
