@@ -504,7 +504,9 @@ __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, i
 
 // resident CTAs per SM the register allocation is tuned for (8 float4 loads in flight per lane)
 #ifndef KGB_GR_MINB_WIDE
-#define KGB_GR_MINB_WIDE 3  // VEC == 4 and G >= 16: the HBM-bound shapes
+#define KGB_GR_MINB_WIDE 3  // VEC == 4 and G == 32 (rows of >= 17 vectors): the HBM-bound shapes.  4 CTAs/SM were measured on
+                            // C4: F=48 (G=16) 2.02 / 2.58 -> 1.97 / 2.41 ms fwd / bwd (latency-bound, so G=16 is "narrow"),
+                            // F=100 2.73 / 3.42 -> 2.68 / 3.62, F=256 6.02 / 6.59 -> 6.51 / 7.58 (spills)
 #endif
 #ifndef KGB_GR_MINB_NARROW
 #define KGB_GR_MINB_NARROW 4
@@ -519,7 +521,7 @@ __device__ __forceinline__ void do_row_block(const GRP& p, int64_t r0, int gl, i
 // 27 % of the SM-cycles idle in the first version.  Which warp computes a row never changes the
 // result, so the output stays deterministic.
 template <int VEC, int G, int NCH, bool IS_MAX, bool HAS_EW, bool HAS_SS, bool SPLIT, bool SQDEV, bool HOT, bool DROP>
-__global__ void __launch_bounds__(256, ((VEC == 4 && G >= 16) ? (IS_MAX ? KGB_GR_MINB_MAX : KGB_GR_MINB_WIDE)
+__global__ void __launch_bounds__(256, ((VEC == 4 && G >= 32) ? (IS_MAX ? KGB_GR_MINB_MAX : KGB_GR_MINB_WIDE)
                                                               : KGB_GR_MINB_NARROW))
 gather_reduce_kernel(const GRP p) {
   constexpr int GPW = 32 / G;
