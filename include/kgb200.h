@@ -111,6 +111,14 @@ int kgb_softmax_xent_fwd(int device, const float* logits, int64_t ld, const int6
                          float* row_loss, kgb_stream_t stream);
 int kgb_softmax_xent_bwd(int device, const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C,
                          const float* grad_loss, float scale, float* dlogits, int64_t ldd, kgb_stream_t stream);
+/* Row-wise L2 normalisation, keras.ops.normalize(axis=-1, order=2) of SAGEConv(normalize=True)
+ * (layers/sage_conv.py:432-433): y[r,:] = x[r,:] / max(||x[r,:]||_2, eps), norm[r] = ||x[r,:]||_2 (saved for the
+ * backward).  bwd: gx = (g - y <g, y>) / max(norm, eps) where norm >= eps, g / eps otherwise.  Rows of up to 1024
+ * floats are kept in registers (one read), wider rows are read twice. */
+int kgb_l2_normalize(int device, const float* x, int64_t ldx, int64_t rows, int32_t F, float eps, float* y, int64_t ldy,
+                     float* norm, kgb_stream_t stream);
+int kgb_l2_normalize_bwd(int device, const float* g, int64_t ldg, const float* y, int64_t ldy, const float* norm,
+                         int64_t rows, int32_t F, float eps, float* gx, int64_t ldgx, kgb_stream_t stream);
 /* out[k] = in[perm[k]]  (bring COO-ordered edge weights into CSR / CSC slot order) */
 int kgb_permute_f32(int device, const float* in, const int32_t* perm, int64_t n, float* out,
                     kgb_stream_t stream);

@@ -123,6 +123,10 @@ SIGNATURES = {
                                   c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, POINTER(GatDropout), POINTER(HubTable), c_void_p]),
     "kgb_reduce_parts": (c_int, [c_int, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "kgb_l2_normalize": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int32, c_float, c_void_p, c_int64, c_void_p,
+                                 c_void_p]),
+    "kgb_l2_normalize_bwd": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_float,
+                                     c_void_p, c_int64, c_void_p]),
     "kgb_linear_tc_rows": (c_int32, [c_int32]),
     "kgb_split_tf32": (c_int, [c_int, c_void_p, c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "kgb_linear_tc": (c_int, [c_int, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
@@ -136,7 +140,7 @@ SIGNATURES = {
     "kgb_linear_tc_dw": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p,
                                  c_int32, c_void_p]),
 }
-ABI_VERSION = 201  # must equal kgb_version() of the loaded library (bumped with every ABI change)
+ABI_VERSION = 202  # must equal kgb_version() of the loaded library (bumped with every ABI change)
 
 _lock = threading.Lock()
 _lib = None

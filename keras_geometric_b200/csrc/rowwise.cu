@@ -1,7 +1,9 @@
 // Row-streaming helpers of the training step (HBM-bound, one pass each):
 //   * kgb_relu_bwd_colsum: g_pre = g * (y > 0) and the bias gradient sum_r g_pre[r,:] in the same pass
 //     (per-CTA column partials in a fixed order -> kgb_reduce_parts; deterministic, no float atomics),
-//   * kgb_softmax_xent_fwd / _bwd: mean softmax cross-entropy over integer labels, one warp per row.
+//   * kgb_softmax_xent_fwd / _bwd: mean softmax cross-entropy over integer labels, one warp per row,
+//   * kgb_l2_normalize / _bwd: y = x / max(||x||_2, eps) per row (SAGEConv normalize=True, sage_conv.py:432-433),
+//     one warp per row, the row is read once and kept in registers.
 #include "common.cuh"
 
 namespace kgb {
@@ -116,6 +118,100 @@ softmax_xent_kernel(const float* __restrict__ logits, int64_t ld, const int64_t*
   }
 }
 
+// ---- row-wise L2 normalisation ----------------------------------------------------------------------------------
+// keras.ops.normalize(axis=-1, order=2) on the torch backend: x / clamp(||x||, min=eps).  One warp per row, lane l owns
+// elements l, l + 32, ... (PER of them, F <= 32 * PER); the squared norm is a fixed-order warp reduction.
+// Backward (y = x / d, d = max(n, eps)): n >= eps -> gx = (g - y <g, y>) / d (clamp passes the gradient, inclusive
+// like torch.clamp's mask), n < eps -> gx = g / d.
+template <int PER, bool BWD>
+__global__ void __launch_bounds__(256)
+l2_normalize_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ y, int64_t ldy,
+                    float* __restrict__ norm, int64_t rows, int F, float eps, float* __restrict__ out, int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wpb = blockDim.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
+    float v[PER];
+    float s = 0.f;
+    if (!BWD) {
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = lane + i * 32;
+        v[i] = (c < F) ? __ldg(a + r * lda + c) : 0.f;
+        s = fmaf(v[i], v[i], s);
+      }
+      const float n = __fsqrt_rn(warp_sum(s));
+      const float d = fmaxf(n, eps);
+      if (lane == 0) norm[r] = n;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = lane + i * 32;
+        if (c < F) out[r * ldo + c] = __fdiv_rn(v[i], d);
+      }
+    } else {
+      float yy[PER];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = lane + i * 32;
+        v[i] = (c < F) ? __ldg(a + r * lda + c) : 0.f;        // upstream gradient
+        yy[i] = (c < F) ? __ldg(y + r * ldy + c) : 0.f;
+        s = fmaf(v[i], yy[i], s);
+      }
+      const float n = __ldg(norm + r);
+      const float d = fmaxf(n, eps);
+      const float dot = (n >= eps) ? warp_sum(s) : 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = lane + i * 32;
+        if (c < F) out[r * ldo + c] = __fdiv_rn(v[i] - yy[i] * dot, d);
+      }
+    }
+  }
+}
+
+// rows wider than 1024 floats: the same arithmetic, the row is read twice instead of being kept in registers
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+l2_normalize_wide_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ y, int64_t ldy,
+                         float* __restrict__ norm, int64_t rows, int F, float eps, float* __restrict__ out, int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wpb = blockDim.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
+    float s = 0.f;
+    for (int c = lane; c < F; c += 32) {
+      const float v = __ldg(a + r * lda + c);
+      s = fmaf(v, BWD ? __ldg(y + r * ldy + c) : v, s);
+    }
+    s = warp_sum(s);
+    const float n = BWD ? __ldg(norm + r) : __fsqrt_rn(s);
+    const float d = fmaxf(n, eps);
+    if (!BWD && lane == 0) norm[r] = n;
+    const float dot = (BWD && n >= eps) ? s : 0.f;
+    for (int c = lane; c < F; c += 32) {
+      const float v = __ldg(a + r * lda + c);
+      out[r * ldo + c] = __fdiv_rn(BWD ? v - __ldg(y + r * ldy + c) * dot : v, d);
+    }
+  }
+}
+
+template <bool BWD>
+static int launch_l2(int device, const float* a, int64_t lda, const float* y, int64_t ldy, float* norm, int64_t rows,
+                     int F, float eps, float* out, int64_t ldo, cudaStream_t st) {
+  int64_t grid = ceil_div(rows, 8);
+  const int64_t cap = (int64_t)sm_count(device) * 8;
+  if (grid > cap) grid = cap;
+#define KGB_L2(P) l2_normalize_kernel<P, BWD><<<(int)grid, 256, 0, st>>>(a, lda, y, ldy, norm, rows, F, eps, out, ldo)
+  if (F <= 32) KGB_L2(1);
+  else if (F <= 64) KGB_L2(2);
+  else if (F <= 128) KGB_L2(4);
+  else if (F <= 256) KGB_L2(8);
+  else if (F <= 512) KGB_L2(16);
+  else if (F <= 1024) KGB_L2(32);
+  else l2_normalize_wide_kernel<BWD><<<(int)grid, 256, 0, st>>>(a, lda, y, ldy, norm, rows, F, eps, out, ldo);
+#undef KGB_L2
+  KGB_CHECK_LAUNCH();
+  return KGB_OK;
+}
+
 template <bool BWD>
 static int launch_xent(int device, const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int C,
                        float* row_loss, const float* gup, float scale, float* dlogits, int64_t ldd, cudaStream_t st) {
@@ -194,6 +290,24 @@ int kgb_softmax_xent_bwd(int device, const float* logits, int64_t ld, const int6
   if (rows == 0) return KGB_OK;
   KGB_REQUIRE(logits && labels && grad_loss && dlogits, "NULL pointer");
   return launch_xent<true>(device, logits, ld, labels, rows, C, nullptr, grad_loss, scale, dlogits, ldd, (cudaStream_t)stream);
+}
+
+int kgb_l2_normalize(int device, const float* x, int64_t ldx, int64_t rows, int32_t F, float eps, float* y, int64_t ldy,
+                     float* norm, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(rows >= 0 && F > 0, "l2_normalize: F > 0");
+  if (rows == 0) return KGB_OK;
+  KGB_REQUIRE(x && y && norm, "NULL pointer");
+  return launch_l2<false>(device, x, ldx, nullptr, 0, norm, rows, F, eps, y, ldy, (cudaStream_t)stream);
+}
+
+int kgb_l2_normalize_bwd(int device, const float* g, int64_t ldg, const float* y, int64_t ldy, const float* norm,
+                         int64_t rows, int32_t F, float eps, float* gx, int64_t ldgx, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(rows >= 0 && F > 0, "l2_normalize: F > 0");
+  if (rows == 0) return KGB_OK;
+  KGB_REQUIRE(g && y && norm && gx, "NULL pointer");
+  return launch_l2<true>(device, g, ldg, y, ldy, const_cast<float*>(norm), rows, F, eps, gx, ldgx, (cudaStream_t)stream);
 }
 
 }  // extern "C"

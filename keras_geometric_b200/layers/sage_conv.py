@@ -178,8 +178,8 @@ class SAGEConv(MessagePassing):
         else:
             aggregated = self.aggregate_neighbors(x, edge_index, num_nodes, training=training)
             out = self._dense_update(aggregated, x, w_neigh, w_self, bias, dropping)
-        if self.normalize:  # ops.normalize(axis=-1, order=2): x / max(||x||, 1e-12)
-            out = out / torch.clamp(torch.linalg.vector_norm(out, ord=2, dim=-1, keepdim=True), min=1e-12)
+        if self.normalize:  # ops.normalize(axis=-1, order=2): x / max(||x||, 1e-12), one fused row pass
+            out = ops.l2_normalize(out, 1e-12)
         return out
 
     def _aggregate_after_transform(self, x, graph, w_neigh, w_self, bias, act_is_relu, exchange=None):
@@ -284,8 +284,8 @@ class SAGEConv(MessagePassing):
             out = ops.linear(aggregated, w_neigh, addend=root, bias=bias, act="relu" if act_is_relu else None)
             if self.activation is not None and not act_is_relu:
                 out = self.activation(out)
-        if self.normalize:
-            out = out / torch.clamp(torch.linalg.vector_norm(out, ord=2, dim=-1, keepdim=True), min=1e-12)
+        if self.normalize:  # ops.normalize(axis=-1, order=2): x / max(||x||, 1e-12), one fused row pass
+            out = ops.l2_normalize(out, 1e-12)
         return out
 
     def get_config(self) -> dict[str, Any]:  # sage_conv.py:441-473

@@ -280,6 +280,51 @@ def softmax_cross_entropy(logits: torch.Tensor, labels: torch.Tensor) -> torch.T
     return _SoftmaxXent.apply(logits, labels)
 
 
+class _L2Normalize(torch.autograd.Function):
+    """y = x / max(||x||_2, eps) per row (keras.ops.normalize(axis=-1, order=2), layers/sage_conv.py:432-433) in one pass
+    forward and one pass backward."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        x = _f32c(x, "x")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        lib = _lib.load()
+        dev = x.device
+        rows, F = int(x.shape[0]), int(x.shape[1])
+        y = torch.empty((rows, F), dtype=torch.float32, device=dev)
+        norm = torch.empty(max(rows, 1), dtype=torch.float32, device=dev)[:rows]
+        _lib.check(lib.kgb_l2_normalize(dev.index, x.data_ptr(), x.stride(0), rows, F, float(eps), y.data_ptr(), y.stride(0),
+                                        norm.data_ptr(), _stream(dev)), "kgb_l2_normalize")
+        ctx.eps = float(eps)
+        ctx.save_for_backward(y, norm)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        y, norm = ctx.saved_tensors
+        g = _f32c(g, "grad")
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        lib = _lib.load()
+        dev = g.device
+        rows, F = int(y.shape[0]), int(y.shape[1])
+        gx = torch.empty((rows, F), dtype=torch.float32, device=dev)
+        _lib.check(lib.kgb_l2_normalize_bwd(dev.index, g.data_ptr(), g.stride(0), y.data_ptr(), y.stride(0), norm.data_ptr(),
+                                            rows, F, ctx.eps, gx.data_ptr(), gx.stride(0), _stream(dev)),
+                   "kgb_l2_normalize_bwd")
+        return gx, None
+
+
+def l2_normalize(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """Row-wise ``x / max(||x||_2, eps)`` on the row kernel (K10)."""
+    require_cuda(x, "x")
+    if x.dim() != 2 or int(x.shape[1]) == 0:
+        raise ValueError("l2_normalize expects a [rows, F] matrix with F > 0")
+    return _L2Normalize.apply(x, eps)
+
+
 def permute_f32(w: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(perm.shape[0], dtype=torch.float32, device=w.device)

@@ -478,6 +478,31 @@ def test_relu_bwd_colsum(rows, F):
     close(col4, wide[:, :F].double().sum(0).float(), rtol=1e-5, atol_scale=1e-5, msg="strided colsum")
 
 
+@pytest.mark.parametrize("rows,F", [(1, 1), (7, 3), (300, 47), (1000, 256), (33, 1000), (5, 1500)])
+def test_l2_normalize_rows(rows, F):
+    """ops.l2_normalize == keras.ops.normalize(axis=-1, order=2) (oracle/keras_ops.py:276) forward and backward,
+    including all-zero rows (norm below eps: y = 0, gradient g / eps) and a tiny row."""
+    from keras_geometric_b200 import ops
+    from oracle import keras_ops as kops
+    rng = np.random.default_rng(rows * 7 + F)
+    x = rng.standard_normal((rows, F)).astype(np.float32)
+    x[0] = 0.0
+    if rows > 2:
+        x[2] *= 1e-20
+    R = rng.standard_normal((rows, F)).astype(np.float32)
+    xg = cuda(x).requires_grad_(True)
+    out = ops.l2_normalize(xg)
+    xo = torch.from_numpy(x).requires_grad_(True)
+    want = kops.normalize(xo, axis=-1, order=2)
+    close(out, want, msg="l2 normalize fwd")
+    (gx,) = torch.autograd.grad((out * cuda(R)).sum(), [xg])
+    (gw,) = torch.autograd.grad((want * torch.from_numpy(R)).sum(), [xo])
+    # rows whose norm is far below eps have gradients of 1e12 * g; compare row by row at the row's own scale
+    got, exp = gx.cpu().numpy(), gw.numpy()
+    for r in range(rows):
+        close(got[r], exp[r], msg=f"l2 normalize bwd row {r}")
+
+
 @pytest.mark.parametrize("rows,C", [(1, 2), (100, 47), (5000, 47), (3000, 7), (2000, 130), (700, 1000)])
 def test_softmax_cross_entropy(rows, C):
     from keras_geometric_b200 import ops
