@@ -377,6 +377,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-suite", action="store_true", help="skip the sum/max/GATv2/CSR-build kernel timings")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 (100 M nodes / 1 B edges) block")
+    ap.add_argument("--no-scramble", action="store_true",
+                    help="N > 1: partition the raw RMAT ids instead of hash-partitioning (scrambled ids)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

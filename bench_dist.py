@@ -23,7 +23,7 @@ def run(args, world, rank, local_rank):
     from bench import C4, RMAT, ClockSampler, build_model, cross_entropy, rmat_edge_index
     import bench_extra
     from keras_geometric_b200 import _lib, ops
-    from keras_geometric_b200.dist import PartitionedGraph, cost_balanced_bounds
+    from keras_geometric_b200.dist import PartitionedGraph, cost_balanced_bounds, scramble_ids
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -43,6 +43,10 @@ def run(args, world, rank, local_rank):
     e_global = cfg["edges"] // div * world // 2 * 2
     scale = cfg["rmat_scale"] - (div.bit_length() - 1) + (world - 1).bit_length()
     ei = rmat_edge_index(n_global, e_global, scale, 0, dev)   # every rank generates the same global list
+    if not args.no_scramble:
+        # hash partitioning: RMAT's hubs are its low ids, so contiguous ranges of the raw ids balance nodes or edges,
+        # never both, and every exchange waits for the slowest rank of that phase (dist.scramble_ids)
+        ei, _ = scramble_ids(ei, n_global)
     bounds = cost_balanced_bounds(ei[1], n_global, world, NODE_WEIGHT)
     lo, hi = bounds[rank], bounds[rank + 1]
     mine = (ei[1] >= lo) & (ei[1] < hi)
@@ -118,7 +122,7 @@ def run(args, world, rank, local_rank):
     pg.close()
     del pg, x, y, layers, params, opt
     torch.cuda.empty_cache()
-    c5 = bench_extra.c5_strong(world, rank, dev) if not args.no_c5 else None
+    c5 = bench_extra.c5_strong(world, rank, dev, scramble=not args.no_scramble) if not args.no_c5 else None
     if rank == 0:
         g = {}
         for rec in prof:
@@ -143,7 +147,7 @@ def run(args, world, rank, local_rank):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C4 x {world}: 3-layer SAGEConv(mean) 100->256->256->47, RMAT graph 1-D "
-                                   "node-partitioned (cost-balanced ranges), halo rows pushed into the receivers' "
+                                   "node-partitioned (" + ("raw RMAT ids, " if args.no_scramble else "ids scrambled = hash partitioning, ") + "cost-balanced ranges), halo rows pushed into the receivers' "
                                    "windows before every aggregation, overlapped with the local-source part of the "
                                    "aggregation and the weight-gradient GEMMs",
                        "nodes": n_global, "edges": e_global, "layers": n_layers, "rmat": list(RMAT), "seed": 0,

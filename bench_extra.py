@@ -116,7 +116,7 @@ def kernel_suite(dev, ei, n, traffic=None):
 
 
 # ------------------------------------------------------------------------------------------ C5 strong scaling
-def c5_strong(world, rank, dev, div=1, reps=3):
+def c5_strong(world, rank, dev, div=1, reps=3, scramble=True):
     """BASELINE configs[4]: N = 100 M, E = 1 B directed RMAT edges (scale 27), x [N, 64] fp32.
     One aggregation layer forward + backward for SAGE-mean and for the GCN-normalised sum (self-loops appended),
     1-D node-partitioned over `world` ranks with the halo exchange inside the timed region.  GTEPS = E_agg / t."""
@@ -166,6 +166,10 @@ def c5_strong(world, rank, dev, div=1, reps=3):
     else:
         # aggregation only, measured at 2 GPUs: 0.095 ms per M edges, 0.48 ms per M owned nodes (output rows of both
         # passes, landing of the returned gradients) -> one node weighs 5 edges
+        if scramble:   # hash partitioning (dist.scramble_ids): ranges balanced in nodes, edges and halo rows
+            from keras_geometric_b200.dist import scramble_ids
+            ei, _ = scramble_ids(ei, n)
+            res["workload"] += ", node ids scrambled before the contiguous split (hash partitioning)"
         bounds = cost_balanced_bounds(ei[1], n, world, node_weight=5.0)
         lo, hi = bounds[rank], bounds[rank + 1]
         mine = (ei[1] >= lo) & (ei[1] < hi)

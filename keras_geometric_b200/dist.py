@@ -16,8 +16,9 @@ target is local.  The conv layers accept a ``PartitionedGraph`` in place of ``ed
 
 Transport.  With CUDA tensors and more than one rank the halo rows do not go through NCCL send/recv: every rank
 owns a WINDOW of device memory that its peers map with CUDA IPC (``PeerWindow``), and the pack kernel
-(kgb_halo_push) stores each requested row straight into the receiver's window over NVLink.  Two tiny all-reduces on
-the communication stream order the ranks (window free / all rows landed).  ``KGB200_HALO=nccl`` (or a failed IPC
+(kgb_halo_push) stores each requested row straight into the receiver's window over NVLink.  One tiny all-reduce on
+the communication stream orders the ranks (all rows landed); the window is double-buffered so that no "window free"
+barrier is needed before the push.  ``KGB200_HALO=nccl`` (or a failed IPC
 mapping) selects ``all_to_all_single`` instead; the CPU tests use gloo for the plan logic.
 """
 from __future__ import annotations
@@ -63,6 +64,32 @@ def cost_balanced_bounds(dst_global: torch.Tensor, n_global: int, world: int, no
     for i in range(1, len(b)):
         b[i] = max(b[i], b[i - 1])
     return b
+
+
+def scramble_ids(edge_index: torch.Tensor, n_global: int, seed: int = 0x5eed, group=None):
+    """Hash partitioning for the contiguous 1-D split: relabel the nodes with a seeded random bijection (the same on
+    every rank: generated on rank 0, broadcast) and return ``(edge_index_new, perm)`` with ``perm[old id] = new id``.
+
+    Generators such as RMAT correlate the degree with the id (the hubs are the low ids), so contiguous ranges are
+    balanced either in nodes or in edges, never both - and the layers synchronise at every exchange, so the forward
+    gathers wait for the rank that owns the hubs and the dense transforms for the rank that owns most rows.  After
+    scrambling every range holds ~n/world nodes AND ~E/world edges and needs about the same number of halo rows
+    (Graph500 scrambles its RMAT ids for the same reason).  Features / labels must be indexed with the new ids:
+    ``x_new[perm] = x_old``."""
+    dev = edge_index.device
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    if rank == 0:
+        gen = torch.Generator(device=dev).manual_seed(int(seed))
+        perm = torch.randperm(int(n_global), device=dev, generator=gen).to(torch.int32)
+    else:
+        perm = torch.empty(int(n_global), dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.broadcast(perm, src=0, group=group)
+    out = torch.empty_like(edge_index)
+    for r in range(2):   # one row at a time: the int64 index temporary is 8 B per edge
+        out[r] = perm[edge_index[r].long()]
+    return out, perm
 
 
 class HaloPlan:
@@ -175,9 +202,17 @@ class _DeviceBytes:
 
 
 class PeerWindow:
-    """One symmetric window per rank: ``[halo region | back region]``, each ``rows x f_cap`` floats, allocated with
-    cudaMalloc by libkgb200 and mapped into every peer with CUDA IPC.  ``ptr[r]`` is rank r's window as seen from
-    THIS device (NVLink peer memory for r != rank)."""
+    """One symmetric window per rank: two copies ("phases") of ``[halo region | back region]``, each region
+    ``rows x f_cap`` floats, allocated with cudaMalloc by libkgb200 and mapped into every peer with CUDA IPC.
+    ``ptr[r]`` is rank r's window as seen from THIS device (NVLink peer memory for r != rank).
+
+    Consecutive exchanges of the same direction alternate between the two phases, which is what lets an exchange
+    start pushing WITHOUT first waiting for "every rank has consumed its previous rows": a rank writes phase p of
+    direction d at exchange k only after it has left the landed-barrier of exchange k-1, which every peer entered
+    after its communication stream waited for its compute stream at the start of exchange k-1 - i.e. after the peer
+    had finished reading the rows of the last exchange that used (d, p), two same-direction exchanges ago.  One
+    barrier per exchange (all rows landed) instead of two; an early rank's rows travel while the late ranks are
+    still computing."""
 
     def __init__(self, plan: HaloPlan, f_cap: int, device, group=None):
         """Collective.  Every stage that can fail locally is followed by a collective that all ranks reach, so a
@@ -190,7 +225,11 @@ class PeerWindow:
         self.tables = t
         row_bytes = 4 * self.f_cap
         self.back_off = [((t["n_halo_all"][r] * row_bytes + 255) // 256) * 256 for r in range(self.world)]
-        nbytes = self.back_off[self.rank] + max(t["n_send_all"][self.rank], 1) * row_bytes + 256
+        # bytes of one phase of rank r's window (every rank knows every rank's layout)
+        self.phase_stride = [((self.back_off[r] + max(t["n_send_all"][r], 1) * row_bytes + 255) // 256) * 256
+                             for r in range(self.world)]
+        self._phase = {True: 0, False: 0}     # next phase of the forward / backward direction
+        nbytes = 2 * self.phase_stride[self.rank] + 256
         self.nbytes = nbytes
         self.base, self.ptr, self._opened, self.error = None, [], [], None
         raw = None
@@ -229,16 +268,23 @@ class PeerWindow:
         """Orders the ranks on the CURRENT stream (a one-element all-reduce; stream-ordered like every collective)."""
         dist.all_reduce(self._flag, group=self.group)
 
-    def halo_view(self, n_rows: int, F: int) -> torch.Tensor:
-        return self.local[:max(n_rows, 1) * F * 4].view(torch.float32).view(max(n_rows, 1), F)
+    def next_phase(self, forward: bool) -> int:
+        """Phase of the exchange that starts now in this direction (same sequence on every rank); toggles it."""
+        ph = self._phase[forward]
+        self._phase[forward] = ph ^ 1
+        return ph
 
-    def back_view(self, n_rows: int, F: int) -> torch.Tensor:
-        o = self.back_off[self.rank]
+    def halo_view(self, n_rows: int, F: int, phase: int = 0) -> torch.Tensor:
+        o = phase * self.phase_stride[self.rank]
         return self.local[o:o + max(n_rows, 1) * F * 4].view(torch.float32).view(max(n_rows, 1), F)
 
-    def push_args(self, F: int, forward: bool):
+    def back_view(self, n_rows: int, F: int, phase: int = 0) -> torch.Tensor:
+        o = phase * self.phase_stride[self.rank] + self.back_off[self.rank]
+        return self.local[o:o + max(n_rows, 1) * F * 4].view(torch.float32).view(max(n_rows, 1), F)
+
+    def push_args(self, F: int, forward: bool, phase: int = 0):
         """Destination table (``kgb_halo_push_args`` without a source): forward = my rows -> peers' halo regions,
-        else my halo-row gradients -> their owners' back regions.  Rows in the window are dense (ld = F)."""
+        else my halo-row gradients -> their owners' back regions, of the given phase.  Rows are dense (ld = F)."""
         from . import _lib
         t = self.tables
         a = _lib.HaloPushArgs()
@@ -248,17 +294,17 @@ class PeerWindow:
         for p in range(self.world + 1):
             a.slot_begin[p] = begin[p]
         for p in range(self.world):
-            a.dst[p] = self.ptr[p] + (0 if forward else self.back_off[p])
+            a.dst[p] = self.ptr[p] + phase * self.phase_stride[p] + (0 if forward else self.back_off[p])
             a.dst_row0[p] = row0[p]
         a.ldd = F
         a.slot_rot = begin[(self.rank + 1) % self.world]   # stagger the receivers across the ranks
         return a
 
-    def push(self, src: torch.Tensor, idx, F: int, forward: bool) -> None:
+    def push(self, src: torch.Tensor, idx, F: int, forward: bool, phase: int = 0) -> None:
         """kgb_halo_push on the CURRENT stream (pack + store into the peers' windows)."""
         from . import _lib
         from .graph import _stream
-        a = self.push_args(F, forward)
+        a = self.push_args(F, forward, phase)
         a.src, a.lds, a.idx = src.data_ptr(), src.stride(0), (idx.data_ptr() if idx is not None else None)
         _lib.check(self.lib.kgb_halo_push(self.device.index, ctypes.byref(a), _stream(self.device)), "kgb_halo_push")
 
@@ -416,19 +462,18 @@ class PartitionedGraph:
 
     def halo_rows_raw(self, x_local: torch.Tensor) -> torch.Tensor:
         """pack + exchange on the CURRENT stream: [n_local, F] -> [n_halo, F].  With the peer-memory transport the
-        result is a view of this rank's window: valid until the next forward exchange on this graph."""
+        result is a view of this rank's window: valid until the second-next forward exchange on this graph."""
         from . import ops
         p = self.plan
         F = int(x_local.shape[1])
         win = self._p2p_window(F)
         if win is not None:
-            with ops._prof("halo_wait_pre", 0, self.device):
-                win.barrier()                               # every rank has consumed its previous halo rows
+            ph = win.next_phase(True)                       # no "window free" barrier: see PeerWindow
             with ops._prof(f"halo_push_fwd_F{F}", p.n_send * F * 4, self.device):
-                win.push(x_local, p.send_idx if p.n_send else None, F, forward=True)
+                win.push(x_local, p.send_idx if p.n_send else None, F, forward=True, phase=ph)
             with ops._prof("halo_wait_post", 0, self.device):
                 win.barrier()                               # every rank's rows have landed
-            return win.halo_view(self.n_halo, F)
+            return win.halo_view(self.n_halo, F, ph)
         halo = torch.empty((max(self.n_halo, 1), F), dtype=x_local.dtype, device=x_local.device)
         send = ops.gather_rows(x_local, p.send_idx) if p.n_send else x_local.new_empty((0, F))
         dist.all_to_all_single(halo[:self.n_halo], send, output_split_sizes=p.recv_counts,
@@ -438,19 +483,18 @@ class PartitionedGraph:
     def halo_grad_raw(self, g_halo: torch.Tensor) -> torch.Tensor:
         """reverse exchange on the CURRENT stream: [n_halo, F] gradient rows -> [n_send, F] rows at their owners
         (to be summed per owner row with ``send_csr``).  Peer-memory transport: a view of this rank's window, valid
-        until the next backward exchange on this graph."""
+        until the second-next backward exchange on this graph."""
         p = self.plan
         F = int(g_halo.shape[1])
         win = self._p2p_window(F)
         if win is not None:
             from . import ops
-            with ops._prof("halo_wait_pre", 0, self.device):
-                win.barrier()
+            ph = win.next_phase(False)
             with ops._prof(f"halo_push_bwd_F{F}", self.n_halo * F * 4, self.device):
-                win.push(g_halo, None, F, forward=False)
+                win.push(g_halo, None, F, forward=False, phase=ph)
             with ops._prof("halo_wait_post", 0, self.device):
                 win.barrier()
-            return win.back_view(p.n_send, F)
+            return win.back_view(p.n_send, F, ph)
         back = torch.empty((max(p.n_send, 1), F), dtype=g_halo.dtype, device=g_halo.device)
         dist.all_to_all_single(back[:p.n_send], g_halo[:self.n_halo], output_split_sizes=p.send_counts,
                                input_split_sizes=p.recv_counts, group=self.group)
@@ -470,16 +514,15 @@ class PartitionedGraph:
         if win is None:
             g_halo, _ = ops.gather_reduce_raw(g, g_h.csc, _lib.OP_SUM, src_scale=tgt_scale, out_scale=halo_scale)
             return self.halo_grad_raw(g_halo)
-        with ops._prof("halo_wait_pre", 0, self.device):
-            win.barrier()                                   # every owner has consumed its previous back rows
+        ph = win.next_phase(False)
         if self.n_halo:
-            args = win.push_args(F, forward=False)
+            args = win.push_args(F, forward=False, phase=ph)
             dummy = self._dummy_row(F)
             ops.gather_reduce_raw(g, g_h.csc, _lib.OP_SUM, src_scale=tgt_scale, out_scale=halo_scale, out=dummy,
                                   out2_push=args, n_split_out=0, label="halo_grad_push")
         with ops._prof("halo_wait_post", 0, self.device):
             win.barrier()                                   # every rank's rows have landed
-        return win.back_view(self.plan.n_send, F)
+        return win.back_view(self.plan.n_send, F, ph)
 
     def land_into(self, back: torch.Tensor, acc: torch.Tensor) -> torch.Tensor:
         """acc[r] += sum of the returned gradient rows of owned row r, IN PLACE, for the rows some peer asked for

@@ -145,3 +145,30 @@ def test_partition_bounds():
     assert partition_bounds(10, 3) == [0, 4, 7, 10]
     assert partition_bounds(2, 4) == [0, 1, 2, 2, 2]
     assert partition_bounds(0, 2) == [0, 0, 0]
+
+
+def test_scramble_ids_is_a_bijection_and_balances_rmat_ranges():
+    """dist.scramble_ids (hash partitioning): a seeded bijection applied to both endpoint rows; after it the
+    cost-balanced contiguous ranges of an RMAT graph hold about the same number of nodes AND edges."""
+    import sys
+    sys.path.insert(0, ROOT) if ROOT not in sys.path else None
+    from bench import rmat_edge_index
+    from keras_geometric_b200.dist import cost_balanced_bounds, scramble_ids
+    n, e, world = 1 << 14, 400_000, 8
+    ei = rmat_edge_index(n, e, 14, 3, torch.device("cpu"))
+    ei2, perm = scramble_ids(ei, n, seed=7)
+    assert sorted(perm.tolist()) == list(range(n))
+    assert torch.equal(ei2, perm[ei.long()]) and ei2.dtype == ei.dtype
+    ei3, perm3 = scramble_ids(ei, n, seed=7)
+    assert torch.equal(perm, perm3) and torch.equal(ei2, ei3)          # reproducible
+
+    def spread(edges):
+        b = cost_balanced_bounds(edges[1], n, world, node_weight=28.0)
+        nodes = [b[r + 1] - b[r] for r in range(world)]
+        cnt = [int(((edges[1] >= b[r]) & (edges[1] < b[r + 1])).sum()) for r in range(world)]
+        return max(nodes) / max(min(nodes), 1), max(cnt) / max(min(cnt), 1)
+
+    raw_nodes, raw_edges = spread(ei)
+    scr_nodes, scr_edges = spread(ei2)
+    assert scr_nodes < 1.3 and scr_edges < 1.3, (scr_nodes, scr_edges)
+    assert raw_edges > 2.0 or raw_nodes > 2.0, (raw_nodes, raw_edges)   # what the scrambling removes
