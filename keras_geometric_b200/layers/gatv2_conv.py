@@ -88,8 +88,6 @@ class GATv2Conv(MessagePassing):
             x = x.to(torch.float32)
         if bool(pg._n_loops) != bool(self.add_self_loops_flag):
             raise ValueError("PartitionedGraph(n_loops_local=...) must match GATv2Conv(add_self_loops=...)")
-        if self.dropout_layer is not None and training:
-            raise NotImplementedError("partitioned GATv2Conv does not support attention dropout")
         if self.linear_transform is None or self.att is None:
             self.build(tuple(x.shape))
             self.built = True
@@ -99,7 +97,12 @@ class GATv2Conv(MessagePassing):
         att = value_of(self.att)
         bias = value_of(self.bias) if (self.use_bias and self.bias is not None) else None
         fuse_bias = bias is not None and (self.concat or H == 1)
-        out = ops.gatv2_aggregate(h_ext, h, att, pg.graph, H, C, self.negative_slope, bias if fuse_bias else None)
+        # attention dropout (training): the fused kernels draw one Philox decision per (local edge id, head); forward and
+        # both backward passes regenerate it, exactly as on one GPU (the mask itself differs from a 1-GPU run's - the
+        # edge ids are rank-local - which no reference fixes either)
+        drop = float(self.dropout_rate) if (self.dropout_layer is not None and training) else 0.0
+        out = ops.gatv2_aggregate(h_ext, h, att, pg.graph, H, C, self.negative_slope, bias if fuse_bias else None,
+                                  dropout=drop)
         if not self.concat and H > 1:
             out = out.reshape(n, H, C).mean(dim=1)
             if bias is not None:

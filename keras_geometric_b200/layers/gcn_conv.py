@@ -155,21 +155,23 @@ class GCNConv(MessagePassing):
     def _call_partitioned(self, x, pg, training=None):
         """1-D node partition: transform locally, exchange the (narrow) transformed halo rows, aggregate.
         ``pg`` must have been built with ``n_loops_local=self.add_self_loops``."""
-        if self.dropout_rate > 0 and training:
-            raise NotImplementedError("partitioned GCNConv does not support message dropout")
         if bool(pg._n_loops) != bool(self.add_self_loops):
             raise ValueError("PartitionedGraph(n_loops_local=...) must match GCNConv(add_self_loops=...)")
         kernel, bias = value_of(self.kernel), value_of(self.bias) if self.use_bias else None
         h = ops.linear(x, kernel)
-        if pg.world > 1 and pg.any_halo:
+        dropping = self.dropout_rate > 0 and bool(training)     # the same on every rank: the path choice stays uniform
+        if pg.world > 1 and pg.any_halo and not dropping:
             # local-source edges (and the self-loops) are reduced while the transformed halo rows are in flight
             return ops.aggregate_partitioned(h, pg, "gcn" if self.normalize else "sum", bias=bias)
+        # training with message dropout (gcn_conv.py:238-242): the [local | halo] source space, where the fused gather
+        # draws the element-wise Philox mask from the rank-local edge id (regenerated by the transposed pass)
         h_ext = pg.exchange(h)
         weight = None
         if self.normalize:
             dis_local, dis_ext = pg.gcn_dis_ext()
             weight = (dis_ext, dis_local)
-        return ops.gather_reduce(h_ext, pg.graph, "sum", weight=weight, bias=bias)
+        return ops.gather_reduce(h_ext, pg.graph, "sum", weight=weight, bias=bias,
+                                 dropout=float(self.dropout_rate) if dropping else 0.0)
 
     def _canonical_cached(self, edge_index):
         key = (id(edge_index), getattr(edge_index, "_version", None))

@@ -225,8 +225,7 @@ class SAGEConv(MessagePassing):
         if not self.built:
             self.build([tuple(x.shape), (2, 0)])
             self.built = True
-        if self.dropout_rate > 0 and training:
-            raise NotImplementedError("partitioned SAGEConv does not support dropout")
+        dropping = self.dropout_rate > 0 and bool(training)     # the same on every rank: the path choice stays uniform
         w_neigh = value_of(self.lin_neigh.kernel)
         w_self = value_of(self.lin_self.kernel) if (self.root_weight and self.lin_self is not None) else None
         bias = value_of(self.bias) if (self.use_bias and self.bias is not None) else None
@@ -234,6 +233,27 @@ class SAGEConv(MessagePassing):
         act_is_none = self._activation_id in (None, "linear")
         linear_agg = self.actual_aggregator in ("mean", "sum")
         fuse_act = act_is_relu or act_is_none
+        if dropping:
+            # training with dropout (sage_conv.py:295-297, 411-433): the [local | halo] source space.  mean / sum drop
+            # the gathered rows inside the fused gather (Philox on the rank-local edge id, regenerated by the
+            # transposed pass); the other aggregators drop explicit per-edge messages like the reference
+            src = x
+            x_ext = pg.exchange(src)
+            agg_name = self.actual_aggregator
+            if agg_name in ("mean", "sum"):
+                aggregated = ops.gather_reduce(x_ext, pg.graph, agg_name, dropout=float(self.dropout_rate))
+            else:
+                x_j = Dropout(self.dropout_rate)(ops.take_rows(x_ext, pg.graph, "src"), training=True)
+                if agg_name == "pooling":
+                    x_j = apply_dense(self.pool_mlp, x_j)
+                if agg_name == "std":
+                    aggregated = ops.segment_std(x_j, pg.graph)
+                else:
+                    aggregated = ops.segment_reduce(x_j, pg.graph, "max" if agg_name == "pooling" else agg_name)
+            out = self._dense_update(aggregated, x, w_neigh, w_self, bias, dropping=True)
+            if self.normalize:
+                out = ops.l2_normalize(out, 1e-12)
+            return out
         if linear_agg and pg.world > 1 and pg.any_halo:   # rank-uniform choice of the path (collectives stay matched)
             # local-source edges are reduced while the halo rows are in flight; the halo part is added on top
             g_local, g_halo, inv_deg = pg.split

@@ -52,6 +52,64 @@ for name, mk, loops in [("sage_mean_reorder", lambda: SAGEConv(12, aggregator="m
     chk(out, out_full[lo:hi], "out"); chk(g[0], gfull[0][lo:hi], "grad_x")
     for i, (a, b_) in enumerate(zip(gw, gfull[1:])): chk(a, b_, f"grad_w{i}")
     if rank == 0: print(name, "checked; halo rows", pg.n_halo, "send", pg.plan.n_send)
+
+# ---- training dropout on the partitioned paths -----------------------------------------------------------------
+# The masks depend on rank-local edge ids, so there is no 1-GPU result to compare with.  Checked instead, per layer:
+#   (1) with the seed pinned the layer is a deterministic function: two calls agree bit for bit;
+#   (2) forward and backward use the SAME mask, across the exchange: the directional derivative of sum(out * R) along
+#       a random direction d (central difference, summed over ranks) equals <grad_x, d>;
+#   (3) (layers linear in x) the mean over 64 draws approaches the inference output: dropout is unbiased.
+from keras_geometric_b200 import ops as _ops
+for name, mk, loops, linear in [("sage_mean_dropout", lambda: SAGEConv(64, aggregator="mean", activation=None, dropout_rate=0.4), False, True),
+                                ("sage_max_dropout", lambda: SAGEConv(64, aggregator="max", activation=None, dropout_rate=0.4), False, False),
+                                ("gcn_dropout", lambda: GCNConv(12, dropout_rate=0.4), True, True),
+                                ("gatv2_dropout", lambda: GATv2Conv(16, heads=4, dropout=0.4), True, False)]:
+    torch.manual_seed(7)
+    layer = mk()
+    pg = PartitionedGraph(torch.from_numpy(ei[0][mine]).cuda(), torch.from_numpy(ei[1][mine]).cuda(), n, rank, world,
+                          n_loops_local=loops)
+    xl = torch.from_numpy(x[lo:hi]).cuda()
+    real_seed = _ops.next_dropout_seed
+
+    def run(xin, seed=1234):
+        _ops.next_dropout_seed = lambda: seed          # pin the in-kernel Philox stream ...
+        torch.manual_seed(99)                          # ... and torch's (SAGE drops the root input with it)
+        try:
+            return layer([xin, pg], training=True)
+        finally:
+            _ops.next_dropout_seed = real_seed
+
+    xr = xl.clone().requires_grad_(True)
+    o1 = run(xr)
+    Rl = torch.from_numpy(R[o1.shape[1]] if o1.shape[1] in R else rng.standard_normal((n, o1.shape[1])).astype(np.float32)).cuda()[lo:hi]
+    (gx,) = torch.autograd.grad((o1 * Rl).sum(), [xr])
+    o2 = run(xl)
+    if not torch.equal(o1.detach(), o2):
+        ok = False; print(f"[rank {rank}] {name}: pinned seed is not deterministic")
+    if not bool(torch.isfinite(o1).all()) or not bool(torch.isfinite(gx).all()):
+        ok = False; print(f"[rank {rank}] {name}: non-finite values")
+    d = torch.from_numpy(rng.standard_normal((n, fin)).astype(np.float32)).cuda()[lo:hi]
+    eps = 1e-4 if "max" in name else 1e-2   # max is piecewise linear: a large step crosses too many argmax switches
+    fd = ((run(xl + eps * d).double() * Rl).sum() - (run(xl - eps * d).double() * Rl).sum()) / (2 * eps)
+    an = (gx.double() * d).sum()
+    both = torch.stack([fd, an]); dist.all_reduce(both)
+    rel = abs(float(both[0] - both[1])) / (abs(float(both[1])) + 1e-30)
+    if rel > (2e-3 if linear else 3e-2):
+        ok = False; print(f"[rank {rank}] {name}: directional derivative {float(both[0]):.6g} vs <grad, d> {float(both[1]):.6g}")
+    if linear:
+        ref_out = layer([xl, pg], training=False)
+        acc = torch.zeros_like(ref_out)
+        for s_ in range(64):
+            _ops.next_dropout_seed = lambda s_=s_: 1000 + s_
+            torch.manual_seed(1000 + s_)
+            acc += layer([xl, pg], training=True)
+        _ops.next_dropout_seed = real_seed
+        bias_err = float((acc / 64 - ref_out).abs().mean() / ref_out.abs().mean())
+        if bias_err > 0.15:
+            ok = False; print(f"[rank {rank}] {name}: mean over 64 draws is off by {bias_err:.3f}")
+    if rank == 0: print(name, "checked; fd vs grad rel diff %.2e" % rel)
+    pg.close()
+
 flag = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0: print("DIST_CHECK", "PASS" if int(flag) else "FAIL")
 dist.destroy_process_group()
