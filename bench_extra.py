@@ -27,7 +27,7 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _time(fn, reps=5, warm=3):
+def _time(fn, reps=10, warm=3):
     """median CUDA-event time of fn() in ms on the current stream"""
     for _ in range(warm):
         fn()
@@ -69,10 +69,10 @@ def kernel_suite(dev, ei, n, traffic=None):
     def build_csr():
         holder["g"] = GraphStructure(ei, n, n, 0)
 
-    ms = _time(build_csr, reps=3, warm=1)
+    ms = _time(build_csr, reps=10, warm=2)
     rec("csr_build", build_bytes, ms, note="kgb_csr_build + hub table + one host sync (status, hub counts)")
     graph = holder["g"]
-    ms = _time(lambda: graph.__setattr__("_csc", None) or graph.csc, reps=3, warm=1)
+    ms = _time(lambda: graph.__setattr__("_csc", None) or graph.csc, reps=10, warm=2)
     rec("csc_build", build_bytes, ms)
     gen = torch.Generator(device=dev).manual_seed(11)
     gtep = {}
