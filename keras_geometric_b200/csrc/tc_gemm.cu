@@ -60,6 +60,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// bulk tensor store / add-reduce of one {32 cols, 32 rows, 1} box from shared memory into a 3-D fp32 tensor
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -567,8 +580,10 @@ struct DwCfg {
   static constexpr int G_BYTES = BN * DW_R * 4;         // BN * 64 B
   static constexpr int HALF = X_BYTES + G_BYTES;        // raw (hi) tiles; the lo tiles follow
   static constexpr int STAGE_BYTES = 2 * HALF;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 6 ? 6 : (192 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_TILE = 32 * 32 * 4;            // one 32 x 32 fp32 tile of the drain (128-byte swizzled rows)
+  static constexpr int EPI_BYTES = 4 * 2 * EPI_TILE;      // two tiles per epilogue warp: one fills while one drains
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 };
 
 // MN-major descriptor for 32-bit operands: the only legal swizzle is SWIZZLE_128B_BASE32B (layout type 1): atoms of
@@ -581,13 +596,15 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lb
 
 template <int BN, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const DwParams p) {
+tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
+             const __grid_constant__ CUtensorMap map_p, const DwParams p) {
   using Cfg = DwCfg<BN, MT>;
   constexpr int S = Cfg::STAGES;
   constexpr int BOX = 32 * DW_R * 4;  // 2 KB per TMA box
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
+  float* stage_all = reinterpret_cast<float*>(smem + S * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full = bars;
   uint64_t* lo_rdy = bars + S;
   uint64_t* empty = bars + 2 * S;
@@ -611,7 +628,12 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
     mbar_init(tempty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const int n_chains = (kblocks + p.chain_blocks - 1) / p.chain_blocks;
+  // The chain boundaries are staggered across the CTAs (the first chain of CTA b is shorter by chain_off k-blocks):
+  // with identical boundaries all 148 CTAs drain 256 KB each into the L2 in the same few microseconds and the drain
+  // runs at the L2's aggregate fp32-add rate (38 MB per burst); spread over the chain period each CTA's drain only
+  // sees its own share.  The offsets are a function of blockIdx: the result stays deterministic.
+  const int chain_off = p.chain_blocks > 1 ? (int)((blockIdx.x * 5u) % (unsigned)p.chain_blocks) : 0;
+  const int n_chains = kblocks > 0 ? (kblocks + chain_off + p.chain_blocks - 1) / p.chain_blocks : 0;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
                  "r"(TMEM_COLS));
@@ -645,8 +667,9 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
       for (int kb = 0; kb < kblocks; ++kb) {
         const int s = kb % S;
         const uint32_t ph = (kb / S) & 1;
-        const int chain = kb / p.chain_blocks, kc = kb % p.chain_blocks;
-        if (kc == 0) {  // new accumulation chain: the epilogue must have drained the previous one
+        const int chain = (kb + chain_off) / p.chain_blocks, kc = (kb + chain_off) % p.chain_blocks;
+        const bool first_kb = (kb == 0) || (kc == 0);
+        if (first_kb) {  // new accumulation chain: the epilogue must have drained the previous one
           mbar_wait(tempty, (chain & 1) ^ 1);
           tc_fence_after();
         }
@@ -663,7 +686,7 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
             const uint64_t xa_hi = make_desc_mn(hi + mt * 4 * BOX + ks * 1024, BOX, 512);
             const uint64_t xa_lo = make_desc_mn(lo + mt * 4 * BOX + ks * 1024, BOX, 512);
             const uint32_t tc = tmem_base + mt * BN;
-            umma_tf32(tc, xa_lo, gb_hi, idesc, (kc | ks) != 0);
+            umma_tf32(tc, xa_lo, gb_hi, idesc, !(first_kb && ks == 0));
             umma_tf32(tc, xa_hi, gb_lo, idesc, 1);
             umma_tf32(tc, xa_hi, gb_hi, idesc, 1);
           }
@@ -696,64 +719,74 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
       if (lane == 0) mbar_arrive(lo_rdy + s);
     }
   } else {
-    // epilogue: after every chain, partial (+)= accumulator with IEEE fp32 adds; a CTA without nodes writes zeros
+    // epilogue: after every chain, partial (+)= accumulator with IEEE fp32 adds; a CTA without nodes writes zeros.
+    // TMEM is full at 256 x 256, so the MMAs of the next chain wait for this drain.  Draining with per-thread
+    // red.global.add.v4 cost 10.7 us per chain (16 k half-filled sector transactions through the LSU; 34 % of the
+    // kernel), through a shared transpose with coalesced reds 7.7 us.  Here the epilogue warps only move TMEM ->
+    // registers -> a 128-byte-swizzled shared tile and hand each 32 x 32 tile to the TMA engine as ONE bulk tensor
+    // add-reduce (cp.reduce.async.bulk.tensor, performed at the L2: IEEE fp32 adds, one writer per address); the
+    // accumulator is released as soon as it has been read, the bulk operations finish behind the next chain's MMAs.
+    // Order of the adds = chain order: every drain first waits for the complete retirement of the previous one.
     const int q = warp & 3;
-    float* out = p.partial + (int64_t)blockIdx.x * p.Kx * p.N;
+    uint8_t* stg_base = reinterpret_cast<uint8_t*>(stage_all) + q * 2 * Cfg::EPI_TILE;
     const int passes = n_chains > 0 ? n_chains : 1;
+    uint32_t n_issued = 0;   // tiles this warp has handed to the TMA so far (selects the staging tile)
 #pragma unroll 1
     for (int chain = 0; chain < passes; ++chain) {
       if (n_chains > 0) {
         mbar_wait(tfull, chain & 1);
         tc_fence_after();
       }
+      if (chain > 0) {   // the previous chain's stores / adds to the same addresses are complete and visible
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
-        const int row = mt * 128 + q * 32 + lane;  // feature index kx
+        const int row0 = mt * 128 + q * 32;  // first feature row (kx) of this warp's TMEM lanes
+        if (row0 >= p.Kx) break;             // rows past Kx do not exist in the partial (their TMEM lanes are padding)
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           if (c0 >= p.N) break;
           uint32_t r[32];
           if (n_chains > 0) {
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + mt * BN + c0));
+            KGB_TMEM_LD32(r, tmem_base + ((uint32_t)(q * 32) << 16) + mt * BN + c0);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = 0u;
           }
-          if (row < p.Kx) {
-            float* drow = out + (int64_t)row * p.N + c0;
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              if (c0 + v * 4 >= p.N) break;
-              const float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                           __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
-              if (chain > 0) {
-                // fire-and-forget fp32 add performed at the L2 (IEEE add, single writer per address => deterministic);
-                // no load sits on the drain's critical path
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + v * 4), "f"(o.x), "f"(o.y),
-                             "f"(o.z), "f"(o.w)
-                             : "memory");
-              } else {
-                *reinterpret_cast<float4*>(drow + v * 4) = o;
-              }
-            }
+          float* stg = reinterpret_cast<float*>(stg_base + (n_issued & 1u) * Cfg::EPI_TILE);
+          if (n_issued >= 2) {   // the bulk operation that last read this tile has finished reading it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
           }
+          // row `lane` of the tile, 16-byte chunk v at position v ^ (lane & 7): the TMA's 128-byte swizzle (and
+          // conflict-free for the eight lanes of a quarter warp)
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((v ^ (lane & 7)) << 2)) =
+                make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                            __uint_as_float(r[4 * v + 3]));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> bulk-copy reads
+          __syncwarp();
+          if (lane == 0) {
+            // columns past N and rows past Kx of the box are clipped by the tensor map
+            if (chain > 0) tma_reduce_add_3d(&map_p, stg, c0, row0, (int)blockIdx.x);
+            else tma_store_3d(&map_p, stg, c0, row0, (int)blockIdx.x);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++n_issued;
         }
       }
-      if (n_chains > 0) {
+      if (n_chains > 0) {   // the accumulator has been read out: the next chain may start
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty);
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // nothing in flight at kernel exit
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -857,8 +890,30 @@ static int tc2_launch(int device, const CUtensorMap& ma, const CUtensorMap& ma2,
   return KGB_OK;
 }
 
+// the per-CTA partials [n_parts, Kx, N] as a 3-D fp32 tensor, box = {32 cols, 32 rows, 1}, 128B swizzle (the drain's
+// bulk stores / add-reduces; columns past N and rows past Kx of a box are clipped)
+static int make_map_partials(CUtensorMap* m, float* base, int64_t n_parts, int64_t Kx, int64_t N) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return KGB_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)Kx, (cuuint64_t)n_parts};
+  cuuint64_t strides[2] = {(cuuint64_t)N * sizeof(float), (cuuint64_t)Kx * (cuuint64_t)N * sizeof(float)};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (partials) failed (%d) parts=%lld Kx=%lld N=%lld", (int)r, (long long)n_parts,
+              (long long)Kx, (long long)N);
+    return KGB_ERR_CUDA;
+  }
+  return KGB_OK;
+}
+
 template <int BN, int MT>
-static int dw_launch(int device, const CUtensorMap& mx, const CUtensorMap& mg, const DwParams& p, int grid,
+static int dw_launch(int device, const CUtensorMap& mx, const CUtensorMap& mg, const CUtensorMap& mp, const DwParams& p, int grid,
                      cudaStream_t st) {
   using Cfg = DwCfg<BN, MT>;
   static bool attr_done[64] = {};
@@ -866,7 +921,7 @@ static int dw_launch(int device, const CUtensorMap& mx, const CUtensorMap& mg, c
     KGB_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done[device] = true;
   }
-  tc_dw_kernel<BN, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mg, p);
+  tc_dw_kernel<BN, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mg, mp, p);
   KGB_CHECK_LAUNCH();
   return KGB_OK;
 }
@@ -898,15 +953,23 @@ int kgb_linear_tc_dw(int device, const float* X, int64_t ldx, const float* G, in
   if (rc != KGB_OK) return rc;
   rc = make_map(&mg, G, M, N, ldg, DW_R, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc != KGB_OK) return rc;
+  CUtensorMap mp;
+  rc = make_map_partials(&mp, partials, n_parts, Kx, N);
+  if (rc != KGB_OK) return rc;
   DwParams p;
   p.M = M; p.Kx = Kx; p.N = N; p.partial = partials;
   const int64_t blocks = (M + DW_R - 1) / DW_R;
   p.nodes_per_cta = (int)(((blocks + n_parts - 1) / n_parts) * DW_R);
   p.chain_blocks = 256 / DW_R;  // promote the TMEM sum to fp32 memory every 256 nodes
+  {
+    // timing experiments only (tools/exp_tc.py): longer chains lose fp32 parity, see the kernel's header comment
+    static const int chain_nodes = [] { const char* e = getenv("KGB200_DW_CHAIN"); return e ? atoi(e) : 0; }();
+    if (chain_nodes >= DW_R) p.chain_blocks = chain_nodes / DW_R;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
   const int MT = Kx <= 128 ? 1 : 2;
-#define KGB_DW_CASE(BN_, MT_) if (BN == BN_ && MT == MT_) return dw_launch<BN_, MT_>(device, mx, mg, p, n_parts, st);
+#define KGB_DW_CASE(BN_, MT_) if (BN == BN_ && MT == MT_) return dw_launch<BN_, MT_>(device, mx, mg, mp, p, n_parts, st);
   KGB_DW_CASE(64, 1) KGB_DW_CASE(64, 2) KGB_DW_CASE(128, 1) KGB_DW_CASE(128, 2) KGB_DW_CASE(256, 1) KGB_DW_CASE(256, 2)
 #undef KGB_DW_CASE
   return KGB_ERR_UNSUPPORTED;
