@@ -28,6 +28,11 @@ def run(args, world, rank, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=dev)
+    # the partitioned autograd nodes run parts of their backward on the communication stream on purpose (and order
+    # the streams themselves); torch's per-step warning about it would bury the log
+    quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+    if quiet is not None:
+        quiet(False)
     lib = _lib.load()
 
     parity = bench_extra.parity_check(world, rank, dev)      # partitioned layers vs the CPU oracle (rank 0's host)
