@@ -402,6 +402,13 @@ int kgb_linear_tc2(int device, const float* A1, int64_t lda1, int32_t K1, const 
 int32_t kgb_linear_tc_dw_parts(int device, int64_t M);
 int kgb_linear_tc_dw(int device, const float* X, int64_t ldx, const float* G, int64_t ldg, int32_t M, int32_t Kx,
                      int32_t N, float* partials, int32_t n_parts, kgb_stream_t stream);
+/* Two weight gradients that share X in one pass: partials[p] = X^T [G1 | 0.. | G2] with G2 starting at column
+ * ceil32(N1) (kgb_linear_tc_dw2_cols(N1, N2) columns in total, <= 256) - X is loaded and split once for both.
+ * SAGEConv's lin_neigh / lin_self gradients when the layer aggregates after the transform (sage_conv.py:201-221). */
+int32_t kgb_linear_tc_dw2_cols(int32_t N1, int32_t N2);
+int kgb_linear_tc_dw2(int device, const float* X, int64_t ldx, const float* G1, int64_t ldg1, int32_t N1, const float* G2,
+                      int64_t ldg2, int32_t N2, int32_t M, int32_t Kx, float* partials, int32_t n_parts,
+                      kgb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -571,6 +571,7 @@ struct DwParams {
   int M, Kx, N;
   int nodes_per_cta;
   int chain_blocks;  // k-blocks (of DW_R nodes) accumulated in TMEM before the sum is promoted to fp32 in memory
+  int g2_box0;       // first 32-column box of the G tile that is loaded from the SECOND gradient operand (>= BN/32: none)
   float* partial;    // [gridDim.x, Kx, N]
 };
 
@@ -597,7 +598,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lb
 template <int BN, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
-             const __grid_constant__ CUtensorMap map_p, const DwParams p) {
+             const __grid_constant__ CUtensorMap map_g2, const __grid_constant__ CUtensorMap map_p, const DwParams p) {
   using Cfg = DwCfg<BN, MT>;
   constexpr int S = Cfg::STAGES;
   constexpr int BOX = 32 * DW_R * 4;  // 2 KB per TMA box
@@ -656,7 +657,12 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
 #pragma unroll
         for (int b = 0; b < MT * 4; ++b) tma_load_2d(base + b * BOX, &map_x, full + s, b * 32, row);
 #pragma unroll
-        for (int b = 0; b < BN / 32; ++b) tma_load_2d(base + Cfg::X_BYTES + b * BOX, &map_g, full + s, b * 32, row);
+        for (int b = 0; b < BN / 32; ++b) {
+          // two gradient operands that share X (dW_a = X^T G1, dW_b = X^T G2): their column boxes sit side by side
+          // in ONE G tile, so X is loaded and split once for both products
+          if (b < p.g2_box0) tma_load_2d(base + Cfg::X_BYTES + b * BOX, &map_g, full + s, b * 32, row);
+          else tma_load_2d(base + Cfg::X_BYTES + b * BOX, &map_g2, full + s, (b - p.g2_box0) * 32, row);
+        }
       }
     }
   } else if (warp == 1) {
@@ -913,7 +919,8 @@ static int make_map_partials(CUtensorMap* m, float* base, int64_t n_parts, int64
 }
 
 template <int BN, int MT>
-static int dw_launch(int device, const CUtensorMap& mx, const CUtensorMap& mg, const CUtensorMap& mp, const DwParams& p, int grid,
+static int dw_launch(int device, const CUtensorMap& mx, const CUtensorMap& mg, const CUtensorMap& mg2, const CUtensorMap& mp,
+                     const DwParams& p, int grid,
                      cudaStream_t st) {
   using Cfg = DwCfg<BN, MT>;
   static bool attr_done[64] = {};
@@ -921,7 +928,7 @@ static int dw_launch(int device, const CUtensorMap& mx, const CUtensorMap& mg, c
     KGB_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done[device] = true;
   }
-  tc_dw_kernel<BN, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mg, mp, p);
+  tc_dw_kernel<BN, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mg, mg2, mp, p);
   KGB_CHECK_LAUNCH();
   return KGB_OK;
 }
@@ -940,20 +947,19 @@ int32_t kgb_linear_tc_dw_parts(int device, int64_t M) {
   return (int32_t)(g < 1 ? 1 : g);
 }
 
-int kgb_linear_tc_dw(int device, const float* X, int64_t ldx, const float* G, int64_t ldg, int32_t M, int32_t Kx,
-                     int32_t N, float* partials, int32_t n_parts, kgb_stream_t stream) {
-  KGB_USE_DEVICE(device);
-  KGB_REQUIRE(M >= 1 && Kx > 0 && N > 0, "kgb_linear_tc_dw needs M >= 1 and positive widths");  // rows past M: TMA zero fill
-  KGB_REQUIRE(X && G && partials, "NULL operand");
-  KGB_REQUIRE(Kx <= 256 && N <= 256 && Kx % 4 == 0 && N % 4 == 0, "needs Kx, N <= 256 and multiples of 4");
-  KGB_REQUIRE(aligned16(X) && aligned16(G) && aligned16(partials) && ldx % 4 == 0 && ldg % 4 == 0, "alignment");
-  KGB_REQUIRE(n_parts == kgb_linear_tc_dw_parts(device, M), "n_parts must come from kgb_linear_tc_dw_parts");
-  CUtensorMap mx, mg;
+// dW = X^T [G1 | G2]: G2 (optional) starts at column N1 rounded up to a whole 32-column box of the virtual G tile
+static int dw_impl(int device, const float* X, int64_t ldx, const float* G, int64_t ldg, int32_t N1, const float* G2,
+                   int64_t ldg2, int32_t N2, int32_t M, int32_t Kx, float* partials, int32_t n_parts, cudaStream_t st) {
+  const int n1_boxes = (N1 + 31) / 32;
+  const int N = G2 ? n1_boxes * 32 + N2 : N1;   // columns of the partial (the gap columns are exact zeros)
+  CUtensorMap mx, mg, mg2, mp;
   int rc = make_map(&mx, X, M, Kx, ldx, DW_R, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc != KGB_OK) return rc;
-  rc = make_map(&mg, G, M, N, ldg, DW_R, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  rc = make_map(&mg, G, M, N1, ldg, DW_R, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc != KGB_OK) return rc;
-  CUtensorMap mp;
+  if (G2) rc = make_map(&mg2, G2, M, N2, ldg2, DW_R, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  else mg2 = mg;
+  if (rc != KGB_OK) return rc;
   rc = make_map_partials(&mp, partials, n_parts, Kx, N);
   if (rc != KGB_OK) return rc;
   DwParams p;
@@ -966,13 +972,41 @@ int kgb_linear_tc_dw(int device, const float* X, int64_t ldx, const float* G, in
     static const int chain_nodes = [] { const char* e = getenv("KGB200_DW_CHAIN"); return e ? atoi(e) : 0; }();
     if (chain_nodes >= DW_R) p.chain_blocks = chain_nodes / DW_R;
   }
-  cudaStream_t st = (cudaStream_t)stream;
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  p.g2_box0 = G2 ? n1_boxes : BN / 32;
   const int MT = Kx <= 128 ? 1 : 2;
-#define KGB_DW_CASE(BN_, MT_) if (BN == BN_ && MT == MT_) return dw_launch<BN_, MT_>(device, mx, mg, mp, p, n_parts, st);
+#define KGB_DW_CASE(BN_, MT_) if (BN == BN_ && MT == MT_) return dw_launch<BN_, MT_>(device, mx, mg, mg2, mp, p, n_parts, st);
   KGB_DW_CASE(64, 1) KGB_DW_CASE(64, 2) KGB_DW_CASE(128, 1) KGB_DW_CASE(128, 2) KGB_DW_CASE(256, 1) KGB_DW_CASE(256, 2)
 #undef KGB_DW_CASE
   return KGB_ERR_UNSUPPORTED;
+}
+
+int kgb_linear_tc_dw(int device, const float* X, int64_t ldx, const float* G, int64_t ldg, int32_t M, int32_t Kx,
+                     int32_t N, float* partials, int32_t n_parts, kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(M >= 1 && Kx > 0 && N > 0, "kgb_linear_tc_dw needs M >= 1 and positive widths");  // rows past M: TMA zero fill
+  KGB_REQUIRE(X && G && partials, "NULL operand");
+  KGB_REQUIRE(Kx <= 256 && N <= 256 && Kx % 4 == 0 && N % 4 == 0, "needs Kx, N <= 256 and multiples of 4");
+  KGB_REQUIRE(aligned16(X) && aligned16(G) && aligned16(partials) && ldx % 4 == 0 && ldg % 4 == 0, "alignment");
+  KGB_REQUIRE(n_parts == kgb_linear_tc_dw_parts(device, M), "n_parts must come from kgb_linear_tc_dw_parts");
+  return dw_impl(device, X, ldx, G, ldg, N, nullptr, 0, 0, M, Kx, partials, n_parts, (cudaStream_t)stream);
+}
+
+int32_t kgb_linear_tc_dw2_cols(int32_t N1, int32_t N2) { return (N1 + 31) / 32 * 32 + N2; }
+
+int kgb_linear_tc_dw2(int device, const float* X, int64_t ldx, const float* G1, int64_t ldg1, int32_t N1, const float* G2,
+                      int64_t ldg2, int32_t N2, int32_t M, int32_t Kx, float* partials, int32_t n_parts,
+                      kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(M >= 1 && Kx > 0 && N1 > 0 && N2 > 0, "kgb_linear_tc_dw2 needs M >= 1 and positive widths");
+  KGB_REQUIRE(X && G1 && G2 && partials, "NULL operand");
+  KGB_REQUIRE(Kx <= 256 && Kx % 4 == 0 && N1 % 4 == 0 && N2 % 4 == 0 && kgb_linear_tc_dw2_cols(N1, N2) <= 256,
+              "needs Kx <= 256, widths multiples of 4 and ceil32(N1) + N2 <= 256");
+  KGB_REQUIRE(aligned16(X) && aligned16(G1) && aligned16(G2) && aligned16(partials) && ldx % 4 == 0 && ldg1 % 4 == 0 &&
+                  ldg2 % 4 == 0,
+              "alignment");
+  KGB_REQUIRE(n_parts == kgb_linear_tc_dw_parts(device, M), "n_parts must come from kgb_linear_tc_dw_parts");
+  return dw_impl(device, X, ldx, G1, ldg1, N1, G2, ldg2, N2, M, Kx, partials, n_parts, (cudaStream_t)stream);
 }
 
 int32_t kgb_linear_tc_rows(int32_t N) { return N <= 64 ? 64 : (N <= 128 ? 128 : 256); }

@@ -832,6 +832,32 @@ def _dw_tc(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     return gw
 
 
+def _dw_tc2(x: torch.Tensor, ga: torch.Tensor, gb: torch.Tensor):
+    """(X^T Ga, X^T Gb) in ONE pass over X (kgb_linear_tc_dw2): the two gradient operands sit side by side in the
+    kernel's G tile, so X is loaded and split once.  Shapes outside the single-launch range use two _dw_tc calls."""
+    lib = _lib.load()
+    M, K = int(x.shape[0]), int(x.shape[1])
+    Na, Nb = int(ga.shape[1]), int(gb.shape[1])
+    ok = (M > 0 and 0 < K <= _TC_SLAB and K % 4 == 0 and Na % 4 == 0 and Nb % 4 == 0 and Na > 0 and Nb > 0
+          and int(lib.kgb_linear_tc_dw2_cols(Na, Nb)) <= _TC_SLAB and _gemm_ok(x, ga, gb))
+    if not ok:
+        return _dw_tc(x, ga), _dw_tc(x, gb)
+    dev = x.device
+    ncols = int(lib.kgb_linear_tc_dw2_cols(Na, Nb))
+    n_parts = lib.kgb_linear_tc_dw_parts(dev.index, M)
+    parts = torch.empty((n_parts, K, ncols), dtype=torch.float32, device=dev)
+    _lib.check(lib.kgb_linear_tc_dw2(dev.index, x.data_ptr(), x.stride(0), ga.data_ptr(), ga.stride(0), Na,
+                                     gb.data_ptr(), gb.stride(0), Nb, M, K, parts.data_ptr(), n_parts, _stream(dev)),
+               "kgb_linear_tc_dw2")
+    if n_parts == 1:
+        both = parts[0]
+    else:
+        both = torch.empty((K, ncols), dtype=torch.float32, device=dev)
+        _lib.check(lib.kgb_reduce_parts(dev.index, parts.data_ptr(), n_parts, K * ncols, both.data_ptr(), _stream(dev)),
+                   "kgb_reduce_parts")
+    return both[:, :Na].contiguous(), both[:, ncols - Nb:].contiguous()
+
+
 class _Linear(torch.autograd.Function):
     """out = act(x @ w + addend + bias) on the tensor cores (K8).  Forward, dX = G W^T and dW = X^T G all run the
     hand-written tcgen05 3xTF32 kernels (csrc/tc_gemm.cu) for every shape: ragged widths are zero-padded to multiples
@@ -965,8 +991,11 @@ class _LinearPair(torch.autograd.Function):
             return g.contiguous() if (g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16) else g
 
         ga, gb = prep(ga), prep(gb)
-        g_wa = _dw_tc(x, ga) if ctx.needs_input_grad[1] else None
-        g_wb = _dw_tc(x, gb) if ctx.needs_input_grad[2] else None
+        if ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+            g_wa, g_wb = _dw_tc2(x, ga, gb)                              # X^T [ga | gb]: X is loaded and split once
+        else:
+            g_wa = _dw_tc(x, ga) if ctx.needs_input_grad[1] else None
+            g_wb = _dw_tc(x, gb) if ctx.needs_input_grad[2] else None
         gx = None
         if ctx.needs_input_grad[0]:
             hi, lo = _split_weight_pair(w_a, w_b, transpose=False)      # [ga | gb] @ [w_a^T ; w_b^T] in one pass

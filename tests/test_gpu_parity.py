@@ -878,6 +878,22 @@ def test_linear_tensor_core_gemm(M, K, N):
     close(gad, R, msg="gemm d addend")
 
 
+@pytest.mark.parametrize("M,K,Na,Nb", [(5000, 256, 48, 48), (777, 100, 12, 64), (40000, 64, 128, 96), (300, 256, 200, 100)])
+def test_two_weight_gradients_one_pass(M, K, Na, Nb):
+    """ops._dw_tc2: (X^T Ga, X^T Gb) with X loaded and split once (kgb_linear_tc_dw2) against fp64; shapes beyond one
+    launch (ceil32(Na) + Nb > 256) fall back to two kgb_linear_tc_dw calls."""
+    from keras_geometric_b200 import ops
+    rng = np.random.default_rng(M + K + Na)
+    x = cuda(rng.standard_normal((M, K)).astype(np.float32))
+    ga = cuda(rng.standard_normal((M, Na)).astype(np.float32))
+    gb = cuda(rng.standard_normal((M, Nb)).astype(np.float32))
+    wa, wb = ops._dw_tc2(x, ga, gb)
+    close(wa, (x.double().t() @ ga.double()).float(), msg="dW a")
+    close(wb, (x.double().t() @ gb.double()).float(), msg="dW b")
+    wa2, wb2 = ops._dw_tc2(x, ga, gb)
+    assert torch.equal(wa, wa2) and torch.equal(wb, wb2)          # run-to-run identical
+
+
 @pytest.mark.parametrize("M,K1,K2,N", [(128, 4, 4, 4), (1000, 100, 100, 256), (4097, 256, 256, 256), (3000, 48, 48, 256),
                                        (2000, 32, 64, 64), (777, 36, 8, 132), (77001, 100, 100, 256)])
 def test_linear_two_operands_one_pass(M, K1, K2, N):
