@@ -973,10 +973,17 @@ class _LinearPair(torch.autograd.Function):
     def forward(ctx, x, w_a, w_b):
         x, w_a, w_b = _f32c(x, "x"), _f32c(w_a, "w_a"), _f32c(w_b, "w_b")
         N = int(w_a.shape[1])
-        hi, lo = _split_weight(w_a, transpose=True)
-        a = linear_tc(x, hi, lo, N)
-        hi, lo = _split_weight(w_b, transpose=True)
-        b = linear_tc(x, hi, lo, N)
+        if 2 * N <= _TC_SLAB and N % 4 == 0:
+            # x @ [w_a | w_b] as ONE GEMM: x (the large operand) is loaded and split once; the two results are column
+            # blocks of one [M, 2N] buffer (the gather and the epilogues downstream take any leading dimension)
+            hi, lo = _split_weight(torch.cat([w_a, w_b], dim=1), transpose=True)
+            both = linear_tc(x, hi, lo, 2 * N)
+            a, b = both[:, :N], both[:, N:]
+        else:
+            hi, lo = _split_weight(w_a, transpose=True)
+            a = linear_tc(x, hi, lo, N)
+            hi, lo = _split_weight(w_b, transpose=True)
+            b = linear_tc(x, hi, lo, N)
         ctx.save_for_backward(x, w_a, w_b)
         return a, b
 
