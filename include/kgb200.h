@@ -406,6 +406,12 @@ int kgb_linear_tc_dw(int device, const float* X, int64_t ldx, const float* G, in
  * ceil32(N1) (kgb_linear_tc_dw2_cols(N1, N2) columns in total, <= 256) - X is loaded and split once for both.
  * SAGEConv's lin_neigh / lin_self gradients when the layer aggregates after the transform (sage_conv.py:201-221). */
 int32_t kgb_linear_tc_dw2_cols(int32_t N1, int32_t N2);
+/* The mirror case, two feature operands that share G: partials[p] = [X1 | 0.. | X2]^T G with X2's rows starting at
+ * row ceil32(Kx1) (kgb_linear_tc_dw2_cols(Kx1, Kx2) rows in total, <= 256) - G is loaded and split once.
+ * SAGEConv's dW_neigh = agg^T g and dW_self = x^T g (sage_conv.py:411-433) when both inputs are at most 128 wide. */
+int kgb_linear_tc_dw_x2(int device, const float* X1, int64_t ldx1, int32_t Kx1, const float* X2, int64_t ldx2, int32_t Kx2,
+                        const float* G, int64_t ldg, int32_t N, int32_t M, float* partials, int32_t n_parts,
+                        kgb_stream_t stream);
 int kgb_linear_tc_dw2(int device, const float* X, int64_t ldx, const float* G1, int64_t ldg1, int32_t N1, const float* G2,
                       int64_t ldg2, int32_t N2, int32_t M, int32_t Kx, float* partials, int32_t n_parts,
                       kgb_stream_t stream);

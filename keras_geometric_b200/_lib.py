@@ -140,10 +140,12 @@ SIGNATURES = {
     "kgb_linear_tc_dw": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p,
                                  c_int32, c_void_p]),
     "kgb_linear_tc_dw2_cols": (c_int32, [c_int32, c_int32]),
+    "kgb_linear_tc_dw_x2": (c_int, [c_int, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int64,
+                                    c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "kgb_linear_tc_dw2": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32,
                                   c_int32, c_void_p, c_int32, c_void_p]),
 }
-ABI_VERSION = 203  # must equal kgb_version() of the loaded library (bumped with every ABI change)
+ABI_VERSION = 204  # must equal kgb_version() of the loaded library (bumped with every ABI change)
 
 _lock = threading.Lock()
 _lib = None

@@ -53,7 +53,7 @@ int sm_count(int device) {
 
 extern "C" {
 
-int kgb_version(void) { return 203; /* ABI version: keras_geometric_b200/_lib.py:ABI_VERSION must match */ }
+int kgb_version(void) { return 204; /* ABI version: keras_geometric_b200/_lib.py:ABI_VERSION must match */ }
 
 const char* kgb_last_error(void) { return kgb::g_err; }
 

@@ -572,6 +572,7 @@ struct DwParams {
   int nodes_per_cta;
   int chain_blocks;  // k-blocks (of DW_R nodes) accumulated in TMEM before the sum is promoted to fp32 in memory
   int g2_box0;       // first 32-column box of the G tile that is loaded from the SECOND gradient operand (>= BN/32: none)
+  int x2_box0;       // first 32-feature box of the X tile that is loaded from the SECOND feature operand (>= MT*4: none)
   float* partial;    // [gridDim.x, Kx, N]
 };
 
@@ -597,8 +598,9 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lb
 
 template <int BN, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
-             const __grid_constant__ CUtensorMap map_g2, const __grid_constant__ CUtensorMap map_p, const DwParams p) {
+tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x2,
+             const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_g2,
+             const __grid_constant__ CUtensorMap map_p, const DwParams p) {
   using Cfg = DwCfg<BN, MT>;
   constexpr int S = Cfg::STAGES;
   constexpr int BOX = 32 * DW_R * 4;  // 2 KB per TMA box
@@ -655,7 +657,13 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         uint8_t* base = smem + s * Cfg::STAGE_BYTES;
         const int row = (int)(node0 + (int64_t)kb * DW_R);
 #pragma unroll
-        for (int b = 0; b < MT * 4; ++b) tma_load_2d(base + b * BOX, &map_x, full + s, b * 32, row);
+        for (int b = 0; b < MT * 4; ++b) {
+          // two feature operands that share G ([X1 | X2]^T G, e.g. SAGE's dW_neigh = agg^T g and dW_self = x^T g when
+          // both are at most 128 wide): their feature boxes sit one after the other in ONE X tile, G is loaded and
+          // split once
+          if (b < p.x2_box0) tma_load_2d(base + b * BOX, &map_x, full + s, b * 32, row);
+          else tma_load_2d(base + b * BOX, &map_x2, full + s, (b - p.x2_box0) * 32, row);
+        }
 #pragma unroll
         for (int b = 0; b < BN / 32; ++b) {
           // two gradient operands that share X (dW_a = X^T G1, dW_b = X^T G2): their column boxes sit side by side
@@ -919,8 +927,8 @@ static int make_map_partials(CUtensorMap* m, float* base, int64_t n_parts, int64
 }
 
 template <int BN, int MT>
-static int dw_launch(int device, const CUtensorMap& mx, const CUtensorMap& mg, const CUtensorMap& mg2, const CUtensorMap& mp,
-                     const DwParams& p, int grid,
+static int dw_launch(int device, const CUtensorMap& mx, const CUtensorMap& mx2, const CUtensorMap& mg, const CUtensorMap& mg2,
+                     const CUtensorMap& mp, const DwParams& p, int grid,
                      cudaStream_t st) {
   using Cfg = DwCfg<BN, MT>;
   static bool attr_done[64] = {};
@@ -928,7 +936,7 @@ static int dw_launch(int device, const CUtensorMap& mx, const CUtensorMap& mg, c
     KGB_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done[device] = true;
   }
-  tc_dw_kernel<BN, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mg, mg2, mp, p);
+  tc_dw_kernel<BN, MT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mx2, mg, mg2, mp, p);
   KGB_CHECK_LAUNCH();
   return KGB_OK;
 }
@@ -949,11 +957,17 @@ int32_t kgb_linear_tc_dw_parts(int device, int64_t M) {
 
 // dW = X^T [G1 | G2]: G2 (optional) starts at column N1 rounded up to a whole 32-column box of the virtual G tile
 static int dw_impl(int device, const float* X, int64_t ldx, const float* G, int64_t ldg, int32_t N1, const float* G2,
-                   int64_t ldg2, int32_t N2, int32_t M, int32_t Kx, float* partials, int32_t n_parts, cudaStream_t st) {
+                   int64_t ldg2, int32_t N2, int32_t M, int32_t Kx1, float* partials, int32_t n_parts, cudaStream_t st,
+                   const float* X2 = nullptr, int64_t ldx2 = 0, int32_t Kx2 = 0) {
   const int n1_boxes = (N1 + 31) / 32;
   const int N = G2 ? n1_boxes * 32 + N2 : N1;   // columns of the partial (the gap columns are exact zeros)
-  CUtensorMap mx, mg, mg2, mp;
-  int rc = make_map(&mx, X, M, Kx, ldx, DW_R, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  const int k1_boxes = (Kx1 + 31) / 32;
+  const int Kx = X2 ? k1_boxes * 32 + Kx2 : Kx1;   // rows of the partial (the gap rows are exact zeros)
+  CUtensorMap mx, mx2, mg, mg2, mp;
+  int rc = make_map(&mx, X, M, Kx1, ldx, DW_R, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != KGB_OK) return rc;
+  if (X2) rc = make_map(&mx2, X2, M, Kx2, ldx2, DW_R, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  else mx2 = mx;
   if (rc != KGB_OK) return rc;
   rc = make_map(&mg, G, M, N1, ldg, DW_R, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc != KGB_OK) return rc;
@@ -975,7 +989,8 @@ static int dw_impl(int device, const float* X, int64_t ldx, const float* G, int6
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
   p.g2_box0 = G2 ? n1_boxes : BN / 32;
   const int MT = Kx <= 128 ? 1 : 2;
-#define KGB_DW_CASE(BN_, MT_) if (BN == BN_ && MT == MT_) return dw_launch<BN_, MT_>(device, mx, mg, mg2, mp, p, n_parts, st);
+  p.x2_box0 = X2 ? k1_boxes : MT * 4;
+#define KGB_DW_CASE(BN_, MT_) if (BN == BN_ && MT == MT_) return dw_launch<BN_, MT_>(device, mx, mx2, mg, mg2, mp, p, n_parts, st);
   KGB_DW_CASE(64, 1) KGB_DW_CASE(64, 2) KGB_DW_CASE(128, 1) KGB_DW_CASE(128, 2) KGB_DW_CASE(256, 1) KGB_DW_CASE(256, 2)
 #undef KGB_DW_CASE
   return KGB_ERR_UNSUPPORTED;
@@ -993,6 +1008,22 @@ int kgb_linear_tc_dw(int device, const float* X, int64_t ldx, const float* G, in
 }
 
 int32_t kgb_linear_tc_dw2_cols(int32_t N1, int32_t N2) { return (N1 + 31) / 32 * 32 + N2; }
+
+int kgb_linear_tc_dw_x2(int device, const float* X1, int64_t ldx1, int32_t Kx1, const float* X2, int64_t ldx2, int32_t Kx2,
+                        const float* G, int64_t ldg, int32_t N, int32_t M, float* partials, int32_t n_parts,
+                        kgb_stream_t stream) {
+  KGB_USE_DEVICE(device);
+  KGB_REQUIRE(M >= 1 && Kx1 > 0 && Kx2 > 0 && N > 0, "kgb_linear_tc_dw_x2 needs M >= 1 and positive widths");
+  KGB_REQUIRE(X1 && X2 && G && partials, "NULL operand");
+  KGB_REQUIRE(N <= 256 && N % 4 == 0 && Kx1 % 4 == 0 && Kx2 % 4 == 0 && kgb_linear_tc_dw2_cols(Kx1, Kx2) <= 256,
+              "needs N <= 256, widths multiples of 4 and ceil32(Kx1) + Kx2 <= 256");
+  KGB_REQUIRE(aligned16(X1) && aligned16(X2) && aligned16(G) && aligned16(partials) && ldx1 % 4 == 0 && ldx2 % 4 == 0 &&
+                  ldg % 4 == 0,
+              "alignment");
+  KGB_REQUIRE(n_parts == kgb_linear_tc_dw_parts(device, M), "n_parts must come from kgb_linear_tc_dw_parts");
+  return dw_impl(device, X1, ldx1, G, ldg, N, nullptr, 0, 0, M, Kx1, partials, n_parts, (cudaStream_t)stream, X2, ldx2,
+                 Kx2);
+}
 
 int kgb_linear_tc_dw2(int device, const float* X, int64_t ldx, const float* G1, int64_t ldg1, int32_t N1, const float* G2,
                       int64_t ldg2, int32_t N2, int32_t M, int32_t Kx, float* partials, int32_t n_parts,

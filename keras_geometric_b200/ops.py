@@ -858,6 +858,32 @@ def _dw_tc2(x: torch.Tensor, ga: torch.Tensor, gb: torch.Tensor):
     return both[:, :Na].contiguous(), both[:, ncols - Nb:].contiguous()
 
 
+def _dw_tc_x2(xa: torch.Tensor, xb: torch.Tensor, g: torch.Tensor):
+    """(Xa^T G, Xb^T G) in ONE pass over G (kgb_linear_tc_dw_x2): the two feature operands sit one after the other in
+    the kernel's X tile, so G is loaded and split once.  Needs ceil32(Ka) + Kb <= 256; otherwise two _dw_tc calls."""
+    lib = _lib.load()
+    M, N = int(g.shape[0]), int(g.shape[1])
+    Ka, Kb = int(xa.shape[1]), int(xb.shape[1])
+    ok = (M > 0 and 0 < N <= _TC_SLAB and N % 4 == 0 and Ka % 4 == 0 and Kb % 4 == 0 and Ka > 0 and Kb > 0
+          and int(lib.kgb_linear_tc_dw2_cols(Ka, Kb)) <= _TC_SLAB and _gemm_ok(xa, xb, g))
+    if not ok:
+        return _dw_tc(xa, g), _dw_tc(xb, g)
+    dev = g.device
+    nrows = int(lib.kgb_linear_tc_dw2_cols(Ka, Kb))
+    n_parts = lib.kgb_linear_tc_dw_parts(dev.index, M)
+    parts = torch.empty((n_parts, nrows, N), dtype=torch.float32, device=dev)
+    _lib.check(lib.kgb_linear_tc_dw_x2(dev.index, xa.data_ptr(), xa.stride(0), Ka, xb.data_ptr(), xb.stride(0), Kb,
+                                       g.data_ptr(), g.stride(0), N, M, parts.data_ptr(), n_parts, _stream(dev)),
+               "kgb_linear_tc_dw_x2")
+    if n_parts == 1:
+        both = parts[0]
+    else:
+        both = torch.empty((nrows, N), dtype=torch.float32, device=dev)
+        _lib.check(lib.kgb_reduce_parts(dev.index, parts.data_ptr(), n_parts, nrows * N, both.data_ptr(), _stream(dev)),
+                   "kgb_reduce_parts")
+    return both[:Ka], both[nrows - Kb:]
+
+
 class _Linear(torch.autograd.Function):
     """out = act(x @ w + addend + bias) on the tensor cores (K8).  Forward, dX = G W^T and dW = X^T G all run the
     hand-written tcgen05 3xTF32 kernels (csrc/tc_gemm.cu) for every shape: ragged widths are zero-padded to multiples
@@ -946,8 +972,11 @@ class _SageLayer(torch.autograd.Function):
         if g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
             g = g.contiguous()
         K = int(x.shape[1])
-        g_wn = _dw_tc(agg, g) if ctx.needs_input_grad[1] else None
-        g_ws = _dw_tc(x, g) if ctx.needs_input_grad[2] else None
+        if ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+            g_wn, g_ws = _dw_tc_x2(agg, x, g)      # [agg | x]^T g: one pass over g when both inputs are narrow
+        else:
+            g_wn = _dw_tc(agg, g) if ctx.needs_input_grad[1] else None
+            g_ws = _dw_tc(x, g) if ctx.needs_input_grad[2] else None
         gx = None
         if ctx.needs_input_grad[0]:
             hi, lo = _split_weight(w_neigh, transpose=False)

@@ -894,6 +894,22 @@ def test_two_weight_gradients_one_pass(M, K, Na, Nb):
     assert torch.equal(wa, wa2) and torch.equal(wb, wb2)          # run-to-run identical
 
 
+@pytest.mark.parametrize("M,Ka,Kb,N", [(5000, 100, 100, 256), (777, 12, 64, 48), (40000, 128, 128, 64), (300, 200, 100, 32)])
+def test_two_feature_operands_one_weight_gradient_pass(M, Ka, Kb, N):
+    """ops._dw_tc_x2: (Xa^T G, Xb^T G) with G loaded and split once (kgb_linear_tc_dw_x2) against fp64; shapes beyond
+    one launch (ceil32(Ka) + Kb > 256) fall back to two kgb_linear_tc_dw calls."""
+    from keras_geometric_b200 import ops
+    rng = np.random.default_rng(M + Ka + N)
+    xa = cuda(rng.standard_normal((M, Ka)).astype(np.float32))
+    xb = cuda(rng.standard_normal((M, Kb)).astype(np.float32))
+    g = cuda(rng.standard_normal((M, N)).astype(np.float32))
+    wa, wb = ops._dw_tc_x2(xa, xb, g)
+    close(wa, (xa.double().t() @ g.double()).float(), msg="dW a")
+    close(wb, (xb.double().t() @ g.double()).float(), msg="dW b")
+    wa2, wb2 = ops._dw_tc_x2(xa, xb, g)
+    assert torch.equal(wa, wa2) and torch.equal(wb, wb2)          # run-to-run identical
+
+
 @pytest.mark.parametrize("M,K1,K2,N", [(128, 4, 4, 4), (1000, 100, 100, 256), (4097, 256, 256, 256), (3000, 48, 48, 256),
                                        (2000, 32, 64, 64), (777, 36, 8, 132), (77001, 100, 100, 256)])
 def test_linear_two_operands_one_pass(M, K1, K2, N):
