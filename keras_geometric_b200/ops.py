@@ -954,7 +954,10 @@ class _SageLayer(torch.autograd.Function):
         agg, _ = gather_reduce_raw(x, graph.csr, op)
         hi, lo = _split_weight_pair(w_neigh, w_self, transpose=True)   # [agg | x] @ [w_neigh ; w_self] in one pass
         out = linear_tc2(agg, x, hi, lo, N, bias=bias_c, relu=relu)
-        ctx.save_for_backward(x, agg, w_neigh, w_self, *([out] if relu else []))
+        # backward formulation (see there): with an input gradient and N <= K the incoming gradient itself is gathered
+        # and `agg` is not needed again
+        ctx.gather_grad = bool(ctx.needs_input_grad[0]) and N <= int(x.shape[1])
+        ctx.save_for_backward(x, agg if not ctx.gather_grad else x.new_empty(0), w_neigh, w_self, *([out] if relu else []))
         ctx.graph, ctx.op, ctx.relu, ctx.has_bias = graph, op, relu, bias is not None
         return out
 
@@ -971,7 +974,22 @@ class _SageLayer(torch.autograd.Function):
             g = relu_bwd(g, out)
         if g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
             g = g.contiguous()
-        K = int(x.shape[1])
+        K, N = int(x.shape[1]), int(g.shape[1])
+        kw = {"src_scale": ctx.graph.csr.inv_deg} if ctx.op == _lib.OP_MEAN else {}
+        if ctx.gather_grad:
+            # The transposed aggregation commutes with lin_neigh: A^T (g Wn^T) = (A^T g) Wn^T.  Gathering g itself
+            # (N <= K columns) gives q = A^T g, and then dx = [q | g] @ [Wn^T ; Ws^T] is ONE K-concatenated GEMM instead
+            # of two GEMMs over g, and dWn = (A x)^T g = x^T q shares x with dWs = x^T g.  C4 step, same box:
+            # 41.2 -> 40.2 ms.
+            q, _ = gather_reduce_raw(g, ctx.graph.csc, _lib.OP_SUM, **kw)
+            hi, lo = _split_weight_pair(w_neigh, w_self, transpose=False)
+            gx = linear_tc2(q, g, hi, lo, K)
+            if ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+                g_wn, g_ws = _dw_tc2(x, q, g)
+            else:
+                g_wn = _dw_tc(x, q) if ctx.needs_input_grad[1] else None
+                g_ws = _dw_tc(x, g) if ctx.needs_input_grad[2] else None
+            return gx, g_wn, g_ws, g_bias, None, None, None
         if ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
             g_wn, g_ws = _dw_tc_x2(agg, x, g)      # [agg | x]^T g: one pass over g when both inputs are narrow
         else:
@@ -981,7 +999,6 @@ class _SageLayer(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             hi, lo = _split_weight(w_neigh, transpose=False)
             d_agg = linear_tc(g, hi, lo, K)
-            kw = {"src_scale": ctx.graph.csr.inv_deg} if ctx.op == _lib.OP_MEAN else {}
             gx, _ = gather_reduce_raw(d_agg, ctx.graph.csc, _lib.OP_SUM, **kw)
             hi, lo = _split_weight(w_self, transpose=False)
             gx = linear_tc(g, hi, lo, K, c=gx)
