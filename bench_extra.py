@@ -257,6 +257,7 @@ def parity_check(world, rank, dev, n=50_000, e=600_000, fin=32, tol=1e-5):
            True: PartitionedGraph(src, dst, n, rank, world, bounds=bounds, n_loops_local=True)}
     cases = [("sage_mean_wide", lambda: SAGEConv(64, aggregator="mean", activation=None), False),
              ("sage_mean_narrow", lambda: SAGEConv(12, aggregator="mean", activation=None), False),
+             ("sage_mean_square_relu", lambda: SAGEConv(fin, aggregator="mean", activation="relu"), False),
              ("sage_sum_relu", lambda: SAGEConv(64, aggregator="sum", activation="relu"), False),
              ("sage_max", lambda: SAGEConv(64, aggregator="max", activation=None), False),
              ("gcn", lambda: GCNConv(16), True),

@@ -1150,9 +1150,12 @@ class _SagePartitioned(torch.autograd.Function):
             back.record_stream(cur)
             return pg.land_into(back, acc)
 
-        if ctx.reorder:
+        if ctx.reorder or (need_x and int(g.shape[1]) <= K):
             # out = act(S A_l z + S A_h halo(z) + x Ws + b), z = x Wn:  dz = A^T (S g) needs the exchange even when x
-            # itself needs no gradient (it feeds dWn)
+            # itself needs no gradient (it feeds dWn).
+            # The aggregate-first layer out = act((S A x) Wn + x Ws + b) has the SAME backward: A^T S (g Wn^T) =
+            # (A^T S g) Wn^T and dWn = (S A x)^T g = x^T (A^T S g).  Taking it when the gradient is not wider than x means
+            # the halo gradients leave at once (no g Wn^T GEMM in front of the push) and dx is one K-concatenated GEMM.
             back = send_back(g)
             g_ws = _dw_tc(x, g) if ctx.needs_input_grad[2] else None
             dz, _ = gather_reduce_raw(g, g_l.csc, _lib.OP_SUM, src_scale=scale)
