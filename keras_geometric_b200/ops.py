@@ -1173,8 +1173,11 @@ class _SagePartitioned(torch.autograd.Function):
             hi, lo = _split_weight(w_neigh, transpose=False)
             d_agg = linear_tc(g, hi, lo, K)
             back = send_back(d_agg)
-        g_wn = _dw_tc(agg, g) if ctx.needs_input_grad[1] else None
-        g_ws = _dw_tc(x, g) if ctx.needs_input_grad[2] else None
+        if ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+            g_wn, g_ws = _dw_tc_x2(agg, x, g)      # [agg | x]^T g: one pass over g when both inputs are narrow
+        else:
+            g_wn = _dw_tc(agg, g) if ctx.needs_input_grad[1] else None
+            g_ws = _dw_tc(x, g) if ctx.needs_input_grad[2] else None
         if need_x:
             gx, _ = gather_reduce_raw(d_agg, g_l.csc, _lib.OP_SUM, src_scale=scale)
             hi, lo = _split_weight(w_self, transpose=False)
