@@ -249,3 +249,26 @@ def test_scripts_parse_and_partition_bounds():
             deg = torch.bincount(dst, minlength=n) + bench_dist.NODE_WEIGHT
             costs = [float(deg[b[i]:b[i + 1]].sum()) for i in range(world)]
             assert max(costs) <= 1.5 * (sum(costs) / world)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle port on a bounded sample) prints ONE JSON line with the keys the
+    measurement contract names; under torchrun every rank but 0 exits silently."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--cpu-sample-div", "2048"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "GTEPS" and d["higher_is_better"] is True
+    assert d["metric"] == "aggregated edges/sec per layer fwd+bwd" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    quiet = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
